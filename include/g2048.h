@@ -1,0 +1,212 @@
+/*
+ * g2048.h — C ABI of the B200-native batched 2048 transition library (libg2048.so).
+ *
+ * This is the drop-in boundary for the game-transition hot path of
+ * schalappe/simulate_2048.  The reference has no FFI of its own: its boundary is the
+ * Python function surface of `twentyfortyeight/core/{gameboard,gamemove}.py`,
+ * `twentyfortyeight/envs/twentyfortyeight.py` and `reinforce/game/{core,env}.py`.  Each
+ * entry point below names the reference function(s) it replaces (paths relative to the
+ * reference repository root); INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *   - Plain C, caller-owned buffers, no allocation on the device-pointer entry points,
+ *     no exceptions: every function returns 0 (G2048_OK) or a negative G2048_E* code.
+ *   - Pointers are DEVICE pointers unless the function name ends in `_host`.
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).
+ *     All device entry points are asynchronous with respect to the host.
+ *   - Re-entrant across streams and devices.  The only library state is a per-device,
+ *     read-only row table that is built once on first use (or by g2048_init).
+ *
+ * Board format (`uint64_t`, one board per word)
+ *   cell (r,c), flat index i = 4r + c (row-major, the order of `argwhere`/`flatten` in
+ *   gameboard.py:154,275 and core.py:206-213); nibble i (bits [4i,4i+4)) holds
+ *   log2(tile), 0 = empty.  Row r is bits [16r,16r+16), column 0 is the low nibble.
+ *   Tiles above 32768 (exponent > 15) are not representable: a 15+15 merge raises
+ *   G2048_FLAG_OVERFLOW for that env (the stored nibble wraps to 0, the reward is exact).
+ *
+ * Actions: 0 left, 1 up, 2 right, 3 down (twentyfortyeight.py:19, gameboard.py:114,
+ *   core.py:142); only the low two bits are used (rot90(k) is modulo 4).
+ *
+ * Spawn byte (injected-spawn mode), one per env:
+ *   bit 7 clear: low nibble = rank of the target cell among the empty cells of the
+ *                afterstate in row-major order (what both engines reduce to:
+ *                `available_cells[chosen]` gameboard.py:284-287, `pos_idx` core.py:210-213);
+ *   bit 7 set  : low nibble = absolute flat cell index;
+ *   bit 4      : spawned tile is a 4 (else a 2).
+ *   A rank >= number of empties, or an occupied absolute cell, spawns nothing and raises
+ *   G2048_FLAG_BADSPAWN.
+ *
+ * Philox mode (spawns == NULL): Philox4x32-10, key = (seed_lo, seed_hi) or the per-env
+ *   key, counter = (env_lo, env_hi, step, tag) with env the GLOBAL env id
+ *   (env_offset + i) — results do not depend on grid size, GPU count or fusion.
+ *   word0 -> rank = mulhi(word0, n_empty); word1 < 0x1999999A -> tile 4 (p = 0.1);
+ *   word2 -> rollout policy: mulhi(word2, n_legal)-th legal action.  Tags:
+ *   0 = play step, 1 / 2 = first / second reset tile.
+ *
+ * Flags byte (per env):
+ */
+#ifndef G2048_H
+#define G2048_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G2048_ABI_VERSION 1
+
+#define G2048_FLAG_LEFT 0x01u     /* legal-action mask of the NEW board, bit a = action a */
+#define G2048_FLAG_UP 0x02u
+#define G2048_FLAG_RIGHT 0x04u
+#define G2048_FLAG_DOWN 0x08u
+#define G2048_FLAG_LEGAL_MASK 0x0Fu
+#define G2048_FLAG_DONE 0x10u     /* no legal action on the new board (core.py:305-321) */
+#define G2048_FLAG_MOVED 0x20u    /* the action changed the board (core.py:258) */
+#define G2048_FLAG_OVERFLOW 0x40u /* a 32768+32768 merge happened (not representable) */
+#define G2048_FLAG_BADSPAWN 0x80u /* injected spawn byte was invalid; nothing spawned */
+
+#define G2048_OK 0
+#define G2048_EINVAL (-1)   /* NULL/misaligned pointer, bad enum */
+#define G2048_ECUDA (-2)    /* a CUDA runtime call failed; see g2048_last_cuda_error */
+#define G2048_ENODEV (-3)   /* no CUDA device / not an sm_100 device */
+#define G2048_ERANGE (-4)   /* tile value not representable (pack) */
+
+#define G2048_PHILOX_TAG_STEP 0u
+#define G2048_PHILOX_TAG_RESET0 1u
+#define G2048_PHILOX_TAG_RESET1 2u
+#define G2048_PHILOX_FOUR_THRESHOLD 0x1999999Au /* word1 < threshold -> spawn a 4 */
+
+/* children layout for g2048_expand */
+#define G2048_CHILDREN_NONE 0
+#define G2048_CHILDREN_DENSE 1   /* children[((i*4 + a)*16 + k)*2 + v], k-th empty, v: 0 -> 2, 1 -> 4 */
+#define G2048_CHILDREN_COMPACT 2 /* children[child_offsets[i] + ...], action-major, cell-major, value-minor */
+
+/* which row-move implementation the step kernel uses (for the ncu comparison) */
+#define G2048_IMPL_AUTO 0
+#define G2048_IMPL_LUT 1      /* 57344-entry row table staged in shared memory by TMA bulk copy */
+#define G2048_IMPL_REGISTER 2 /* pure register arithmetic, no table */
+
+int g2048_abi_version(void);
+const char* g2048_error_string(int code);
+const char* g2048_last_cuda_error(void); /* thread-local text of the last CUDA failure */
+
+/* Build the per-device row table now (otherwise done lazily). device < 0 = current. */
+int g2048_init(int device);
+/* Select the row-move implementation used by g2048_step/g2048_env_step (process-wide). */
+int g2048_set_impl(int impl);
+
+/*
+ * Raw transition: replaces gameboard.py:291 next_state (+ is_done :328, gamemove.py:45
+ * legal_actions_mask on the result) and core.py:234 next_state / :275 / :305.
+ *   boards_in[n], actions[n], spawns[n] or NULL (Philox), step_ctr[n] or NULL (then every
+ *   env uses step_base), env_keys[n] or NULL (per-env 64-bit Philox key replacing seed),
+ *   done_in[n] or NULL: a non-zero entry passes the env through (env.py:103-104):
+ *   board unchanged, reward 0, DONE set.
+ *   Outputs: boards_out[n] (may alias boards_in), rewards[n] (sum of merged tile values,
+ *   0 for an illegal move), flags[n].
+ */
+int g2048_step(const uint64_t* boards_in, const uint8_t* actions, const uint8_t* spawns,
+               uint64_t seed, uint64_t env_offset, const uint32_t* step_ctr, uint32_t step_base,
+               const uint64_t* env_keys, const uint8_t* done_in, uint64_t* boards_out,
+               int32_t* rewards, uint8_t* flags, size_t n, void* stream);
+
+/*
+ * Stateful env step on a GameState (env.py:33 GameState, :79 step, :211 batched_step):
+ * updates boards / step_count / done / total_reward in place; step_count increments even
+ * for an illegal action (env.py:116); done envs pass through with reward 0.
+ *   Philox counter step = step_count before the increment.
+ *   Optional outputs (NULL to skip): rewards f32[n], flags u8[n], obs f32[n*16]
+ *   (core.py:346 encode_observation of the new board), max_tile i32[n] (core.py:427,
+ *   the tile VALUE).
+ */
+int g2048_env_step(uint64_t* boards, int32_t* step_count, uint8_t* done, float* total_reward,
+                   const uint8_t* actions, const uint8_t* spawns, uint64_t seed,
+                   uint64_t env_offset, const uint64_t* env_keys, float* rewards,
+                   uint8_t* flags, float* obs, int32_t* max_tile, size_t n, void* stream);
+
+/* Legal mask + done of boards (gamemove.py:45, core.py:275/:305); flags has the LEGAL/DONE bits. */
+int g2048_mask(const uint64_t* boards, uint8_t* flags, size_t n, void* stream);
+
+/*
+ * MCTS leaf expansion (gameboard.py:105 latent_state for the four actions, :132
+ * after_state for every legal afterstate, gamemove.py:45):
+ *   after[n*4] afterstates, rewards[n*4], mask[n] (LEGAL|DONE bits, bit 6 = any overflow),
+ *   num_empty[n*4] (empties of each afterstate; the spawn probability of a child is
+ *   {0.9, 0.1}/num_empty, gameboard.py:166), child_count[n*4] (2*num_empty for a legal
+ *   action with empties, 1 for a legal action whose afterstate is full, 0 for an illegal one),
+ *   children per `child_layout`; child_offsets[n] (exclusive prefix sum over envs of the
+ *   per-env total child_count) is required for G2048_CHILDREN_COMPACT.
+ *   Any output pointer may be NULL to skip it.
+ */
+int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* rewards, uint8_t* mask,
+                 uint8_t* num_empty, uint8_t* child_count, uint64_t* children,
+                 const int64_t* child_offsets, int child_layout, size_t n, void* stream);
+
+/* Chance children of given boards (gameboard.py:132 after_state, :174 after_state_lazy):
+ * children[n*32] dense (slot 2k + v = k-th empty cell in row-major order, v: 0 -> tile 2,
+ * 1 -> tile 4; a full board yields children[0] = the board itself), num_empty[n], and
+ * empty_cells[n] (optional): 16-bit mask, bit c = flat cell c is empty. */
+int g2048_after_state(const uint64_t* boards, uint64_t* children, uint8_t* num_empty,
+                      uint16_t* empty_cells, size_t n, void* stream);
+
+/* New games: two spawns on the empty board (core.py:324 create_initial_board,
+ * twentyfortyeight.py:84 reset).  spawns[n*2] injected or NULL for Philox tags 1, 2. */
+int g2048_reset(uint64_t seed, uint64_t env_offset, const uint64_t* env_keys,
+                const uint8_t* spawns, uint64_t* boards_out, size_t n, void* stream);
+
+/* One tile on each board (gameboard.py:247 fill_cells with number_tile = 1, core.py:173
+ * fill_cells): a full board is returned unchanged.  spawns[n] injected, or NULL for Philox with
+ * counter (env, step_base, tag).  flags (optional) receives G2048_FLAG_BADSPAWN per env. */
+int g2048_spawn(uint64_t* boards_io, const uint8_t* spawns, uint64_t seed, uint64_t env_offset,
+                const uint64_t* env_keys, uint32_t step_base, uint32_t tag, uint8_t* flags,
+                size_t n, void* stream);
+
+/* Observation (core.py:346: exponent/16 as f32[16]) and max tile exponent (core.py:427). */
+int g2048_observe(const uint64_t* boards, float* obs, uint8_t* max_exp, size_t n, void* stream);
+
+/*
+ * Fused random-policy rollout to termination, board in registers:
+ *   policy = uniform over legal actions (Philox word2), spawns from Philox words 0/1.
+ *   boards_io[n]: start boards if `from_reset` == 0 (updated to the final boards), else
+ *   output only (games start from g2048_reset's Philox boards).
+ *   score_out i64[n] (sum of rewards), steps_out i32[n], maxexp_out u8[n] — any may be NULL.
+ *   stats_out u64[G2048_STATS_WORDS] (device, accumulated atomically; zero it first):
+ *     [0] episodes, [1] total steps, [2] total score, [3] max score, [4] max steps,
+ *     [5] episodes stopped by max_steps, [6] overflow count, [7] reserved,
+ *     [8 + e] episodes whose max tile exponent is e (e = 0..15).
+ *   trace (optional, u8[n * trace_stride]): byte per step = action | spawn_cell << 2 |
+ *     spawn_is_four << 6 | 0x80, zero-terminated — for replay through the reference.
+ */
+#define G2048_STATS_WORDS 24
+int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint32_t max_steps,
+                  int from_reset, uint64_t* boards_io, int64_t* score_out, int32_t* steps_out,
+                  uint8_t* maxexp_out, uint64_t* stats_out, uint8_t* trace,
+                  uint32_t trace_stride, void* stream);
+
+/* int32 tile values [n*16] <-> packed boards.  `status` (device int32, optional) is set
+ * to G2048_ERANGE if any value is not 0 or a power of two in [2, 32768]. */
+int g2048_pack(const int32_t* tiles, uint64_t* boards, int32_t* status, size_t n, void* stream);
+int g2048_unpack(const uint64_t* boards, int32_t* tiles, size_t n, void* stream);
+
+/* Copy the device row table (65536 x {result u16, reward u32, moved u8}) to HOST buffers. */
+int g2048_row_table_host(uint16_t* result, uint32_t* reward, uint8_t* moved);
+
+/*
+ * HOST-buffer transition (the reference-facing call: host ndarray in, host ndarray out).
+ * Same semantics as g2048_step; pointers are host memory (pinned memory from
+ * g2048_host_alloc gives full PCIe bandwidth, pageable memory works).  The batch is cut
+ * into chunks that move H2D, compute and move D2H on separate streams so both PCIe
+ * directions and the kernel overlap.  Synchronous: returns when outputs are in place.
+ */
+int g2048_step_host(const uint64_t* boards_in, const uint8_t* actions, const uint8_t* spawns,
+                    uint64_t seed, uint64_t env_offset, uint32_t step_base,
+                    uint64_t* boards_out, int32_t* rewards, uint8_t* flags, size_t n);
+int g2048_host_alloc(void** ptr, size_t bytes); /* pinned host memory */
+int g2048_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G2048_H */

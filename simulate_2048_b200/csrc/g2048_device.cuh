@@ -1,0 +1,296 @@
+// g2048_device.cuh — device primitives for packed 2048 boards (sm_100a).
+//
+// A board is one u64: nibble i = log2(tile) of flat cell i = 4r + c (include/g2048.h).
+// The GPU is a 32-bit machine, so every primitive works on the two halves
+//   lo = rows 0,1   hi = rows 2,3
+// and is written so that ptxas emits LOP3 / SHF / PRMT / IMAD and nothing wider.
+//
+// Reference semantics implemented here (paths relative to the reference repo):
+//   row move        twentyfortyeight/core/gameboard.py:23-69 merge_column (+ :72-102 padding),
+//                   reinforce/game/core.py:43-101 merge_row
+//   direction map   gameboard.py:105-129 / core.py:129-170 (rot90(k=action) + slide left)
+//   legal mask      twentyfortyeight/core/gamemove.py:45-83, core.py:275-302
+//   spawn           gameboard.py:247-288 fill_cells, core.py:173-231 (rank-th empty, row-major)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/g2048.h"
+
+namespace g2048 {
+
+typedef unsigned int u32;
+typedef unsigned long long u64;
+
+// ---------------------------------------------------------------------------------------------
+// Row table entry (u32): bits 0..15 = row after a left move, bits 16..31 = (merge score) >> 2.
+// Score of a row is a multiple of 4 and at most 131072, so score >> 2 fits 16 bits exactly.
+// The shared-memory copy holds rows [0, kSmemRows): every row whose column-3 tile is <= 8192.
+// Rows outside it (a 16384 / 32768 tile in the last column of the oriented board) take the
+// exact slow path through the full table in global memory.
+// ---------------------------------------------------------------------------------------------
+constexpr u32 kRows = 65536u;
+constexpr u32 kSmemRows = 0xE000u;             // 57344 entries = 229376 bytes
+constexpr u32 kSmemTableBytes = kSmemRows * 4u;
+
+struct Board {
+    u32 lo, hi;
+};
+
+__device__ __forceinline__ Board split(u64 b) { return Board{(u32)b, (u32)(b >> 32)}; }
+__device__ __forceinline__ u64 join(Board b) { return ((u64)b.hi << 32) | b.lo; }
+
+// Transpose the 4x4 nibble matrix: 2x2 nibble blocks inside each half (xor-swap), then the
+// 2x2 block of bytes across the halves (two PRMT).
+__device__ __forceinline__ Board transpose(Board b) {
+    u32 t = (b.lo ^ (b.lo >> 12)) & 0x0000F0F0u;
+    u32 lo = b.lo ^ t ^ (t << 12);
+    t = (b.hi ^ (b.hi >> 12)) & 0x0000F0F0u;
+    u32 hi = b.hi ^ t ^ (t << 12);
+    return Board{__byte_perm(lo, hi, 0x6240), __byte_perm(lo, hi, 0x7351)};
+}
+
+// Reverse the four nibbles of every row (mirror left <-> right).
+__device__ __forceinline__ u32 reverse_rows(u32 h) {
+    h = ((h & 0x0F0F0F0Fu) << 4) | ((h >> 4) & 0x0F0F0F0Fu);
+    return __byte_perm(h, 0u, 0x2301);
+}
+__device__ __forceinline__ Board reverse_rows(Board b) {
+    return Board{reverse_rows(b.lo), reverse_rows(b.hi)};
+}
+
+// bit 3 of every nibble = (nibble != 0); exact per nibble, no carries cross nibbles.
+__device__ __forceinline__ u32 nz8(u32 v) {
+    return (((v & 0x77777777u) + 0x77777777u) | v) & 0x88888888u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact scalar row move, used to build the table and on the rare slow path.
+// Returns the entry format above; *overflow is set when a 15+15 merge happened.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline u32 row_left_exact(u32 row, u32* score_out, bool* overflow) {
+    u32 cells[4];
+    int k = 0;
+    for (int j = 0; j < 4; ++j) {
+        u32 e = (row >> (4 * j)) & 0xFu;
+        if (e) cells[k++] = e;  // drop empties (gameboard.py:46)
+    }
+    u32 out = 0, score = 0;
+    bool ovf = false;
+    int m = 0, i = 0;
+    while (i < k) {  // greedy left-to-right pairing, each tile merges once (gameboard.py:56-64)
+        if (i + 1 < k && cells[i] == cells[i + 1]) {
+            u32 e = cells[i] + 1;
+            score += 1u << e;
+            if (e > 15u) ovf = true;
+            out |= (e & 0xFu) << (4 * m);
+            i += 2;
+        } else {
+            out |= cells[i] << (4 * m);
+            i += 1;
+        }
+        ++m;
+    }
+    if (score_out) *score_out = score;
+    if (overflow) *overflow = ovf;
+    return out;
+}
+
+__host__ __device__ inline u32 make_entry(u32 row) {
+    u32 score;
+    bool ovf;
+    u32 res = row_left_exact(row, &score, &ovf);
+    return res | ((score >> 2) << 16);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Row-table accessors.  `SmemTable` reads the staged copy (one LDS per row); `GlobalTable`
+// gathers from the full table through L1/L2.
+// ---------------------------------------------------------------------------------------------
+struct GlobalTable {
+    const u32* __restrict__ tab;
+    __device__ __forceinline__ u32 operator()(u32 row) const { return __ldg(tab + row); }
+    // every row is in range
+    __device__ __forceinline__ bool covers(Board) const { return true; }
+};
+
+struct SmemTable {
+    const u32* smem;              // kSmemRows entries
+    const u32* __restrict__ tab;  // full table (slow path)
+    __device__ __forceinline__ u32 operator()(u32 row) const { return smem[row]; }
+    // true when all four rows index inside the staged window
+    __device__ __forceinline__ bool covers(Board b) const {
+        return (b.lo < 0xE0000000u) & (b.hi < 0xE0000000u) & ((b.lo << 16) < 0xE0000000u) &
+               ((b.hi << 16) < 0xE0000000u);
+    }
+};
+
+struct MoveResult {
+    Board after;
+    u32 score;      // sum of merged tile values
+    bool overflow;  // exact
+};
+
+// Exact out-of-line move for boards with a 16384 / 32768 tile in the oriented last column or a
+// 15+15 merge.  Kept out of line so the hot path stays small.
+__device__ __noinline__ MoveResult move_left_slow(Board x) {
+    MoveResult r;
+    u32 res[4];
+    r.score = 0;
+    r.overflow = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const u32 h = (i < 2) ? x.lo : x.hi;
+        const u32 row = (i & 1) ? (h >> 16) : (h & 0xFFFFu);
+        u32 s;
+        bool o;
+        res[i] = row_left_exact(row, &s, &o);
+        r.score += s;
+        r.overflow |= o;
+    }
+    r.after.lo = res[0] | (res[1] << 16);
+    r.after.hi = res[2] | (res[3] << 16);
+    return r;
+}
+
+// Left move of all four rows of an oriented board.
+template <class Table>
+__device__ __forceinline__ MoveResult move_left(Board x, const Table& T) {
+    MoveResult r;
+    if (T.covers(x)) {
+        u32 e0 = T(x.lo & 0xFFFFu), e1 = T(x.lo >> 16), e2 = T(x.hi & 0xFFFFu), e3 = T(x.hi >> 16);
+        r.after.lo = __byte_perm(e0, e1, 0x5410);
+        r.after.hi = __byte_perm(e2, e3, 0x5410);
+        r.score = ((e0 >> 16) + (e1 >> 16) + (e2 >> 16) + (e3 >> 16)) << 2;
+        r.overflow = false;
+        if (r.score < 65536u) return r;  // a 15+15 merge scores 65536 on its own
+    }
+    // slow path: tiles >= 16384 present; exact arithmetic, never taken in ordinary play
+    return move_left_slow(x);
+}
+
+// Afterstate of `b` under `action` (0 left, 1 up, 2 right, 3 down): orient so that the move is
+// a left move (transpose for vertical, mirror for right/down), move, undo.
+template <class Table>
+__device__ __forceinline__ MoveResult move_action(Board b, u32 action, const Table& T) {
+    const bool vertical = action & 1u, mirrored = action & 2u;
+    Board x = b;
+    if (vertical) x = transpose(x);
+    if (mirrored) x = reverse_rows(x);
+    MoveResult r = move_left(x, T);
+    if (mirrored) r.after = reverse_rows(r.after);
+    if (vertical) r.after = transpose(r.after);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Legal-action mask, pure register arithmetic (gamemove.py:45-83): bit a = action a is legal.
+//   merge possible : a non-empty cell equals its right / lower neighbour
+//   slide possible : an empty cell has a non-empty neighbour on the far side
+// All tests run nibble-parallel on the bit-3 indicators produced by nz8().
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 legal_mask(Board b, u32 nlo, u32 nhi) {
+    // horizontal: neighbour j+1 aligned on j; column 3 is masked out by M
+    const u32 elo = nz8(b.lo ^ (b.lo >> 4)), ehi = nz8(b.hi ^ (b.hi >> 4));  // cells differ
+    const u32 slo = nlo >> 4, shi = nhi >> 4;                                // neighbour non-empty
+    const u32 M = 0x08880888u;
+    const u32 L = (((nlo & ~elo) | (~nlo & slo)) | ((nhi & ~ehi) | (~nhi & shi))) & M;
+    const u32 R = (((nlo & ~elo) | (nlo & ~slo)) | ((nhi & ~ehi) | (nhi & ~shi))) & M;
+    // vertical: row r+1 aligned on row r = (hi:lo) >> 16; row 3 has no lower neighbour
+    const u32 vlo = __byte_perm(b.lo, b.hi, 0x5432), vhi = b.hi >> 16;
+    const u32 flo = nz8(b.lo ^ vlo), fhi = nz8(b.hi ^ vhi);
+    const u32 tlo = __byte_perm(nlo, nhi, 0x5432), thi = nhi >> 16;
+    const u32 U = ((nlo & ~flo) | (~nlo & tlo)) | (((nhi & ~fhi) | (~nhi & thi)) & 0x0000FFFFu);
+    const u32 D = ((nlo & ~flo) | (nlo & ~tlo)) | (((nhi & ~fhi) | (nhi & ~thi)) & 0x0000FFFFu);
+    return (L != 0u ? 1u : 0u) | (U != 0u ? 2u : 0u) | (R != 0u ? 4u : 0u) | (D != 0u ? 8u : 0u);
+}
+__device__ __forceinline__ u32 legal_mask(Board b) { return legal_mask(b, nz8(b.lo), nz8(b.hi)); }
+
+// flags byte of a board: legal mask + DONE when nothing is legal (core.py:305-321)
+__device__ __forceinline__ u32 board_flags(u32 mask) {
+    return mask | (mask == 0u ? G2048_FLAG_DONE : 0u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Spawn: place a tile of exponent `exp` (1 or 2) on the rank-th empty cell in row-major order.
+// `zlo/zhi` carry bit 0 of every empty nibble.  Within a half, a multiply by 0x11111111 turns
+// the indicators into inclusive prefix counts (<= 8, no carry), adding (7 - r) per nibble sets
+// bit 3 exactly where the count exceeds r, and the lowest such nibble is the target.
+// Returns false (board untouched) when rank >= number of empties.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void empties(Board b, u32& zlo, u32& zhi) {
+    zlo = (~nz8(b.lo) >> 3) & 0x11111111u;
+    zhi = (~nz8(b.hi) >> 3) & 0x11111111u;
+}
+
+__device__ __forceinline__ bool spawn_rank(Board& b, u32 zlo, u32 zhi, u32 rank, u32 exp) {
+    const u32 clo = __popc(zlo), n = clo + __popc(zhi);
+    if (rank >= n) return false;
+    const bool in_hi = rank >= clo;
+    const u32 z = in_hi ? zhi : zlo;
+    const u32 r = in_hi ? rank - clo : rank;
+    const u32 g = (z * 0x11111111u + (0x77777777u - r * 0x11111111u)) & 0x88888888u;
+    const u32 tile = ((g & (0u - g)) >> 3) * exp;
+    if (in_hi) b.hi |= tile; else b.lo |= tile;
+    return true;
+}
+
+__device__ __forceinline__ bool spawn_cell(Board& b, u32 cell, u32 exp) {
+    const u32 sh = (cell & 7u) * 4u;
+    u32& h = (cell & 8u) ? b.hi : b.lo;
+    if ((h >> sh) & 0xFu) return false;
+    h |= exp << sh;
+    return true;
+}
+
+// Injected spawn byte (include/g2048.h).  Returns false -> G2048_FLAG_BADSPAWN.
+__device__ __forceinline__ bool spawn_byte(Board& b, u32 zlo, u32 zhi, u32 byte) {
+    const u32 exp = (byte & 0x10u) ? 2u : 1u;
+    if (byte & 0x80u) return spawn_cell(b, byte & 0xFu, exp);
+    return spawn_rank(b, zlo, zhi, byte & 0xFu, exp);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  key = (k0,k1); counter = (env_lo, env_hi, step, tag).
+// ---------------------------------------------------------------------------------------------
+struct Philox4 {
+    u32 x, y, z, w;
+};
+
+__device__ __forceinline__ Philox4 philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, u32 k0, u32 k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const u32 h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const u32 h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0;
+        c1 = l1;
+        c2 = h0 ^ c3 ^ k1;
+        c3 = l0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ Philox4 philox_env(u64 key, u64 env, u32 step, u32 tag) {
+    return philox4x32_10((u32)env, (u32)(env >> 32), step, tag, (u32)key, (u32)(key >> 32));
+}
+
+// Philox spawn: rank = mulhi(word0, n_empty), four iff word1 < 0x1999999A.
+__device__ __forceinline__ void spawn_philox(Board& b, u32 zlo, u32 zhi, const Philox4& p) {
+    const u32 n = __popc(zlo) + __popc(zhi);
+    if (n == 0u) return;
+    spawn_rank(b, zlo, zhi, __umulhi(p.x, n), p.y < G2048_PHILOX_FOUR_THRESHOLD ? 2u : 1u);
+}
+
+__device__ __forceinline__ u32 max_exponent(Board b) {
+    u32 m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        m = max(m, (b.lo >> (4 * i)) & 0xFu);
+        m = max(m, (b.hi >> (4 * i)) & 0xFu);
+    }
+    return m;
+}
+
+}  // namespace g2048

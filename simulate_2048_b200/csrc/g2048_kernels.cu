@@ -1,0 +1,1132 @@
+// g2048_kernels.cu — sm_100a kernels and the C ABI of libg2048.so (include/g2048.h).
+//
+// Hot path (BASELINE.json north_star): one batched 2048 transition per env
+//   board(u64) , action(u8) [, spawn(u8)]  ->  board(u64), reward(i32), flags(u8)
+// HBM-bound: 22 B/env (Philox) or 23 B/env (injected spawns).  Design:
+//   * persistent grid, one 1024-thread CTA per SM, 4 consecutive envs per thread so every
+//     stream is one wide access per thread: 256-bit board load/store (LDG.E.256 / STG.E.256),
+//     128-bit reward store, 32-bit action / spawn / flags;
+//   * the 57344-entry row table (224 KiB) is staged into shared memory once per CTA by a TMA
+//     bulk copy (cp.async.bulk, UBLKCP) that completes on an mbarrier while the first boards
+//     are already in flight; a move is then 4 LDS + 2 PRMT;
+//   * up / right / down are reduced to "left" by a nibble transpose (8 LOP/SHF + 2 PRMT) and a
+//     row mirror, reward rides in the table entry, the legal mask / done of the NEW board and
+//     the tile spawn are nibble-parallel register arithmetic in the same pass;
+//   * inputs of tile t+1 are loaded before tile t is computed (register double buffering).
+// No Triton, no CPU fallback: every entry point either launches these kernels or fails.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "g2048_device.cuh"
+
+using namespace g2048;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_cuda_err[256] = "";
+
+static int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_cuda_err, sizeof g_cuda_err, "%s: %s", what, cudaGetErrorString(e));
+    return G2048_ECUDA;
+}
+#define CU(call)                                               \
+    do {                                                       \
+        cudaError_t e_ = (call);                               \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call);    \
+    } while (0)
+
+extern "C" int g2048_abi_version(void) { return G2048_ABI_VERSION; }
+extern "C" const char* g2048_last_cuda_error(void) { return g_cuda_err; }
+extern "C" const char* g2048_error_string(int code) {
+    switch (code) {
+        case G2048_OK: return "ok";
+        case G2048_EINVAL: return "invalid argument (NULL or misaligned pointer, bad enum)";
+        case G2048_ECUDA: return "CUDA runtime failure (see g2048_last_cuda_error)";
+        case G2048_ENODEV: return "no usable CUDA device (sm_100 required)";
+        case G2048_ERANGE: return "tile value not representable (0 or a power of two in [2, 32768])";
+        default: return "unknown error";
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-device state: the row table
+// ---------------------------------------------------------------------------------------------
+__global__ void build_table_kernel(u32* __restrict__ tab) {
+    u32 row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row < kRows) tab[row] = make_entry(row);
+}
+
+struct DeviceState {
+    std::mutex mu;
+    bool ready = false;
+    u32* table = nullptr;
+    int sms = 0;
+    size_t smem_optin = 0;
+};
+static DeviceState g_dev[64];
+static int g_impl = G2048_IMPL_AUTO;
+
+static int current_state(DeviceState** out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cuda_fail(e, "cudaGetDevice");
+        return G2048_ENODEV;
+    }
+    if (dev < 0 || dev >= 64) return G2048_EINVAL;
+    DeviceState& s = g_dev[dev];
+    if (!s.ready) {
+        std::lock_guard<std::mutex> lk(s.mu);
+        if (!s.ready) {
+            cudaDeviceProp p;
+            CU(cudaGetDeviceProperties(&p, dev));
+            if (p.major != 10) {
+                snprintf(g_cuda_err, sizeof g_cuda_err, "device %d is sm_%d%d, need sm_100", dev,
+                         p.major, p.minor);
+                return G2048_ENODEV;
+            }
+            s.sms = p.multiProcessorCount;
+            s.smem_optin = p.sharedMemPerBlockOptin;
+            CU(cudaMalloc(&s.table, kRows * sizeof(u32)));
+            build_table_kernel<<<kRows / 256, 256>>>(s.table);
+            CU(cudaGetLastError());
+            CU(cudaDeviceSynchronize());
+            s.ready = true;
+        }
+    }
+    *out = &s;
+    return G2048_OK;
+}
+
+extern "C" int g2048_init(int device) {
+    if (device >= 0) CU(cudaSetDevice(device));
+    DeviceState* s;
+    return current_state(&s);
+}
+
+extern "C" int g2048_set_impl(int impl) {
+    if (impl < G2048_IMPL_AUTO || impl > G2048_IMPL_REGISTER) return G2048_EINVAL;
+    g_impl = impl;
+    return G2048_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// wide global accesses (streaming: nothing is re-read, keep it out of L1)
+// ---------------------------------------------------------------------------------------------
+struct Boards4 {
+    u64 b[4];
+};
+
+__device__ __forceinline__ Boards4 ld_boards4(const u64* p) {
+    Boards4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(r.b[0]), "=l"(r.b[1]), "=l"(r.b[2]), "=l"(r.b[3])
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_boards4(u64* p, const Boards4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(v.b[0]),
+                 "l"(v.b[1]), "l"(v.b[2]), "l"(v.b[3])
+                 : "memory");
+}
+__device__ __forceinline__ u32 ld_u32_stream(const void* p) {
+    u32 r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_u32_stream(void* p, u32 v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_int4_stream(void* p, int4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA bulk copy of the row table into shared memory, completion on an mbarrier
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_addr(const void* p) {
+    return (u32)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void table_stage_begin(u32* smem_tab, u64* bar, const u32* gtab) {
+    if (threadIdx.x == 0) {
+        const u32 b = smem_addr(bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b),
+                     "r"(kSmemTableBytes)
+                     : "memory");
+        constexpr u32 kChunk = 32768u;  // 7 bulk copies of 32 KiB
+#pragma unroll
+        for (u32 off = 0; off < kSmemTableBytes; off += kChunk) {
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                    "r"(smem_addr(smem_tab) + off),
+                "l"(reinterpret_cast<const char*>(gtab) + off), "r"(kChunk), "r"(b)
+                : "memory");
+        }
+    }
+}
+
+__device__ __forceinline__ void table_stage_wait(u64* bar) {
+    __syncthreads();  // the barrier init by thread 0 is visible before anyone polls it
+    const u32 b = smem_addr(bar);
+    u32 done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(b)
+            : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// one transition, shared by every step kernel
+// ---------------------------------------------------------------------------------------------
+template <class Table, bool kPhilox>
+__device__ __forceinline__ void transition(Board b, u32 action, u32 spawn, u64 key, u64 env,
+                                           u32 step, const Table& T, Board& out, u32& reward,
+                                           u32& flags) {
+    MoveResult m = move_action(b, action & 3u, T);
+    const bool moved = (m.after.lo != b.lo) | (m.after.hi != b.hi);  // core.py:258
+    Board nb = m.after;  // an illegal move leaves the board as it was (gameboard.py:325)
+    u32 nlo = nz8(nb.lo), nhi = nz8(nb.hi);
+    u32 f = (moved ? G2048_FLAG_MOVED : 0u) | (m.overflow ? G2048_FLAG_OVERFLOW : 0u);
+    // spawn on the afterstate of a legal move (gameboard.py:323, core.py:267)
+    const u32 zlo = (~nlo >> 3) & 0x11111111u, zhi = (~nhi >> 3) & 0x11111111u;
+    const u32 clo = __popc(zlo), n_empty = clo + __popc(zhi);
+    u32 rank, exp;
+    bool ok = true;
+    if (kPhilox) {
+        const Philox4 p = philox_env(key, env, step, G2048_PHILOX_TAG_STEP);
+        rank = __umulhi(p.x, n_empty);
+        exp = p.y < G2048_PHILOX_FOUR_THRESHOLD ? 2u : 1u;
+    } else {
+        exp = (spawn & 0x10u) ? 2u : 1u;
+        rank = spawn & 0xFu;
+        if (spawn & 0x80u) {  // absolute cell: translate to its rank among the empties
+            const u32 cell = spawn & 0xFu, sh = (cell & 7u) * 4u;
+            const u32 zh = (cell & 8u) ? zhi : zlo;
+            ok = (zh >> sh) & 1u;
+            rank = __popc(zh & ((1u << sh) - 1u)) + ((cell & 8u) ? clo : 0u);
+        }
+    }
+    ok = ok & (rank < n_empty);
+    if (moved & ok) {
+        const bool in_hi = rank >= clo;
+        const u32 z = in_hi ? zhi : zlo;
+        const u32 r = in_hi ? rank - clo : rank;
+        const u32 g = (z * 0x11111111u + (0x77777777u - r * 0x11111111u)) & 0x88888888u;
+        const u32 bit3 = g & (0u - g);  // bit 3 of the target nibble
+        const u32 tile = (bit3 >> 3) * exp;
+        if (in_hi) {
+            nb.hi |= tile;
+            nhi |= bit3;
+        } else {
+            nb.lo |= tile;
+            nlo |= bit3;
+        }
+    }
+    if (moved & !ok) f |= G2048_FLAG_BADSPAWN;
+    f |= board_flags(legal_mask(nb, nlo, nhi));
+    out = nb;
+    reward = m.score;
+    flags = f;
+}
+
+struct StepArgs {
+    const u64* boards_in;
+    const uint8_t* actions;
+    const uint8_t* spawns;
+    u64 seed, env_offset;
+    const u32* step_ctr;
+    u32 step_base;
+    const u64* env_keys;
+    const uint8_t* done_in;
+    u64* boards_out;
+    int32_t* rewards;
+    uint8_t* flags;
+    size_t n;
+    const u32* table;
+};
+
+// ---------------------------------------------------------------------------------------------
+// fast step kernel: smem table, 4 envs / thread, persistent, double buffered
+// ---------------------------------------------------------------------------------------------
+constexpr int kStepThreads = 1024;
+constexpr int kEnvsPerThread = 4;
+constexpr size_t kTileEnvs = (size_t)kStepThreads * kEnvsPerThread;
+
+struct TileIn {
+    Boards4 boards;
+    u32 actions, spawns;
+};
+
+template <bool kPhilox>
+__device__ __forceinline__ TileIn load_tile(const StepArgs& a, size_t env0) {
+    TileIn t;
+    t.boards = ld_boards4(a.boards_in + env0);
+    t.actions = ld_u32_stream(a.actions + env0);
+    t.spawns = kPhilox ? 0u : ld_u32_stream(a.spawns + env0);
+    return t;
+}
+
+template <bool kPhilox>
+__global__ void __launch_bounds__(kStepThreads, 1) step_lut_kernel(const StepArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    u32* smem_tab = reinterpret_cast<u32*>(smem_raw);
+    u64* bar = reinterpret_cast<u64*>(smem_raw + kSmemTableBytes);
+
+    table_stage_begin(smem_tab, bar, a.table);
+
+    const size_t full_tiles = a.n / kTileEnvs;
+    const size_t t0 = blockIdx.x;
+    TileIn cur;
+    if (t0 < full_tiles) cur = load_tile<kPhilox>(a, t0 * kTileEnvs + threadIdx.x * kEnvsPerThread);
+
+    table_stage_wait(bar);
+    const SmemTable T{smem_tab, a.table};
+
+    for (size_t t = t0; t < full_tiles; t += gridDim.x) {
+        const size_t env0 = t * kTileEnvs + threadIdx.x * kEnvsPerThread;
+        const size_t tn = t + gridDim.x;
+        TileIn nxt;
+        if (tn < full_tiles) nxt = load_tile<kPhilox>(a, tn * kTileEnvs + threadIdx.x * kEnvsPerThread);
+
+        Boards4 ob;
+        int4 rw;
+        u32 fl = 0;
+        int* rwp = &rw.x;
+#pragma unroll
+        for (int k = 0; k < kEnvsPerThread; ++k) {
+            Board nb;
+            u32 r, f;
+            transition<SmemTable, kPhilox>(split(cur.boards.b[k]), cur.actions >> (8 * k),
+                                           (cur.spawns >> (8 * k)) & 0xFFu, a.seed,
+                                           a.env_offset + env0 + k, a.step_base, T, nb, r, f);
+            ob.b[k] = join(nb);
+            rwp[k] = (int)r;
+            fl |= f << (8 * k);
+        }
+        st_boards4(a.boards_out + env0, ob);
+        st_int4_stream(a.rewards + env0, rw);
+        st_u32_stream(a.flags + env0, fl);
+        cur = nxt;
+    }
+
+    // ragged tail (< one tile): CTA 0, one env per thread-iteration
+    if (blockIdx.x == 0) {
+        for (size_t i = full_tiles * kTileEnvs + threadIdx.x; i < a.n; i += kStepThreads) {
+            Board nb;
+            u32 r, f;
+            transition<SmemTable, kPhilox>(split(a.boards_in[i]), a.actions[i],
+                                           kPhilox ? 0u : a.spawns[i], a.seed, a.env_offset + i,
+                                           a.step_base, T, nb, r, f);
+            a.boards_out[i] = join(nb);
+            a.rewards[i] = (int)r;
+            a.flags[i] = (uint8_t)f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// general step kernel: every optional input, any alignment, table gathered from global/L2.
+// Used for small batches (no 224 KiB staging) and for the rarely used options.
+// ---------------------------------------------------------------------------------------------
+template <bool kPhilox>
+__global__ void __launch_bounds__(256) step_general_kernel(const StepArgs a) {
+    const GlobalTable T{a.table};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const Board b = split(a.boards_in[i]);
+        if (a.done_in && a.done_in[i]) {  // env.py:103-104 pass-through
+            a.boards_out[i] = join(b);
+            a.rewards[i] = 0;
+            a.flags[i] = (uint8_t)(legal_mask(b) | G2048_FLAG_DONE);
+            continue;
+        }
+        Board nb;
+        u32 r, f;
+        transition<GlobalTable, kPhilox>(b, a.actions[i], kPhilox ? 0u : a.spawns[i],
+                                         a.env_keys ? a.env_keys[i] : a.seed, a.env_offset + i,
+                                         a.step_ctr ? a.step_ctr[i] : a.step_base, T, nb, r, f);
+        a.boards_out[i] = join(nb);
+        a.rewards[i] = (int)r;
+        a.flags[i] = (uint8_t)f;
+    }
+}
+
+static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+static int grid_for(size_t n, int threads, int sms, int per_sm) {
+    size_t blocks = (n + threads - 1) / threads;
+    size_t cap = (size_t)sms * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// smallest batch for which staging the 224 KiB table per SM beats gathering it through L2
+constexpr size_t kLutMinEnvs = (size_t)1 << 18;
+
+extern "C" int g2048_step(const uint64_t* boards_in, const uint8_t* actions, const uint8_t* spawns,
+                          uint64_t seed, uint64_t env_offset, const uint32_t* step_ctr,
+                          uint32_t step_base, const uint64_t* env_keys, const uint8_t* done_in,
+                          uint64_t* boards_out, int32_t* rewards, uint8_t* flags, size_t n,
+                          void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!boards_in || !actions || !boards_out || !rewards || !flags) return G2048_EINVAL;
+    if (!aligned(boards_in, 8) || !aligned(boards_out, 8) || !aligned(rewards, 4)) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    StepArgs a{reinterpret_cast<const u64*>(boards_in), actions, spawns, seed, env_offset, step_ctr,
+               step_base, reinterpret_cast<const u64*>(env_keys), done_in,
+               reinterpret_cast<u64*>(boards_out), rewards, flags, n, s->table};
+
+    const bool plain = !step_ctr && !env_keys && !done_in;
+    const bool vec_ok = aligned(boards_in, 32) && aligned(boards_out, 32) && aligned(rewards, 16) &&
+                        aligned(actions, 4) && aligned(flags, 4) && (!spawns || aligned(spawns, 4));
+    bool use_lut = plain && vec_ok && s->smem_optin >= kSmemTableBytes + 64;
+    if (g_impl == G2048_IMPL_AUTO) use_lut = use_lut && n >= kLutMinEnvs;
+    if (g_impl == G2048_IMPL_REGISTER) use_lut = false;
+
+    if (use_lut) {
+        const int smem = (int)kSmemTableBytes + 64;
+        size_t tiles = n / kTileEnvs;
+        int grid = (int)(tiles < (size_t)s->sms ? (tiles ? tiles : 1) : (size_t)s->sms);
+        if (spawns) {
+            CU(cudaFuncSetAttribute(step_lut_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            step_lut_kernel<false><<<grid, kStepThreads, smem, st>>>(a);
+        } else {
+            CU(cudaFuncSetAttribute(step_lut_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            step_lut_kernel<true><<<grid, kStepThreads, smem, st>>>(a);
+        }
+    } else {
+        int grid = grid_for(n, 256, s->sms, 8);
+        if (spawns) step_general_kernel<false><<<grid, 256, 0, st>>>(a);
+        else step_general_kernel<true><<<grid, 256, 0, st>>>(a);
+    }
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GameState step (env.py:79-133), one pass, in place
+// ---------------------------------------------------------------------------------------------
+struct EnvStepArgs {
+    u64* boards;
+    int32_t* step_count;
+    uint8_t* done;
+    float* total_reward;
+    const uint8_t* actions;
+    const uint8_t* spawns;
+    u64 seed, env_offset;
+    const u64* env_keys;
+    float* rewards;
+    uint8_t* flags;
+    float* obs;
+    int32_t* max_tile;
+    size_t n;
+    const u32* table;
+};
+
+__device__ __forceinline__ void write_obs(float* obs, size_t i, Board b) {
+    // core.py:371-375: log2(tile)/16 = exponent * 0.0625f, exact in f32
+    float4* o = reinterpret_cast<float4*>(obs + i * 16);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const u32 h = (q < 2) ? b.lo : b.hi;
+        const u32 row = (h >> ((q & 1) * 16)) & 0xFFFFu;
+        o[q] = make_float4((float)(row & 0xFu) * 0.0625f, (float)((row >> 4) & 0xFu) * 0.0625f,
+                           (float)((row >> 8) & 0xFu) * 0.0625f, (float)(row >> 12) * 0.0625f);
+    }
+}
+
+template <bool kPhilox>
+__global__ void __launch_bounds__(256) env_step_kernel(const EnvStepArgs a) {
+    const GlobalTable T{a.table};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const Board b = split(a.boards[i]);
+        Board nb = b;
+        u32 r = 0, f;
+        if (a.done[i]) {  // env.py:103-104
+            f = legal_mask(b) | G2048_FLAG_DONE;
+        } else {
+            const int sc = a.step_count[i];
+            transition<GlobalTable, kPhilox>(b, a.actions[i], kPhilox ? 0u : a.spawns[i],
+                                             a.env_keys ? a.env_keys[i] : a.seed, a.env_offset + i,
+                                             (u32)sc, T, nb, r, f);
+            a.boards[i] = join(nb);
+            a.step_count[i] = sc + 1;                             // env.py:116
+            a.done[i] = (f & G2048_FLAG_DONE) ? 1 : 0;            // env.py:111
+            a.total_reward[i] = a.total_reward[i] + (float)r;     // env.py:118
+        }
+        if (a.rewards) a.rewards[i] = (float)r;
+        if (a.flags) a.flags[i] = (uint8_t)f;
+        if (a.obs) write_obs(a.obs, i, nb);
+        if (a.max_tile) {
+            const u32 e = max_exponent(nb);
+            a.max_tile[i] = e ? (1 << e) : 0;  // core.py:427 returns the tile value
+        }
+    }
+}
+
+extern "C" int g2048_env_step(uint64_t* boards, int32_t* step_count, uint8_t* done,
+                              float* total_reward, const uint8_t* actions, const uint8_t* spawns,
+                              uint64_t seed, uint64_t env_offset, const uint64_t* env_keys,
+                              float* rewards, uint8_t* flags, float* obs, int32_t* max_tile,
+                              size_t n, void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!boards || !step_count || !done || !total_reward || !actions) return G2048_EINVAL;
+    if (obs && !aligned(obs, 16)) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    EnvStepArgs a{reinterpret_cast<u64*>(boards), step_count, done, total_reward, actions, spawns,
+                  seed, env_offset, reinterpret_cast<const u64*>(env_keys), rewards, flags, obs,
+                  max_tile, n, s->table};
+    int grid = grid_for(n, 256, s->sms, 8);
+    if (spawns) env_step_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    else env_step_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mask / observe / pack / unpack / reset
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) mask_kernel(const u64* __restrict__ boards,
+                                                   uint8_t* __restrict__ flags, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        flags[i] = (uint8_t)board_flags(legal_mask(split(boards[i])));
+}
+
+extern "C" int g2048_mask(const uint64_t* boards, uint8_t* flags, size_t n, void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!boards || !flags) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    mask_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const u64*>(boards), flags, n);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
+__global__ void __launch_bounds__(256) observe_kernel(const u64* __restrict__ boards,
+                                                      float* __restrict__ obs,
+                                                      uint8_t* __restrict__ max_exp, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const Board b = split(boards[i]);
+        if (obs) write_obs(obs, i, b);
+        if (max_exp) max_exp[i] = (uint8_t)max_exponent(b);
+    }
+}
+
+extern "C" int g2048_observe(const uint64_t* boards, float* obs, uint8_t* max_exp, size_t n,
+                             void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!boards || (obs && !aligned(obs, 16))) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    observe_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const u64*>(boards), obs, max_exp, n);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
+__global__ void __launch_bounds__(256) pack_kernel(const int32_t* __restrict__ tiles,
+                                                   u64* __restrict__ boards,
+                                                   int32_t* __restrict__ status, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        u64 b = 0;
+        bool bad = false;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const int32_t t = tiles[i * 16 + c];
+            u32 e = 0;
+            if (t != 0) {
+                if (t < 2 || t > 32768 || (t & (t - 1)) != 0) bad = true;
+                else e = 31u - __clz(t);
+            }
+            b |= (u64)e << (4 * c);
+        }
+        boards[i] = b;
+        if (bad && status) *status = G2048_ERANGE;
+    }
+}
+
+__global__ void __launch_bounds__(256) unpack_kernel(const u64* __restrict__ boards,
+                                                     int32_t* __restrict__ tiles, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const u64 b = boards[i];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            const u32 e = (u32)(b >> (4 * c)) & 0xFu;
+            tiles[i * 16 + c] = e ? (1 << e) : 0;
+        }
+    }
+}
+
+extern "C" int g2048_pack(const int32_t* tiles, uint64_t* boards, int32_t* status, size_t n,
+                          void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!tiles || !boards) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    pack_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        tiles, reinterpret_cast<u64*>(boards), status, n);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
+extern "C" int g2048_unpack(const uint64_t* boards, int32_t* tiles, size_t n, void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!tiles || !boards) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    unpack_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const u64*>(boards), tiles, n);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
+// two sequential spawns on the empty board (core.py:338-342)
+__device__ __forceinline__ Board reset_board(u64 key, u64 env, const uint8_t* spawn2) {
+    Board b{0u, 0u};
+#pragma unroll
+    for (u32 t = 0; t < 2; ++t) {
+        u32 zlo, zhi;
+        empties(b, zlo, zhi);
+        if (spawn2) {
+            spawn_byte(b, zlo, zhi, spawn2[t]);
+        } else {
+            spawn_philox(b, zlo, zhi, philox_env(key, env, 0u, G2048_PHILOX_TAG_RESET0 + t));
+        }
+    }
+    return b;
+}
+
+__global__ void __launch_bounds__(256) reset_kernel(u64 seed, u64 env_offset,
+                                                    const u64* __restrict__ env_keys,
+                                                    const uint8_t* __restrict__ spawns,
+                                                    u64* __restrict__ boards, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        boards[i] = join(reset_board(env_keys ? env_keys[i] : seed, env_offset + i,
+                                     spawns ? spawns + 2 * i : nullptr));
+}
+
+extern "C" int g2048_reset(uint64_t seed, uint64_t env_offset, const uint64_t* env_keys,
+                           const uint8_t* spawns, uint64_t* boards_out, size_t n, void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!boards_out) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    reset_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        seed, env_offset, reinterpret_cast<const u64*>(env_keys), spawns,
+        reinterpret_cast<u64*>(boards_out), n);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
+__global__ void __launch_bounds__(256) spawn_kernel(u64* __restrict__ boards,
+                                                    const uint8_t* __restrict__ spawns, u64 seed,
+                                                    u64 env_offset, const u64* __restrict__ env_keys,
+                                                    u32 step, u32 tag, uint8_t* __restrict__ flags,
+                                                    size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        Board b = split(boards[i]);
+        u32 zlo, zhi;
+        empties(b, zlo, zhi);
+        bool ok = true;
+        if ((zlo | zhi) != 0u) {  // a full board is returned unchanged (gameboard.py:277-278)
+            if (spawns) ok = spawn_byte(b, zlo, zhi, spawns[i]);
+            else spawn_philox(b, zlo, zhi, philox_env(env_keys ? env_keys[i] : seed, env_offset + i, step, tag));
+            boards[i] = join(b);
+        }
+        if (flags) flags[i] = ok ? 0 : G2048_FLAG_BADSPAWN;
+    }
+}
+
+extern "C" int g2048_spawn(uint64_t* boards_io, const uint8_t* spawns, uint64_t seed,
+                           uint64_t env_offset, const uint64_t* env_keys, uint32_t step_base,
+                           uint32_t tag, uint8_t* flags, size_t n, void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!boards_io) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    spawn_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<u64*>(boards_io), spawns, seed, env_offset,
+        reinterpret_cast<const u64*>(env_keys), step_base, tag, flags, n);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// MCTS leaf expansion (gameboard.py:105 x4, :132 after_state, gamemove.py:45)
+// One thread per board for the fixed-size outputs; children are written by the whole warp,
+// lane j producing child j of the current (board, action), so stores are contiguous.
+// ---------------------------------------------------------------------------------------------
+struct ExpandArgs {
+    const u64* boards;
+    u64* after;
+    int32_t* rewards;
+    uint8_t* mask;
+    uint8_t* num_empty;
+    uint8_t* child_count;
+    u64* children;
+    const int64_t* child_offsets;
+    int layout;
+    size_t n;
+    const u32* table;
+};
+
+// position (0..15) of the k-th set bit of a 16-bit cell mask
+__device__ __forceinline__ u32 kth_set_bit16(u32 m, u32 k) {
+    for (u32 i = 0; i < k; ++i) m &= m - 1u;
+    return __ffs(m) - 1u;
+}
+
+__device__ __forceinline__ u32 empty_cells16(Board b) {
+    // one bit per cell: gather bit 3 of every nibble of ~nz8
+    const u32 zlo = (~nz8(b.lo)) & 0x88888888u, zhi = (~nz8(b.hi)) & 0x88888888u;
+    u32 m = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        m |= ((zlo >> (4 * i + 3)) & 1u) << i;
+        m |= ((zhi >> (4 * i + 3)) & 1u) << (8 + i);
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(256) expand_kernel(const ExpandArgs a) {
+    const GlobalTable T{a.table};
+    const u32 lane = threadIdx.x & 31u;
+    const size_t warp_base0 = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) - lane;
+    for (size_t wb = warp_base0; wb < a.n; wb += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = wb + lane;
+        const bool live = i < a.n;
+        Board b = live ? split(a.boards[i]) : Board{0u, 0u};
+        u64 aft[4];
+        u32 cc[4], em[4];
+        u32 m = 0, ovf = 0;
+        // shared work: the transposed board serves up and down
+        const Board bt = transpose(b);
+#pragma unroll
+        for (u32 act = 0; act < 4; ++act) {
+            Board x = (act & 1u) ? bt : b;
+            if (act & 2u) x = reverse_rows(x);
+            MoveResult r = move_left(x, T);
+            if (act & 2u) r.after = reverse_rows(r.after);
+            if (act & 1u) r.after = transpose(r.after);
+            const bool moved = (r.after.lo != b.lo) | (r.after.hi != b.hi);
+            m |= moved ? (1u << act) : 0u;
+            ovf |= r.overflow ? 1u : 0u;
+            aft[act] = join(r.after);
+            em[act] = empty_cells16(r.after);
+            const u32 ne = __popc(em[act]);
+            cc[act] = moved ? (ne ? 2u * ne : 1u) : 0u;
+            if (live) {
+                if (a.after) a.after[i * 4 + act] = aft[act];
+                if (a.rewards) a.rewards[i * 4 + act] = (int32_t)r.score;
+                if (a.num_empty) a.num_empty[i * 4 + act] = (uint8_t)ne;
+                if (a.child_count) a.child_count[i * 4 + act] = (uint8_t)cc[act];
+            }
+        }
+        if (live && a.mask)
+            a.mask[i] = (uint8_t)(board_flags(m) | (ovf ? G2048_FLAG_OVERFLOW : 0u));
+
+        if (a.layout == G2048_CHILDREN_NONE || !a.children) continue;
+        // warp-cooperative child generation
+        int64_t off = (a.layout == G2048_CHILDREN_COMPACT && live) ? a.child_offsets[i] : 0;
+        for (u32 src = 0; src < 32u; ++src) {
+            if (wb + src >= a.n) break;
+            int64_t o = __shfl_sync(0xFFFFFFFFu, off, src);
+#pragma unroll
+            for (u32 act = 0; act < 4; ++act) {
+                const u64 p = __shfl_sync(0xFFFFFFFFu, aft[act], src);
+                const u32 e = __shfl_sync(0xFFFFFFFFu, em[act], src);
+                const u32 c = __shfl_sync(0xFFFFFFFFu, cc[act], src);
+                u64* dst = (a.layout == G2048_CHILDREN_DENSE)
+                               ? a.children + ((wb + src) * 4 + act) * 32
+                               : a.children + o;
+                if (lane < c) {
+                    u64 child = p;  // full afterstate: [(state, 1.0)] (gameboard.py:158-159)
+                    if (e) {
+                        const u32 cell = kth_set_bit16(e, lane >> 1);
+                        child = p | ((u64)(1u + (lane & 1u)) << (4 * cell));  // 2 first, then 4
+                    }
+                    dst[lane] = child;
+                }
+                o += c;
+            }
+        }
+    }
+}
+
+extern "C" int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* rewards,
+                            uint8_t* mask, uint8_t* num_empty, uint8_t* child_count,
+                            uint64_t* children, const int64_t* child_offsets, int child_layout,
+                            size_t n, void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!boards) return G2048_EINVAL;
+    if (child_layout < G2048_CHILDREN_NONE || child_layout > G2048_CHILDREN_COMPACT) return G2048_EINVAL;
+    if (child_layout != G2048_CHILDREN_NONE && !children) return G2048_EINVAL;
+    if (child_layout == G2048_CHILDREN_COMPACT && !child_offsets) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    ExpandArgs a{reinterpret_cast<const u64*>(boards), reinterpret_cast<u64*>(after), rewards, mask,
+                 num_empty, child_count, reinterpret_cast<u64*>(children), child_offsets,
+                 child_layout, n, s->table};
+    expand_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(a);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
+__global__ void __launch_bounds__(256) after_state_kernel(const u64* __restrict__ boards,
+                                                          u64* __restrict__ children,
+                                                          uint8_t* __restrict__ num_empty,
+                                                          uint16_t* __restrict__ empty_cells, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const u64 p = boards[i];
+        u32 e = empty_cells16(split(p));
+        if (num_empty) num_empty[i] = (uint8_t)__popc(e);
+        if (empty_cells) empty_cells[i] = (uint16_t)e;
+        if (!children) continue;
+        u64* dst = children + i * 32;
+        if (e == 0u) dst[0] = p;  // gameboard.py:158-159
+        for (u32 k = 0; e; ++k, e &= e - 1u) {
+            const u32 cell = __ffs(e) - 1u;
+            dst[2 * k] = p | (1ull << (4 * cell));      // tile 2 first (gameboard.py:162)
+            dst[2 * k + 1] = p | (2ull << (4 * cell));  // then tile 4
+        }
+    }
+}
+
+extern "C" int g2048_after_state(const uint64_t* boards, uint64_t* children, uint8_t* num_empty,
+                                 uint16_t* empty_cells, size_t n, void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!boards) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    after_state_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const u64*>(boards), reinterpret_cast<u64*>(children), num_empty,
+        empty_cells, n);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused random rollout: board, score, step counter live in registers until the game ends
+// ---------------------------------------------------------------------------------------------
+struct RolloutArgs {
+    u64 seed, env_offset;
+    size_t n;
+    u32 max_steps;
+    int from_reset;
+    u64* boards_io;
+    int64_t* score_out;
+    int32_t* steps_out;
+    uint8_t* maxexp_out;
+    u64* stats;
+    uint8_t* trace;
+    u32 trace_stride;
+    const u32* table;
+};
+
+// idx-th set bit (0-based) of a 4-bit mask
+__device__ __forceinline__ u32 pick_action(u32 mask, u32 idx) {
+    for (u32 i = 0; i < idx; ++i) mask &= mask - 1u;
+    return __ffs(mask) - 1u;
+}
+
+// Persistent lanes: every loop iteration is ONE game step for each lane that holds a live
+// game, so the step code runs convergent; lanes whose game ended pull the next env id at the
+// top of the loop (one warp-aggregated atomic for all lanes that need one).  Results are
+// keyed by the global env id and step, so they do not depend on which lane played the game.
+template <class Table>
+__device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const Table& T, u64* sh_stats,
+                                             unsigned long long* next) {
+    const u32 lane = threadIdx.x & 31u;
+    const u32 FULL = 0xFFFFFFFFu;
+    bool active = false, exhausted = false;
+    size_t i = 0;
+    u64 env = 0, score = 0;
+    Board b{0u, 0u};
+    u32 step = 0, ovf = 0, mask = 0, nlo = 0, nhi = 0;
+    for (;;) {
+        const u32 need = __ballot_sync(FULL, !active && !exhausted);
+        if (need) {
+            unsigned long long base = 0;
+            const u32 leader = __ffs(need) - 1u;
+            if (lane == leader) base = atomicAdd(next, (unsigned long long)__popc(need));
+            base = __shfl_sync(FULL, base, leader);
+            if (!active && !exhausted) {
+                i = (size_t)base + __popc(need & ((1u << lane) - 1u));
+                if (i < a.n) {
+                    env = a.env_offset + i;
+                    b = a.from_reset ? reset_board(a.seed, env, nullptr) : split(a.boards_io[i]);
+                    score = 0;
+                    step = 0;
+                    ovf = 0;
+                    nlo = nz8(b.lo);
+                    nhi = nz8(b.hi);
+                    mask = legal_mask(b, nlo, nhi);
+                    active = true;
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (!__any_sync(FULL, active)) break;
+        if (!active) continue;
+        if (mask == 0u || step >= a.max_steps) {  // game over: emit the episode
+            if (a.trace) a.trace[i * a.trace_stride + min(step, a.trace_stride - 1u)] = 0;
+            const u32 mx = max_exponent(b);
+            if (a.boards_io) a.boards_io[i] = join(b);
+            if (a.score_out) a.score_out[i] = (int64_t)score;
+            if (a.steps_out) a.steps_out[i] = (int32_t)step;
+            if (a.maxexp_out) a.maxexp_out[i] = (uint8_t)mx;
+            if (sh_stats) {
+                atomicAdd(&sh_stats[0], 1ull);
+                atomicAdd(&sh_stats[1], (u64)step);
+                atomicAdd(&sh_stats[2], score);
+                atomicMax(&sh_stats[3], score);
+                atomicMax(&sh_stats[4], (u64)step);
+                if (mask != 0u) atomicAdd(&sh_stats[5], 1ull);
+                if (ovf) atomicAdd(&sh_stats[6], 1ull);
+                atomicAdd(&sh_stats[8 + mx], 1ull);
+            }
+            active = false;
+            continue;
+        }
+        // one step: uniform-legal action (word2), move, spawn (words 0/1), new mask
+        const Philox4 p = philox_env(a.seed, env, step, G2048_PHILOX_TAG_STEP);
+        const u32 action = pick_action(mask, __umulhi(p.z, (u32)__popc(mask)));
+        MoveResult m = move_action(b, action, T);
+        b = m.after;
+        score += m.score;
+        ovf |= m.overflow ? 1u : 0u;
+        nlo = nz8(b.lo);
+        nhi = nz8(b.hi);
+        const u32 zlo = (~nlo >> 3) & 0x11111111u, zhi = (~nhi >> 3) & 0x11111111u;
+        const u32 clo = __popc(zlo), ne = clo + __popc(zhi);
+        const u32 rank = __umulhi(p.x, ne);
+        const u32 exp = p.y < G2048_PHILOX_FOUR_THRESHOLD ? 2u : 1u;
+        const bool in_hi = rank >= clo;
+        const u32 z = in_hi ? zhi : zlo, r = in_hi ? rank - clo : rank;
+        const u32 g = (z * 0x11111111u + (0x77777777u - r * 0x11111111u)) & 0x88888888u;
+        const u32 bit3 = g & (0u - g);
+        const u32 tile = (bit3 >> 3) * exp;
+        if (in_hi) { b.hi |= tile; nhi |= bit3; } else { b.lo |= tile; nlo |= bit3; }
+        if (a.trace && step + 1u < a.trace_stride) {
+            const u32 cell = ((__ffs(bit3) - 1u) >> 2) + (in_hi ? 8u : 0u);
+            a.trace[i * a.trace_stride + step] =
+                (uint8_t)(0x80u | action | (cell << 2) | ((exp - 1u) << 6));
+        }
+        ++step;
+        mask = legal_mask(b, nlo, nhi);
+    }
+}
+
+template <bool kSmem>
+__global__ void __launch_bounds__(512, 1) rollout_kernel(const RolloutArgs a, unsigned long long* next) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ u64 sh_stats[G2048_STATS_WORDS];
+    u32* smem_tab = reinterpret_cast<u32*>(smem_raw);
+    u64* bar = reinterpret_cast<u64*>(smem_raw + kSmemTableBytes);
+    if (kSmem) table_stage_begin(smem_tab, bar, a.table);
+    if (threadIdx.x < G2048_STATS_WORDS) sh_stats[threadIdx.x] = 0;
+    if (kSmem) table_stage_wait(bar); else __syncthreads();
+
+    if (kSmem) rollout_loop(a, SmemTable{smem_tab, a.table}, a.stats ? sh_stats : nullptr, next);
+    else rollout_loop(a, GlobalTable{a.table}, a.stats ? sh_stats : nullptr, next);
+
+    __syncthreads();
+    if (a.stats && threadIdx.x < G2048_STATS_WORDS) {
+        const u64 v = sh_stats[threadIdx.x];
+        if (threadIdx.x == 3 || threadIdx.x == 4) atomicMax(&a.stats[threadIdx.x], v);
+        else if (v) atomicAdd(&a.stats[threadIdx.x], v);
+    }
+}
+
+extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint32_t max_steps,
+                             int from_reset, uint64_t* boards_io, int64_t* score_out,
+                             int32_t* steps_out, uint8_t* maxexp_out, uint64_t* stats_out,
+                             uint8_t* trace, uint32_t trace_stride, void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!from_reset && !boards_io) return G2048_EINVAL;
+    if (trace && trace_stride < 2) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    RolloutArgs a{seed, env_offset, n, max_steps, from_reset, reinterpret_cast<u64*>(boards_io),
+                  score_out, steps_out, maxexp_out, reinterpret_cast<u64*>(stats_out), trace,
+                  trace_stride, s->table};
+    unsigned long long* next = nullptr;
+    CU(cudaMallocAsync(&next, sizeof(unsigned long long), st));
+    CU(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
+    const bool smem = n >= (size_t)s->sms * 512 && s->smem_optin >= kSmemTableBytes + 64;
+    if (smem) {
+        const int bytes = (int)kSmemTableBytes + 64;
+        CU(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        rollout_kernel<true><<<s->sms, 512, bytes, st>>>(a, next);
+    } else {
+        int grid = grid_for(n, 512, s->sms, 1);
+        rollout_kernel<false><<<grid, 512, 0, st>>>(a, next);
+    }
+    CU(cudaGetLastError());
+    CU(cudaFreeAsync(next, st));
+    return G2048_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// row table dump (tests: SURVEY.md §8c hashes)
+// ---------------------------------------------------------------------------------------------
+__global__ void row_table_kernel(uint16_t* res, u32* reward, uint8_t* moved) {
+    u32 row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= kRows) return;
+    u32 score;
+    bool ovf;
+    u32 r = row_left_exact(row, &score, &ovf);
+    res[row] = (uint16_t)r;
+    reward[row] = score;
+    moved[row] = (uint8_t)(r != row);
+}
+
+extern "C" int g2048_row_table_host(uint16_t* result, uint32_t* reward, uint8_t* moved) {
+    if (!result || !reward || !moved) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    uint16_t* d_res;
+    u32* d_rew;
+    uint8_t* d_mv;
+    CU(cudaMalloc(&d_res, kRows * 2));
+    CU(cudaMalloc(&d_rew, kRows * 4));
+    CU(cudaMalloc(&d_mv, kRows));
+    row_table_kernel<<<kRows / 256, 256>>>(d_res, d_rew, d_mv);
+    CU(cudaGetLastError());
+    // cross-check the packed entries actually used by the kernels
+    static u32 h_tab[kRows];
+    CU(cudaMemcpy(result, d_res, kRows * 2, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(reward, d_rew, kRows * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(moved, d_mv, kRows, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h_tab, s->table, kRows * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_res);
+    cudaFree(d_rew);
+    cudaFree(d_mv);
+    for (u32 r = 0; r < kRows; ++r)
+        if ((h_tab[r] & 0xFFFFu) != result[r] || (h_tab[r] >> 16) != (reward[r] >> 2)) {
+            snprintf(g_cuda_err, sizeof g_cuda_err, "row table entry %u inconsistent", r);
+            return G2048_ECUDA;
+        }
+    return G2048_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer transition: chunked H2D -> kernel -> D2H pipeline over 3 streams
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct HostPipe {
+    static constexpr int kSlots = 3;
+    static constexpr size_t kChunk = (size_t)1 << 22;  // 4 Mi envs / chunk: 40 MB in, 52 MB out
+    bool ready = false;
+    cudaStream_t stream[kSlots];
+    uint64_t *d_in[kSlots], *d_out[kSlots];
+    uint8_t *d_act[kSlots], *d_spn[kSlots], *d_flg[kSlots];
+    int32_t* d_rew[kSlots];
+};
+thread_local HostPipe g_pipe[64];
+
+int pipe_get(HostPipe** out) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    HostPipe& p = g_pipe[dev];
+    if (!p.ready) {
+        for (int i = 0; i < HostPipe::kSlots; ++i) {
+            CU(cudaStreamCreateWithFlags(&p.stream[i], cudaStreamNonBlocking));
+            CU(cudaMalloc(&p.d_in[i], HostPipe::kChunk * 8));
+            CU(cudaMalloc(&p.d_out[i], HostPipe::kChunk * 8));
+            CU(cudaMalloc(&p.d_act[i], HostPipe::kChunk));
+            CU(cudaMalloc(&p.d_spn[i], HostPipe::kChunk));
+            CU(cudaMalloc(&p.d_flg[i], HostPipe::kChunk));
+            CU(cudaMalloc(&p.d_rew[i], HostPipe::kChunk * 4));
+        }
+        p.ready = true;
+    }
+    *out = &p;
+    return G2048_OK;
+}
+}  // namespace
+
+extern "C" int g2048_step_host(const uint64_t* boards_in, const uint8_t* actions,
+                               const uint8_t* spawns, uint64_t seed, uint64_t env_offset,
+                               uint32_t step_base, uint64_t* boards_out, int32_t* rewards,
+                               uint8_t* flags, size_t n) {
+    if (n == 0) return G2048_OK;
+    if (!boards_in || !actions || !boards_out || !rewards || !flags) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    HostPipe* p;
+    rc = pipe_get(&p);
+    if (rc) return rc;
+    size_t done = 0;
+    int slot = 0;
+    while (done < n) {
+        const size_t m = (n - done < HostPipe::kChunk) ? n - done : HostPipe::kChunk;
+        cudaStream_t st = p->stream[slot];
+        // stream order makes reuse of this slot's buffers safe (previous chunk's D2H precedes)
+        CU(cudaMemcpyAsync(p->d_in[slot], boards_in + done, m * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(p->d_act[slot], actions + done, m, cudaMemcpyHostToDevice, st));
+        if (spawns) CU(cudaMemcpyAsync(p->d_spn[slot], spawns + done, m, cudaMemcpyHostToDevice, st));
+        rc = g2048_step(p->d_in[slot], p->d_act[slot], spawns ? p->d_spn[slot] : nullptr, seed,
+                        env_offset + done, nullptr, step_base, nullptr, nullptr, p->d_out[slot],
+                        p->d_rew[slot], p->d_flg[slot], m, st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(boards_out + done, p->d_out[slot], m * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(rewards + done, p->d_rew[slot], m * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(flags + done, p->d_flg[slot], m, cudaMemcpyDeviceToHost, st));
+        done += m;
+        slot = (slot + 1) % HostPipe::kSlots;
+    }
+    for (int i = 0; i < HostPipe::kSlots; ++i) CU(cudaStreamSynchronize(p->stream[i]));
+    return G2048_OK;
+}
+
+extern "C" int g2048_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return G2048_EINVAL;
+    CU(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    return G2048_OK;
+}
+
+extern "C" int g2048_host_free(void* ptr) {
+    CU(cudaFreeHost(ptr));
+    return G2048_OK;
+}

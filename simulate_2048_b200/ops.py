@@ -1,0 +1,330 @@
+"""Tensor-level operators over the C ABI (include/g2048.h).
+
+Every function takes CUDA ``torch`` tensors (torch is only the owner of device memory and
+streams here), checks dtype / device / contiguity, and launches the matching ``g2048_*`` entry
+point on the current CUDA stream.  Boards are packed ``int64`` tensors (bit pattern of the
+``uint64`` word: nibble ``i`` = log2 of flat cell ``i = 4r + c``).  Nothing here computes on
+the CPU and nothing falls back: a missing library or a non-CUDA tensor raises.
+"""
+
+from __future__ import annotations
+
+from typing import NamedTuple, Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import check, lib
+
+__all__ = [
+    'StepOut', 'ExpandOut', 'RolloutOut', 'step', 'env_step', 'legal_flags', 'expand', 'reset',
+    'observe', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'step_host', 'row_table', 'set_impl', 'init',
+    'pinned_empty',
+]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype: torch.dtype, name: str, n: Optional[int] = None) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f'{name}: expected a torch.Tensor, got {type(t).__name__}')
+    if not t.is_cuda:
+        raise ValueError(f'{name}: must be a CUDA tensor (simulate_2048_b200 has no CPU path)')
+    if t.dtype != dtype:
+        raise TypeError(f'{name}: expected dtype {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise ValueError(f'{name}: must be contiguous')
+    if n is not None and t.numel() != n:
+        raise ValueError(f'{name}: expected {n} elements, got {t.numel()}')
+    return t
+
+
+def _opt(t, dtype, name, n=None):
+    return None if t is None else _req(t, dtype, name, n)
+
+
+def _u8(actions: torch.Tensor, name: str, n: int) -> torch.Tensor:
+    """Accept uint8 directly; cast int32/int64 actions (the reference passes int32)."""
+    if actions.dtype != torch.uint8:
+        actions = actions.to(torch.uint8)
+    return _req(actions.contiguous(), torch.uint8, name, n)
+
+
+def init(device: Optional[int] = None) -> None:
+    """Build the per-device row table now (g2048_init)."""
+    check(lib().g2048_init(-1 if device is None else int(device)))
+
+
+def set_impl(impl: int) -> None:
+    check(lib().g2048_set_impl(int(impl)))
+
+
+class StepOut(NamedTuple):
+    boards: torch.Tensor   # int64[N] packed
+    rewards: torch.Tensor  # int32[N]
+    flags: torch.Tensor    # uint8[N]  (see include/g2048.h G2048_FLAG_*)
+
+
+def step(boards: torch.Tensor, actions: torch.Tensor, spawns: Optional[torch.Tensor] = None, *,
+         seed: int = 0, env_offset: int = 0, step_ctr: Optional[torch.Tensor] = None,
+         step_base: int = 0, env_keys: Optional[torch.Tensor] = None,
+         done_in: Optional[torch.Tensor] = None, out: Optional[StepOut] = None) -> StepOut:
+    """Raw batched transition (g2048_step): gameboard.py:291 / core.py:234 next_state fused with
+    the legal mask and done flag of the new board.  ``spawns=None`` selects Philox spawns."""
+    n = boards.numel()
+    _req(boards, torch.int64, 'boards')
+    actions = _u8(actions, 'actions', n)
+    spawns = None if spawns is None else _u8(spawns, 'spawns', n)
+    _opt(step_ctr, torch.int32, 'step_ctr', n)
+    _opt(env_keys, torch.int64, 'env_keys', n)
+    done_in = None if done_in is None else _u8(done_in, 'done_in', n)
+    if out is None:
+        out = StepOut(torch.empty_like(boards), torch.empty(n, dtype=torch.int32, device=boards.device),
+                      torch.empty(n, dtype=torch.uint8, device=boards.device))
+    else:
+        _req(out.boards, torch.int64, 'out.boards', n)
+        _req(out.rewards, torch.int32, 'out.rewards', n)
+        _req(out.flags, torch.uint8, 'out.flags', n)
+    with torch.cuda.device(boards.device):
+        check(lib().g2048_step(_ptr(boards), _ptr(actions), _ptr(spawns), seed & (2**64 - 1),
+                               env_offset, _ptr(step_ctr), step_base & 0xFFFFFFFF, _ptr(env_keys),
+                               _ptr(done_in), _ptr(out.boards), _ptr(out.rewards), _ptr(out.flags),
+                               n, _stream()))
+    return out
+
+
+def env_step(boards: torch.Tensor, step_count: torch.Tensor, done: torch.Tensor,
+             total_reward: torch.Tensor, actions: torch.Tensor,
+             spawns: Optional[torch.Tensor] = None, *, seed: int = 0, env_offset: int = 0,
+             env_keys: Optional[torch.Tensor] = None, rewards: Optional[torch.Tensor] = None,
+             flags: Optional[torch.Tensor] = None, obs: Optional[torch.Tensor] = None,
+             max_tile: Optional[torch.Tensor] = None) -> None:
+    """In-place GameState step (g2048_env_step; env.py:79-133)."""
+    n = boards.numel()
+    _req(boards, torch.int64, 'boards')
+    _req(step_count, torch.int32, 'step_count', n)
+    _req(done, torch.uint8, 'done', n)
+    _req(total_reward, torch.float32, 'total_reward', n)
+    actions = _u8(actions, 'actions', n)
+    spawns = None if spawns is None else _u8(spawns, 'spawns', n)
+    _opt(env_keys, torch.int64, 'env_keys', n)
+    _opt(rewards, torch.float32, 'rewards', n)
+    _opt(flags, torch.uint8, 'flags', n)
+    _opt(obs, torch.float32, 'obs', n * 16)
+    _opt(max_tile, torch.int32, 'max_tile', n)
+    with torch.cuda.device(boards.device):
+        check(lib().g2048_env_step(_ptr(boards), _ptr(step_count), _ptr(done), _ptr(total_reward),
+                                   _ptr(actions), _ptr(spawns), seed & (2**64 - 1), env_offset,
+                                   _ptr(env_keys), _ptr(rewards), _ptr(flags), _ptr(obs),
+                                   _ptr(max_tile), n, _stream()))
+
+
+def legal_flags(boards: torch.Tensor) -> torch.Tensor:
+    """uint8[N]: bits 0-3 legal (L,U,R,D), bit 4 done (g2048_mask; gamemove.py:45, core.py:275)."""
+    _req(boards, torch.int64, 'boards')
+    flags = torch.empty(boards.numel(), dtype=torch.uint8, device=boards.device)
+    with torch.cuda.device(boards.device):
+        check(lib().g2048_mask(_ptr(boards), _ptr(flags), boards.numel(), _stream()))
+    return flags
+
+
+class ExpandOut(NamedTuple):
+    after: torch.Tensor        # int64[N,4] afterstates (gameboard.py:105)
+    rewards: torch.Tensor      # int32[N,4]
+    mask: torch.Tensor         # uint8[N] legal | done | overflow
+    num_empty: torch.Tensor    # uint8[N,4]
+    child_count: torch.Tensor  # uint8[N,4]
+    children: Optional[torch.Tensor]       # int64[N,4,16,2] dense or int64[total] compact
+    child_offsets: Optional[torch.Tensor]  # int64[N] (compact)
+
+
+def expand(boards: torch.Tensor, children: str = 'none') -> ExpandOut:
+    """MCTS leaf expansion (g2048_expand): mask, the four afterstates + rewards and every chance
+    child of each legal afterstate (gameboard.py:132 after_state order: cell-major, 2 then 4;
+    probability of a child = {0.9, 0.1} / num_empty)."""
+    _req(boards, torch.int64, 'boards')
+    n = boards.numel()
+    dev = boards.device
+    layout = {'none': _cabi.CHILDREN_NONE, 'dense': _cabi.CHILDREN_DENSE,
+              'compact': _cabi.CHILDREN_COMPACT}[children]
+    after = torch.empty((n, 4), dtype=torch.int64, device=dev)
+    rewards = torch.empty((n, 4), dtype=torch.int32, device=dev)
+    mask = torch.empty(n, dtype=torch.uint8, device=dev)
+    num_empty = torch.empty((n, 4), dtype=torch.uint8, device=dev)
+    child_count = torch.empty((n, 4), dtype=torch.uint8, device=dev)
+    ch = off = None
+    with torch.cuda.device(dev):
+        if layout == _cabi.CHILDREN_COMPACT:
+            # pass 1 sizes the children, pass 2 writes them (afterstates are recomputed: 8 B read)
+            check(lib().g2048_expand(_ptr(boards), None, None, None, None, _ptr(child_count), None,
+                                     None, _cabi.CHILDREN_NONE, n, _stream()))
+            per_env = child_count.to(torch.int64).sum(dim=1)
+            incl = torch.cumsum(per_env, dim=0)
+            off = (incl - per_env).contiguous()
+            total = int(incl[-1].item()) if n else 0
+            ch = torch.empty(total, dtype=torch.int64, device=dev)
+        elif layout == _cabi.CHILDREN_DENSE:
+            ch = torch.zeros((n, 4, 16, 2), dtype=torch.int64, device=dev)
+        check(lib().g2048_expand(_ptr(boards), _ptr(after), _ptr(rewards), _ptr(mask),
+                                 _ptr(num_empty), _ptr(child_count), _ptr(ch), _ptr(off), layout, n,
+                                 _stream()))
+    return ExpandOut(after, rewards, mask, num_empty, child_count, ch, off)
+
+
+def after_state(boards: torch.Tensor, want_children: bool = True):
+    """Chance children of the given boards (g2048_after_state; gameboard.py:132/:174).
+    Returns (children int64[N,16,2] or None, num_empty uint8[N], empty_cells int16[N])."""
+    _req(boards, torch.int64, 'boards')
+    n = boards.numel()
+    dev = boards.device
+    ch = torch.zeros((n, 16, 2), dtype=torch.int64, device=dev) if want_children else None
+    ne = torch.empty(n, dtype=torch.uint8, device=dev)
+    ec = torch.empty(n, dtype=torch.int16, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().g2048_after_state(_ptr(boards), _ptr(ch), _ptr(ne), _ptr(ec), n, _stream()))
+    return ch, ne, ec
+
+
+def reset(n: int, *, seed: int = 0, env_offset: int = 0, env_keys: Optional[torch.Tensor] = None,
+          spawns: Optional[torch.Tensor] = None, device=None) -> torch.Tensor:
+    """New boards with two tiles (g2048_reset; core.py:324, twentyfortyeight.py:84)."""
+    dev = torch.device('cuda' if device is None else device)
+    _opt(env_keys, torch.int64, 'env_keys', n)
+    if spawns is not None:
+        spawns = _u8(spawns, 'spawns', 2 * n)
+    boards = torch.empty(n, dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().g2048_reset(seed & (2**64 - 1), env_offset, _ptr(env_keys), _ptr(spawns),
+                                _ptr(boards), n, _stream()))
+    return boards
+
+
+def spawn(boards: torch.Tensor, spawns: Optional[torch.Tensor] = None, *, seed: int = 0,
+          env_offset: int = 0, env_keys: Optional[torch.Tensor] = None, step: int = 0,
+          tag: int = 0, flags: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One new tile per board (g2048_spawn; gameboard.py:247 / core.py:173 fill_cells).  Returns
+    a new tensor; a full board comes back unchanged."""
+    _req(boards, torch.int64, 'boards')
+    n = boards.numel()
+    spawns = None if spawns is None else _u8(spawns, 'spawns', n)
+    _opt(env_keys, torch.int64, 'env_keys', n)
+    _opt(flags, torch.uint8, 'flags', n)
+    out = boards.clone()
+    with torch.cuda.device(boards.device):
+        check(lib().g2048_spawn(_ptr(out), _ptr(spawns), seed & (2**64 - 1), env_offset,
+                                _ptr(env_keys), step & 0xFFFFFFFF, tag & 0xFFFFFFFF, _ptr(flags), n,
+                                _stream()))
+    return out
+
+
+def observe(boards: torch.Tensor, want_max: bool = True):
+    """f32[N,16] observation = exponent/16 (core.py:346) and uint8[N] max exponent."""
+    _req(boards, torch.int64, 'boards')
+    n = boards.numel()
+    obs = torch.empty((n, 16), dtype=torch.float32, device=boards.device)
+    mx = torch.empty(n, dtype=torch.uint8, device=boards.device) if want_max else None
+    with torch.cuda.device(boards.device):
+        check(lib().g2048_observe(_ptr(boards), _ptr(obs), _ptr(mx), n, _stream()))
+    return obs, mx
+
+
+class RolloutOut(NamedTuple):
+    boards: torch.Tensor   # int64[N] final boards
+    score: torch.Tensor    # int64[N]
+    steps: torch.Tensor    # int32[N]
+    maxexp: torch.Tensor   # uint8[N]
+    stats: torch.Tensor    # int64[24] (see include/g2048.h)
+    trace: Optional[torch.Tensor]
+
+
+def rollout(n: int, *, seed: int = 0, env_offset: int = 0, max_steps: int = 1 << 20,
+            boards: Optional[torch.Tensor] = None, trace_stride: int = 0,
+            per_env: bool = True, stats: Optional[torch.Tensor] = None, device=None) -> RolloutOut:
+    """Fused random-policy rollouts to termination (g2048_rollout).  ``boards=None`` starts from
+    reset boards; ``per_env=False`` keeps only the statistics vector."""
+    dev = torch.device('cuda' if device is None else device) if boards is None else boards.device
+    from_reset = boards is None
+    if boards is not None:
+        boards = _req(boards, torch.int64, 'boards', n).clone()
+    elif per_env:
+        boards = torch.empty(n, dtype=torch.int64, device=dev)
+    score = torch.empty(n, dtype=torch.int64, device=dev) if per_env else None
+    steps = torch.empty(n, dtype=torch.int32, device=dev) if per_env else None
+    mx = torch.empty(n, dtype=torch.uint8, device=dev) if per_env else None
+    if stats is None:
+        stats = torch.zeros(_cabi.STATS_WORDS, dtype=torch.int64, device=dev)
+    else:
+        _req(stats, torch.int64, 'stats', _cabi.STATS_WORDS)
+    trace = torch.zeros((n, trace_stride), dtype=torch.uint8, device=dev) if trace_stride else None
+    with torch.cuda.device(dev):
+        check(lib().g2048_rollout(seed & (2**64 - 1), env_offset, n, max_steps & 0xFFFFFFFF,
+                                  1 if from_reset else 0, _ptr(boards), _ptr(score), _ptr(steps),
+                                  _ptr(mx), _ptr(stats), _ptr(trace), trace_stride, _stream()))
+    return RolloutOut(boards, score, steps, mx, stats, trace)
+
+
+def pack(tiles: torch.Tensor) -> torch.Tensor:
+    """int32[N,4,4] (or [N,16]) tile values -> packed int64[N]; raises on unrepresentable tiles."""
+    _req(tiles, torch.int32, 'tiles')
+    if tiles.numel() % 16:
+        raise ValueError('tiles: need a multiple of 16 elements')
+    n = tiles.numel() // 16
+    boards = torch.empty(n, dtype=torch.int64, device=tiles.device)
+    status = torch.zeros(1, dtype=torch.int32, device=tiles.device)
+    with torch.cuda.device(tiles.device):
+        check(lib().g2048_pack(_ptr(tiles), _ptr(boards), _ptr(status), n, _stream()))
+    code = int(status.item())
+    if code:
+        check(code)
+    return boards
+
+
+def unpack(boards: torch.Tensor) -> torch.Tensor:
+    """packed int64[N] -> int32[N,4,4] tile values."""
+    _req(boards, torch.int64, 'boards')
+    n = boards.numel()
+    tiles = torch.empty((n, 4, 4), dtype=torch.int32, device=boards.device)
+    with torch.cuda.device(boards.device):
+        check(lib().g2048_unpack(_ptr(boards), _ptr(tiles), n, _stream()))
+    return tiles
+
+
+def pinned_empty(n: int, dtype: torch.dtype) -> np.ndarray:
+    """NumPy array backed by pinned host memory (full PCIe bandwidth for step_host).
+    The array keeps the torch storage alive through its ``base``."""
+    return torch.empty(n, dtype=dtype).pin_memory().numpy()
+
+
+def step_host(boards: np.ndarray, actions: np.ndarray, spawns: Optional[np.ndarray] = None, *,
+              seed: int = 0, env_offset: int = 0, step_base: int = 0, out=None):
+    """HOST ndarray in, HOST ndarray out (g2048_step_host): the reference-facing call.  The H2D
+    copy, kernel and D2H copy of successive chunks overlap inside the library."""
+    b = np.ascontiguousarray(boards).view(np.uint64).reshape(-1)
+    n = b.size
+    a = np.ascontiguousarray(actions, dtype=np.uint8).reshape(-1)
+    s = None if spawns is None else np.ascontiguousarray(spawns, dtype=np.uint8).reshape(-1)
+    if a.size != n or (s is not None and s.size != n):
+        raise ValueError('actions / spawns must have one entry per board')
+    if out is None:
+        out = (np.empty(n, dtype=np.uint64), np.empty(n, dtype=np.int32), np.empty(n, dtype=np.uint8))
+    ob, orw, ofl = out
+    check(lib().g2048_step_host(b.ctypes.data, a.ctypes.data, None if s is None else s.ctypes.data,
+                                seed & (2**64 - 1), env_offset, step_base & 0xFFFFFFFF,
+                                ob.ctypes.data, orw.ctypes.data, ofl.ctypes.data, n))
+    return ob, orw, ofl
+
+
+def row_table():
+    """(result u16[65536], reward u32[65536], moved u8[65536]) read back from the device table."""
+    res = np.empty(65536, dtype=np.uint16)
+    rew = np.empty(65536, dtype=np.uint32)
+    mv = np.empty(65536, dtype=np.uint8)
+    check(lib().g2048_row_table_host(res.ctypes.data, rew.ctypes.data, mv.ctypes.data))
+    return res, rew, mv

@@ -1,0 +1,52 @@
+"""Drop-in for ``twentyfortyeight/envs/twentyfortyeight.py`` (class ``TwentyFortyEight``)."""
+
+from __future__ import annotations
+
+from numpy import int64, ndarray, zeros
+
+from ..core.gameboard import fill_cells, is_done, next_state
+
+
+class TwentyFortyEight:
+    """twentyfortyeight.py:10 — 4x4 game; the ``encoded`` / ``normalize`` presentation variants of
+    the reference are out of scope for the device path and raise."""
+
+    ACTIONS = {'left': 0, 'up': 1, 'right': 2, 'down': 3}  # twentyfortyeight.py:19
+
+    def __init__(self, size: int = 4, encoded: bool = False, normalize: bool = False):
+        if size != 4 or encoded or normalize:
+            raise NotImplementedError('device path implements size=4, encoded=False, normalize=False')
+        self.size = size
+        self._encoded = encoded
+        self._normalize = normalize
+        self._current_state: ndarray = zeros((size, size), dtype=int64)
+        self._current_reward: float = 0.0
+        self.reset()
+
+    @property
+    def is_finished(self) -> bool:
+        return is_done(self._current_state)
+
+    @property
+    def observation(self) -> ndarray:
+        return self._current_state
+
+    @property
+    def reward(self) -> float:
+        return self._current_reward
+
+    def reset(self, seed: int | None = None) -> ndarray:
+        """twentyfortyeight.py:84 — empty board + two tiles, reward 0."""
+        self._current_state = zeros((self.size, self.size), dtype=int64)
+        self._current_state = fill_cells(state=self._current_state, number_tile=2, seed=seed)
+        self._current_reward = 0
+        return self.observation
+
+    def step(self, action: int) -> tuple[ndarray, float, bool]:
+        """twentyfortyeight.py:106 — (observation, reward of this step, finished)."""
+        self._current_state, self._current_reward = next_state(state=self._current_state, action=action)
+        return self.observation, self.reward, self.is_finished
+
+    def render(self) -> None:
+        for row in self._current_state.tolist():
+            print(' \t'.join(map(str, row)))
