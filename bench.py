@@ -1,0 +1,456 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of the batched 2048 transition on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, N > 1)
+
+A "step" is one pass of the hot path (g2048_step) over one batch of synthetic boards.
+Workload: BASELINE.json configs[1] ("single batched step on 1M synthetic random boards") scaled
+to 2^26 boards per GPU per launch — the 1M set tiled 64x with fresh actions/spawns — because a
+1M batch (23 MB) sits in L2 and lasts about one launch latency; the 1M case
+is reported beside it as `latency_1m`.  Each rank owns its own 2^26 envs ("weak" scaling, no
+collective on the step path).
+
+One JSON line on stdout (rank 0):
+  value      whole-job env-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through g2048_step_host: pinned HOST buffers in, HOST buffers out,
+             H2D and D2H copies inside the timed region
+  roofline   algorithmic bytes per launch / mean launch time vs the measured HBM copy peak
+  cpu_baseline  the CPU oracle port timed on this box's host cores (rank 0, N = 1)
+plus secondary measurements (philox mode, 1M latency, expand, rollout, self-play loop).
+`--impl reference` times the reference's CPU algorithm (NumPy port of the engine, one Python
+call per env as the reference runs it) on all host cores and prints the same line shape.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BYTES_INJECTED = 23  # read board 8 + action 1 + spawn 1; write board 8 + reward 4 + flags 1
+BYTES_PHILOX = 22
+METRIC = 'env_steps_per_sec'
+UNIT = 'env-steps/s'
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def measured_peak():
+    """(GB/s, 'measured'|'fallback')"""
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic workload (SURVEY.md §8d generator, seed 2048)
+# --------------------------------------------------------------------------------------------
+
+def synthetic_packed(n: int, seed: int = 2048) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    cnt = rng.integers(1, 17, n)
+    keys = rng.random((n, 16))
+    ex = rng.integers(1, 12, (n, 16))
+    order = np.argsort(keys, axis=1, kind='stable')
+    ranks = np.empty_like(order)
+    np.put_along_axis(ranks, order, np.arange(16)[None, :].repeat(n, 0), axis=1)
+    vals = np.take_along_axis(ex, ranks, axis=1)
+    exps = np.where(ranks < cnt[:, None], vals, 0).astype(np.uint64)
+    return np.bitwise_or.reduce(exps << (4 * np.arange(16, dtype=np.uint64))[None, :], axis=1)
+
+
+# --------------------------------------------------------------------------------------------
+# clocks during the timed region
+# --------------------------------------------------------------------------------------------
+
+REASONS = {0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap',
+           0x8: 'hw_slowdown', 0x10: 'sync_boost', 0x20: 'sw_thermal_slowdown',
+           0x40: 'hw_thermal_slowdown', 0x80: 'hw_power_brake_slowdown', 0x100: 'display_clock_setting'}
+
+
+class ClockSampler:
+    def __init__(self, index: int, period: float = 0.05):
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self._stop = threading.Event()
+        self._t = None
+        self.period = period
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            log('clock sampling unavailable:', e)
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for b, name in REASONS.items():
+                    if bits & b and name != 'gpu_idle':
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+        return {'sm_mhz': int(statistics.median(self.samples)), 'sm_max_mhz': self.max_mhz,
+                'reasons': sorted(self.reasons), 'samples': len(self.samples),
+                'power_w_max': round(max(self.power), 1) if self.power else None}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baselines (oracle; the only place bench.py executes oracle/)
+# --------------------------------------------------------------------------------------------
+
+def _np_worker(args):
+    tiles, actions, seed = args
+    from oracle import np_engine
+    t0 = time.perf_counter()
+    np_engine.step_boards(tiles, actions, seed)
+    return time.perf_counter() - t0
+
+
+def numpy_port_rate(packed: np.ndarray, actions: np.ndarray, per_worker: int, workers: int, pool=None):
+    """env-steps/s of the NumPy port (one next_state call per env) over `workers` processes."""
+    from oracle import c_oracle
+    total = per_worker * workers
+    idx = np.arange(total) % packed.size
+    tiles = c_oracle.unpack(packed[idx]).astype(np.int64)
+    jobs = [(tiles[w * per_worker:(w + 1) * per_worker], actions[idx][w * per_worker:(w + 1) * per_worker], w)
+            for w in range(workers)]
+    t0 = time.perf_counter()
+    if workers == 1:
+        _np_worker(jobs[0])
+    else:
+        pool.map(_np_worker, jobs)
+    dt = time.perf_counter() - t0
+    return total / dt, dt
+
+
+def cpu_baseline_block(packed, actions, cores):
+    """Bounded sample (~10-30 s of CPU work): NumPy port on all cores + the C oracle."""
+    import multiprocessing as mp
+    from oracle import c_oracle
+    c_oracle.build()
+    per_worker = 1 << 13
+    with mp.get_context('fork').Pool(cores) as pool:
+        rate, dt = numpy_port_rate(packed, actions, per_worker, cores, pool)
+    rate1, _ = numpy_port_rate(packed, actions, 1 << 12, 1)
+    n_c = min(packed.size, 1 << 22)
+    t0 = time.perf_counter()
+    c_oracle.step(packed[:n_c], actions[:n_c], None, seed=2048, threads=cores)
+    c_rate = n_c / (time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    c_oracle.step(packed[: n_c // 8], actions[: n_c // 8], None, seed=2048, threads=1)
+    c_rate1 = (n_c // 8) / (time.perf_counter() - t0)
+    return {
+        'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+        'sample': f'NumPy port of the reference engine (oracle/np_engine.py next_state, one Python call '
+                  f'per env), {per_worker} boards x {cores} processes of the config-2 set, {dt:.1f} s',
+        'single_core_value': rate1,
+        'c_oracle': {'value': c_rate, 'single_core_value': c_rate1, 'cores': cores, 'unit': UNIT,
+                     'sample': f'oracle/g2048_oracle.c orc_step, {n_c} boards, pthreads'},
+    }
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm
+# --------------------------------------------------------------------------------------------
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    from oracle import c_oracle
+    c_oracle.build()
+    cores = host_cores()
+    packed = synthetic_packed(1 << 16)
+    actions = np.random.default_rng(0).integers(0, 4, packed.size).astype(np.uint8)
+    total_steps = args.steps + args.warmup
+    with mp.get_context('fork').Pool(cores) as pool:
+        probe, _ = numpy_port_rate(packed, actions, 512, cores, pool)   # untimed sizing probe
+        budget = 90.0  # seconds for the whole run
+        per_worker = int(max(256, min(1 << 14, probe * budget / total_steps / cores)))
+        for _ in range(args.warmup):
+            numpy_port_rate(packed, actions, per_worker, cores, pool)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            numpy_port_rate(packed, actions, per_worker, cores, pool)
+        dt = time.perf_counter() - t0
+    envs = per_worker * cores * args.steps
+    value = envs / dt
+    sample = (f'{per_worker * cores} boards per step ({per_worker} x {cores} processes) of the config-2 '
+              f'synthetic set through the NumPy port of twentyfortyeight next_state')
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64',
+        'data': 'synthetic',
+        'config': {'workload': 'single batched 2048 step (configs[1]) on the CPU engine; bounded sample: ' + sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from simulate_2048_b200 import ops
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus and world > 1:
+        log(f'warning: --gpus {args.gpus} but WORLD_SIZE {world}')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    ops.init(local)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- workload: the 1M config-2 set tiled to B boards, fresh actions / spawns per copy ----
+    B = 1 << args.boards_log2
+    base_np = synthetic_packed(1 << 20)
+    base = torch.from_numpy(base_np.view(np.int64)).to(dev)
+    boards = base.repeat(B // base.numel()).contiguous()
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    actions = torch.randint(0, 4, (B,), dtype=torch.uint8, device=dev, generator=gen)
+    # valid injected spawns: rank uniform over the empties of the afterstate, four w.p. 0.1
+    spawns = torch.empty(B, dtype=torch.uint8, device=dev)
+    chunk = 1 << 22
+    for lo in range(0, B, chunk):
+        ex = ops.expand(boards[lo:lo + chunk], children='none')
+        ne = ex.num_empty.gather(1, actions[lo:lo + chunk].to(torch.int64).unsqueeze(1)).squeeze(1)
+        r = torch.randint(0, 1 << 30, (chunk,), device=dev, generator=gen) % ne.clamp(min=1).to(torch.int64)
+        four = (torch.rand(chunk, device=dev, generator=gen) < 0.1).to(torch.int64) << 4
+        spawns[lo:lo + chunk] = (r | four).to(torch.uint8)
+        del ex
+    out = ops.StepOut(torch.empty_like(boards), torch.empty(B, dtype=torch.int32, device=dev),
+                      torch.empty(B, dtype=torch.uint8, device=dev))
+    env_offset = rank * B
+
+    def timed(fn, steps, warmup):
+        """CUDA events on the launching (current) stream around every step; barrier + sync on
+        both sides; returns (total seconds = max over ranks, mean launch seconds)."""
+        for _ in range(warmup):
+            fn()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for a, b in ev:
+            a.record()
+            fn()
+            b.record()
+        t1.record()
+        barrier()
+        total = max_over_ranks(t0.elapsed_time(t1) / 1e3)
+        per = [a.elapsed_time(b) / 1e3 for a, b in ev]
+        return total, sum(per) / len(per), min(per)
+
+    # ---- primary: injected spawns (the mode that is bit-exact against the reference) ----
+    step_inj = lambda: ops.step(boards, actions, spawns, env_offset=env_offset, out=out)  # noqa: E731
+    step_phx = lambda: ops.step(boards, actions, None, seed=2048, env_offset=env_offset, out=out)  # noqa: E731
+    with ClockSampler(local) as clocks:
+        total, mean_launch, best_launch = timed(step_inj, args.steps, args.warmup)
+    value = world * B * args.steps / total
+    peak, peak_src = measured_peak()
+    achieved = BYTES_INJECTED * B / mean_launch / 1e9
+
+    p_total, p_mean, _ = timed(step_phx, max(args.steps // 2, 5), 3)
+    philox = {'value': world * B * max(args.steps // 2, 5) / p_total, 'unit': UNIT,
+              'achieved_gbs': BYTES_PHILOX * B / p_mean / 1e9,
+              'frac': BYTES_PHILOX * B / p_mean / 1e9 / peak}
+
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': total / args.steps * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u64', 'data': 'synthetic',
+        'config': {
+            'workload': f'single batched 2048 step (BASELINE configs[1]) on 2^{args.boards_log2} synthetic '
+                        'random boards per GPU per launch (the 1M-board set tiled, fresh actions and injected '
+                        'spawns per copy)',
+            'boards_per_gpu': B, 'spawn_mode': 'injected', 'bytes_per_env_step': BYTES_INJECTED,
+            'l2': f'inputs {B * 10 / 1e6:.0f} MB + outputs {B * 13 / 1e6:.0f} MB per step, larger than the 126 MB L2; no flush needed',
+            'parallelism': f'env-sharded x{world}, no collective on the step path',
+        },
+        'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                     'frac': achieved / peak, 'traffic': args.ncu_traffic, 'peak_source': peak_src,
+                     'kernel': 'step_lut_kernel<false>', 'mean_launch_ms': mean_launch * 1e3,
+                     'best_launch_ms': best_launch * 1e3,
+                     'algorithmic_bytes_per_launch': BYTES_INJECTED * B},
+        'clocks': clocks.summary(),
+        'gpu_launches': args.steps,
+        'philox_mode': philox,
+    }
+
+    # ---- e2e: pinned host buffers through g2048_step_host (H2D + kernel + D2H timed) ----
+    Be = 1 << args.e2e_log2
+    h_b = ops.pinned_empty(Be, torch.int64)
+    h_a = ops.pinned_empty(Be, torch.uint8)
+    h_s = ops.pinned_empty(Be, torch.uint8)
+    h_b[:] = boards[:Be].cpu().numpy()
+    h_a[:] = actions[:Be].cpu().numpy()
+    h_s[:] = spawns[:Be].cpu().numpy()
+    h_out = (ops.pinned_empty(Be, torch.int64).view(np.uint64), ops.pinned_empty(Be, torch.int32),
+             ops.pinned_empty(Be, torch.uint8))
+    e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        ops.step_host(h_b, h_a, h_s, env_offset=env_offset, out=h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        ops.step_host(h_b, h_a, h_s, env_offset=env_offset, out=h_out)  # synchronous
+    torch.cuda.synchronize()
+    e_total = max_over_ranks(time.perf_counter() - t0)
+    line['e2e'] = {'value': world * Be * e_steps / e_total, 'unit': UNIT,
+                   'h2d_bytes_per_step': Be * 10, 'd2h_bytes_per_step': Be * 13,
+                   'boards_per_step': Be, 'steps': e_steps, 'ms_per_step': e_total / e_steps * 1e3,
+                   'api': 'simulate_2048_b200.ops.step_host -> g2048_step_host (pinned host ndarrays in/out)'}
+    del h_b, h_a, h_s, h_out
+
+    # ---- secondary measurements (rank-local, short) ----
+    if rank == 0 and not args.quick:
+        extra = {}
+        # 1M-board launches over rotating buffers (64 distinct 1M slices => cold in L2)
+        m1 = 1 << 20
+        views = [(boards[i * m1:(i + 1) * m1], actions[i * m1:(i + 1) * m1], spawns[i * m1:(i + 1) * m1],
+                  ops.StepOut(out.boards[i * m1:(i + 1) * m1], out.rewards[i * m1:(i + 1) * m1],
+                              out.flags[i * m1:(i + 1) * m1])) for i in range(B // m1)]
+        k = [0]
+
+        def one_m():
+            b_, a_, s_, o_ = views[k[0] % len(views)]
+            k[0] += 1
+            ops.step(b_, a_, s_, out=o_)
+        _, lat_mean, lat_min = timed(one_m, 256, 64)
+        extra['latency_1m'] = {'boards': m1, 'us_per_launch_mean': lat_mean * 1e6,
+                               'us_per_launch_min': lat_min * 1e6, 'env_steps_per_sec': m1 / lat_mean,
+                               'note': '2^20-board launches over 64 rotating slices (BASELINE configs[1] as written)'}
+        # config 3: MCTS leaf expansion, 65536 boards, compact children
+        eb = boards[:65536].contiguous()
+        ex = ops.expand(eb, children='compact')
+        n_children = int(ex.children.numel())
+        _, ex_mean, _ = timed(lambda: ops.expand(eb, children='dense'), 50, 5)
+        extra['expand_65536'] = {'boards_per_sec': 65536 / ex_mean, 'children_per_board': n_children / 65536,
+                                 'us_per_call': ex_mean * 1e6, 'layout': 'dense [N,4,16,2]'}
+        # config 4: fused rollouts to termination
+        n_roll = 1 << 20
+        ro = ops.rollout(n_roll, seed=1, per_env=False)
+        torch.cuda.synchronize()
+        r_steps = int(ro.stats[1].item())
+        _, ro_mean, _ = timed(lambda: ops.rollout(n_roll, seed=1, per_env=False), 3, 1)
+        extra['rollout'] = {'envs': n_roll, 'env_steps_per_sec': r_steps / ro_mean,
+                            'mean_length': r_steps / n_roll, 'ms': ro_mean * 1e3}
+        # config 5: self-play stepping loop, N = 4096, 200 steps, three API calls per iteration
+        from simulate_2048_b200 import game
+        st = game.batched_reset(7, 4096, device=dev)
+        acts = torch.randint(0, 4, (200, 4096), dtype=torch.uint8, device=dev, generator=gen)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in range(200):
+            game.batched_get_observation(st)
+            game.batched_get_legal_actions(st)
+            st, _, _, _ = game.batched_step(st, acts[t], 5, inplace=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        extra['selfplay_4096'] = {'us_per_iteration': dt / 200 * 1e6, 'env_steps_per_sec': 4096 * 200 / dt}
+        line['secondary'] = extra
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line['cpu_baseline'] = cpu_baseline_block(base_np, actions[: base_np.size].cpu().numpy(), host_cores())
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--boards-log2', type=int, default=26)
+    ap.add_argument('--e2e-log2', type=int, default=24)
+    ap.add_argument('--quick', action='store_true', help='skip the secondary measurements')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline block')
+    ap.add_argument('--ncu-traffic', type=float, default=None,
+                    help='dram bytes per launch from the committed ncu capture (profiles/)')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    return run_reference(args) if args.impl == 'reference' else run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -45,9 +45,9 @@ def reduce_stats(stats: torch.Tensor, group: Optional[dist.ProcessGroup] = None)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return stats.clone()
     world = dist.get_world_size(group)
-    stack = torch.empty((world, STATS_WORDS), dtype=stats.dtype, device=stats.device)
-    dist.all_gather_into_tensor(stack, stats.contiguous(), group=group)
-    return combine_stats(stack)
+    flat = torch.empty(world * STATS_WORDS, dtype=stats.dtype, device=stats.device)
+    dist.all_gather_into_tensor(flat, stats.contiguous().reshape(-1), group=group)
+    return combine_stats(flat.reshape(world, STATS_WORDS))
 
 
 @dataclass

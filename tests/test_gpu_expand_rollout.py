@@ -1,0 +1,172 @@
+"""GPU parity of the MCTS-leaf expansion (config 3) and the fused rollout (config 4)."""
+
+import numpy as np
+import pytest
+
+from tests.helpers import pack_tiles, synthetic_packed
+
+pytestmark = pytest.mark.gpu
+
+FLAG_DONE, FLAG_MOVED, FLAG_OVERFLOW = 0x10, 0x20, 0x40
+
+
+@pytest.fixture(scope='module')
+def T():
+    import torch
+    return torch
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from simulate_2048_b200 import ops
+    ops.init()
+    return ops
+
+
+def dev(T, a):
+    a = np.ascontiguousarray(a)
+    if a.dtype == np.uint64:
+        a = a.view(np.int64)
+    return T.from_numpy(a).cuda()
+
+
+def host(t):
+    a = t.cpu().numpy()
+    return a.view(np.uint64) if a.dtype == np.int64 else a
+
+
+# ------------------------------------------------------------------ expand
+
+def test_expand_reproduces_reference(T, ops, golden):
+    """mask + latent_state x4 + after_state children of the real reference (fixture)."""
+    g = golden('synthetic')
+    ex = ops.expand(dev(T, g['packed']), children='compact')
+    np.testing.assert_array_equal(host(ex.after), g['after'])
+    np.testing.assert_array_equal(ex.rewards.cpu().numpy(), g['rewards'].astype(np.int32))
+    np.testing.assert_array_equal(ex.mask.cpu().numpy() & 0xF, g['mask'])
+    np.testing.assert_array_equal(ex.child_count.cpu().numpy(), g['child_count'])
+    np.testing.assert_array_equal(host(ex.children), g['children'])
+    assert int(ex.child_count.sum().item()) == 249022
+
+
+@pytest.mark.parametrize('n', [1, 31, 33, 65536, 65536 + 7])
+def test_expand_vs_oracle(T, ops, oracle, n):
+    boards = synthetic_packed(n, seed=n + 1, max_exp=6 if n % 2 else 11)
+    for layout, code in (('none', 0), ('dense', 1), ('compact', 2)):
+        ex = ops.expand(dev(T, boards), children=layout)
+        want = oracle.expand(boards, child_layout=code)
+        np.testing.assert_array_equal(host(ex.after), want['after'])
+        np.testing.assert_array_equal(ex.rewards.cpu().numpy(), want['rewards'])
+        np.testing.assert_array_equal(ex.mask.cpu().numpy(), want['mask'])
+        np.testing.assert_array_equal(ex.num_empty.cpu().numpy(), want['num_empty'])
+        np.testing.assert_array_equal(ex.child_count.cpu().numpy(), want['child_count'])
+        if code == 1:
+            np.testing.assert_array_equal(host(ex.children), want['children'])
+        if code == 2:
+            np.testing.assert_array_equal(ex.child_offsets.cpu().numpy(), want['child_offsets'])
+            np.testing.assert_array_equal(host(ex.children), want['children'])
+
+
+def test_expand_edge_cases(T, ops, oracle):
+    tiles = np.array([
+        [[0] * 4] * 4,
+        [[2, 4, 2, 4], [4, 2, 4, 2], [2, 4, 2, 4], [4, 2, 4, 2]],
+        [[2, 2, 4, 8], [16, 32, 64, 128], [256, 512, 1024, 2048], [4096, 8192, 16384, 32768]],
+        [[32768, 32768, 0, 0], [32768, 0, 0, 0], [0] * 4, [0] * 4],
+        [[2, 4, 8, 16], [32, 64, 128, 0], [256, 512, 1024, 2048], [4096, 8192, 16384, 32768]],
+    ])
+    boards = pack_tiles(tiles)
+    ex = ops.expand(dev(T, boards), children='dense')
+    want = oracle.expand(boards, child_layout=1)
+    np.testing.assert_array_equal(host(ex.after), want['after'])
+    np.testing.assert_array_equal(ex.mask.cpu().numpy(), want['mask'])
+    np.testing.assert_array_equal(ex.child_count.cpu().numpy(), want['child_count'])
+    np.testing.assert_array_equal(host(ex.children), want['children'])
+    m = ex.mask.cpu().numpy()
+    assert m[0] == FLAG_DONE and m[1] == FLAG_DONE and m[3] & FLAG_OVERFLOW
+    # a legal move onto a full afterstate cannot exist (a move frees or keeps an empty cell);
+    # the single-empty board has 2 children per legal action with P = 0.9 / 0.1
+    cc = ex.child_count.cpu().numpy()
+    assert set(cc[4][cc[4] > 0]) == {2}
+
+
+def test_after_state_vs_oracle(T, ops, oracle):
+    boards = synthetic_packed(20000, seed=3)
+    boards[:3] = pack_tiles(np.array([[[0] * 4] * 4, [[2] * 4] * 4, [[2, 4, 8, 16], [32, 64, 128, 0], [2, 4, 8, 16], [32, 64, 128, 256]]]))
+    ch, ne, ec = ops.after_state(dev(T, boards))
+    o_ch, o_ne, o_ec = oracle.after_state(boards)
+    np.testing.assert_array_equal(host(ch).reshape(-1, 32), o_ch)
+    np.testing.assert_array_equal(ne.cpu().numpy(), o_ne)
+    np.testing.assert_array_equal(ec.cpu().numpy().view(np.uint16), o_ec)
+
+
+# ------------------------------------------------------------------ rollout
+
+@pytest.mark.parametrize('n', [1, 100, 20000, 148 * 512 + 13])
+def test_rollout_vs_oracle(T, ops, oracle, n):
+    """Every episode is bit-identical to the oracle's (same Philox stream keyed by env, step):
+    final board, score, length, max tile and the statistics vector."""
+    kw = dict(seed=0xABCDEF, env_offset=10**12)
+    out = ops.rollout(n, **kw)
+    want = oracle.rollout(n, **kw)
+    np.testing.assert_array_equal(host(out.boards), want['boards'])
+    np.testing.assert_array_equal(out.score.cpu().numpy(), want['score'])
+    np.testing.assert_array_equal(out.steps.cpu().numpy(), want['steps'])
+    np.testing.assert_array_equal(out.maxexp.cpu().numpy(), want['maxexp'])
+    np.testing.assert_array_equal(out.stats.cpu().numpy().view(np.uint64), want['stats'])
+    assert ((ops.legal_flags(out.boards).cpu().numpy() & FLAG_DONE) != 0).all()
+
+
+def test_rollout_trace_replays_through_step(T, ops, oracle):
+    """Trace mode: (action, spawn cell, value) per step replayed through g2048_step with
+    injected absolute-cell spawns AND through the oracle reproduces the episode."""
+    n, stride = 256, 4096
+    out = ops.rollout(n, seed=7, trace_stride=stride)
+    trace = out.trace.cpu().numpy()
+    want = oracle.rollout(n, seed=7, trace_stride=stride)
+    np.testing.assert_array_equal(trace, want['trace'])
+    boards = oracle.reset(n, seed=7)
+    score = np.zeros(n, np.int64)
+    alive = np.ones(n, bool)
+    for t in range(int(out.steps.max().item())):
+        byte = trace[:, t]
+        alive &= byte != 0
+        actions = (byte & 3).astype(np.uint8)
+        spawns = (0x80 | ((byte >> 2) & 0xF) | np.where(byte & 0x40, 0x10, 0)).astype(np.uint8)
+        res = ops.step(dev(T, boards), dev(T, actions), dev(T, spawns), done_in=dev(T, (~alive).astype(np.uint8)))
+        boards = host(res.boards)
+        score += np.where(alive, res.rewards.cpu().numpy(), 0)
+    np.testing.assert_array_equal(boards, host(out.boards))
+    np.testing.assert_array_equal(score, out.score.cpu().numpy())
+
+
+def test_rollout_sharding_invariance_and_caps(T, ops, oracle):
+    n = 6000
+    whole = ops.rollout(n, seed=3)
+    a = ops.rollout(2500, seed=3, env_offset=0)
+    b = ops.rollout(3500, seed=3, env_offset=2500)
+    np.testing.assert_array_equal(T.cat([a.score, b.score]).cpu().numpy(), whole.score.cpu().numpy())
+    from simulate_2048_b200.parallel import combine_stats
+    np.testing.assert_array_equal(combine_stats(T.stack([a.stats, b.stats])).cpu().numpy(),
+                                  whole.stats.cpu().numpy())
+    capped = ops.rollout(1000, seed=3, max_steps=50)
+    want = oracle.rollout(1000, seed=3, max_steps=50)
+    np.testing.assert_array_equal(capped.steps.cpu().numpy(), want['steps'])
+    np.testing.assert_array_equal(capped.stats.cpu().numpy().view(np.uint64), want['stats'])
+    assert int(capped.stats[5].item()) > 0
+    # from given boards
+    start = synthetic_packed(3000, seed=12)
+    got = ops.rollout(3000, seed=1, boards=dev(T, start))
+    want = oracle.rollout(3000, seed=1, from_reset=False, boards=start)
+    np.testing.assert_array_equal(host(got.boards), want['boards'])
+    np.testing.assert_array_equal(got.score.cpu().numpy(), want['score'])
+
+
+def test_rollout_statistics_sanity(T, ops):
+    """Random play statistics agree with the reference engine's (mean length
+    ~117, mean score ~1.1k; max tile mostly 64..256)."""
+    from simulate_2048_b200.parallel import EpisodeStats
+    out = ops.rollout(200000, seed=11, per_env=False)
+    s = EpisodeStats.from_vector(out.stats.cpu()).summary()
+    assert 105 < s['mean_length'] < 130 and 950 < s['mean_reward'] < 1250
+    assert s['max_tile'] <= 2048 and s['reached_2048'] < 20
