@@ -259,6 +259,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     ops.init(local)
+    if os.environ.get('G2048_STEP_THREADS'):
+        ops.set_tuning(int(os.environ['G2048_STEP_THREADS']))
 
     def barrier():
         if world > 1:

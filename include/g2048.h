@@ -96,6 +96,8 @@ const char* g2048_last_cuda_error(void); /* thread-local text of the last CUDA f
 int g2048_init(int device);
 /* Select the row-move implementation used by g2048_step/g2048_env_step (process-wide). */
 int g2048_set_impl(int impl);
+/* Tuning knob: threads per CTA of the smem-table step kernel (512, 768 or 1024; one CTA per SM). */
+int g2048_set_tuning(int step_threads);
 
 /*
  * Raw transition: replaces gameboard.py:291 next_state (+ is_done :328, gamemove.py:45

@@ -23,7 +23,7 @@ typedef unsigned int u32;
 typedef unsigned long long u64;
 
 // ---------------------------------------------------------------------------------------------
-// Row table entry (u32): bits 0..15 = row after a left move, bits 16..31 = (merge score) >> 2.
+// Row table entry (u32): bits 0..15 = (merge score) >> 2, bits 16..31 = row after a left move.
 // Score of a row is a multiple of 4 and at most 131072, so score >> 2 fits 16 bits exactly.
 // The shared-memory copy holds rows [0, kSmemRows): every row whose column-3 tile is <= 8192.
 // Rows outside it (a 16384 / 32768 tile in the last column of the oriented board) take the
@@ -100,7 +100,7 @@ __host__ __device__ inline u32 make_entry(u32 row) {
     u32 score;
     bool ovf;
     u32 res = row_left_exact(row, &score, &ovf);
-    return res | ((score >> 2) << 16);
+    return (score >> 2) | (res << 16);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -159,9 +159,9 @@ __device__ __forceinline__ MoveResult move_left(Board x, const Table& T) {
     MoveResult r;
     if (T.covers(x)) {
         u32 e0 = T(x.lo & 0xFFFFu), e1 = T(x.lo >> 16), e2 = T(x.hi & 0xFFFFu), e3 = T(x.hi >> 16);
-        r.after.lo = __byte_perm(e0, e1, 0x5410);
-        r.after.hi = __byte_perm(e2, e3, 0x5410);
-        r.score = ((e0 >> 16) + (e1 >> 16) + (e2 >> 16) + (e3 >> 16)) << 2;
+        r.after.lo = __byte_perm(e0, e1, 0x7632);
+        r.after.hi = __byte_perm(e2, e3, 0x7632);
+        r.score = ((e0 & 0xFFFFu) + (e1 & 0xFFFFu) + (e2 & 0xFFFFu) + (e3 & 0xFFFFu)) << 2;
         r.overflow = false;
         if (r.score < 65536u) return r;  // a 15+15 merge scores 65536 on its own
     }

@@ -19,6 +19,7 @@
 #include <mutex>
 
 #include "g2048_device.cuh"
+#include "g2048_fast.cuh"
 
 using namespace g2048;
 
@@ -53,20 +54,28 @@ extern "C" const char* g2048_error_string(int code) {
 // ---------------------------------------------------------------------------------------------
 // per-device state: the row table
 // ---------------------------------------------------------------------------------------------
-__global__ void build_table_kernel(u32* __restrict__ tab) {
+// tab: natural order (general kernels, slow path); tab_hashed: entry of `row` stored at
+// fast::hash_row16(row) — the copy the step kernel stages into shared memory.
+__global__ void build_table_kernel(u32* __restrict__ tab, u32* __restrict__ tab_hashed) {
     u32 row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row < kRows) tab[row] = make_entry(row);
+    if (row < kRows) {
+        const u32 e = make_entry(row);
+        tab[row] = e;
+        tab_hashed[fast::hash_row16(row)] = e;
+    }
 }
 
 struct DeviceState {
     std::mutex mu;
     bool ready = false;
     u32* table = nullptr;
+    u32* table_hashed = nullptr;
     int sms = 0;
     size_t smem_optin = 0;
 };
 static DeviceState g_dev[64];
 static int g_impl = G2048_IMPL_AUTO;
+static int g_step_threads = 1024;  // tuning knob (g2048_set_tuning)
 
 static int current_state(DeviceState** out) {
     int dev = 0;
@@ -90,7 +99,8 @@ static int current_state(DeviceState** out) {
             s.sms = p.multiProcessorCount;
             s.smem_optin = p.sharedMemPerBlockOptin;
             CU(cudaMalloc(&s.table, kRows * sizeof(u32)));
-            build_table_kernel<<<kRows / 256, 256>>>(s.table);
+            CU(cudaMalloc(&s.table_hashed, kRows * sizeof(u32)));
+            build_table_kernel<<<kRows / 256, 256>>>(s.table, s.table_hashed);
             CU(cudaGetLastError());
             CU(cudaDeviceSynchronize());
             s.ready = true;
@@ -104,6 +114,12 @@ extern "C" int g2048_init(int device) {
     if (device >= 0) CU(cudaSetDevice(device));
     DeviceState* s;
     return current_state(&s);
+}
+
+extern "C" int g2048_set_tuning(int step_threads) {
+    if (step_threads != 512 && step_threads != 768 && step_threads != 1024) return G2048_EINVAL;
+    g_step_threads = step_threads;
+    return G2048_OK;
 }
 
 extern "C" int g2048_set_impl(int impl) {
@@ -255,14 +271,14 @@ struct StepArgs {
     uint8_t* flags;
     size_t n;
     const u32* table;
+    const u32* table_hashed;
+    u32 one;  // always 1: a run-time multiplier that keeps adds on the FMA pipe (g2048_fast.cuh)
 };
 
 // ---------------------------------------------------------------------------------------------
 // fast step kernel: smem table, 4 envs / thread, persistent, double buffered
 // ---------------------------------------------------------------------------------------------
-constexpr int kStepThreads = 1024;
 constexpr int kEnvsPerThread = 4;
-constexpr size_t kTileEnvs = (size_t)kStepThreads * kEnvsPerThread;
 
 struct TileIn {
     Boards4 boards;
@@ -278,60 +294,149 @@ __device__ __forceinline__ TileIn load_tile(const StepArgs& a, size_t env0) {
     return t;
 }
 
+// exact out-of-line transition for the rare envs the fast path does not cover (a tile >= 16384
+// on the board, or an absolute-cell spawn byte)
 template <bool kPhilox>
-__global__ void __launch_bounds__(kStepThreads, 1) step_lut_kernel(const StepArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    u32* smem_tab = reinterpret_cast<u32*>(smem_raw);
-    u64* bar = reinterpret_cast<u64*>(smem_raw + kSmemTableBytes);
+__device__ __noinline__ uint4 transition_slow(u64 board, u32 action, u32 spawn, u64 key, u64 env,
+                                              u32 step, const u32* __restrict__ table) {
+    Board nb;
+    u32 reward, flags;
+    transition<GlobalTable, kPhilox>(split(board), action, spawn, key, env, step, GlobalTable{table},
+                                     nb, reward, flags);
+    return make_uint4(nb.lo, nb.hi, reward, flags);
+}
 
-    table_stage_begin(smem_tab, bar, a.table);
+__constant__ fast::Orient c_orient[4] = G2048_ORIENT_TABLE;
 
-    const size_t full_tiles = a.n / kTileEnvs;
-    const size_t t0 = blockIdx.x;
-    TileIn cur;
-    if (t0 < full_tiles) cur = load_tile<kPhilox>(a, t0 * kTileEnvs + threadIdx.x * kEnvsPerThread);
+struct SmemLut {
+    const u32* tab;  // staged table in shared memory, indexed by WORD: LDS R, [R*4 + UR]
+    __device__ __forceinline__ u32 operator()(u32 word) const { return tab[word]; }
+};
 
-    table_stage_wait(bar);
-    const SmemTable T{smem_tab, a.table};
-
-    for (size_t t = t0; t < full_tiles; t += gridDim.x) {
-        const size_t env0 = t * kTileEnvs + threadIdx.x * kEnvsPerThread;
-        const size_t tn = t + gridDim.x;
-        TileIn nxt;
-        if (tn < full_tiles) nxt = load_tile<kPhilox>(a, tn * kTileEnvs + threadIdx.x * kEnvsPerThread);
-
-        Boards4 ob;
-        int4 rw;
-        u32 fl = 0;
-        int* rwp = &rw.x;
+// Four consecutive envs of one thread.  The byte streams are decoded once per tile (one LOP3
+// per field for all four envs, then one PRMT per env), the four transitions are independent so
+// the scheduler interleaves them, and the rare inputs the fast path does not cover (a tile
+// >= 16384, an absolute-cell spawn byte) send the whole thread-tile to the exact slow path.
+template <bool kPhilox>
+__device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 spawns,
+                                           const StepArgs& a, u64 env0, const SmemLut& lut,
+                                           const uint4* __restrict__ s_orient, Boards4& ob,
+                                           int4& rw, u32& fl) {
+    u32 big = 0;
 #pragma unroll
-        for (int k = 0; k < kEnvsPerThread; ++k) {
-            Board nb;
-            u32 r, f;
-            transition<SmemTable, kPhilox>(split(cur.boards.b[k]), cur.actions >> (8 * k),
-                                           (cur.spawns >> (8 * k)) & 0xFFu, a.seed,
-                                           a.env_offset + env0 + k, a.step_base, T, nb, r, f);
-            ob.b[k] = join(nb);
-            rwp[k] = (int)r;
-            fl |= f << (8 * k);
+    for (int k = 0; k < 4; ++k) big |= fast::big_tile_bits((u32)in.b[k], (u32)(in.b[k] >> 32));
+    const bool slow = (big != 0u) | (!kPhilox && (spawns & 0x80808080u) != 0u);
+    int rws[4];
+    fl = 0;
+    if (slow) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // unrolled: static indices keep the arrays in registers
+            const uint4 r = transition_slow<kPhilox>(in.b[k], (actions >> (8 * k)) & 0xFFu,
+                                                     (spawns >> (8 * k)) & 0xFFu, a.seed, env0 + k,
+                                                     a.step_base, a.table);
+            ob.b[k] = ((u64)r.y << 32) | r.x;
+            rws[k] = (int)r.z;
+            fl |= r.w << (8 * k);
         }
-        st_boards4(a.boards_out + env0, ob);
-        st_int4_stream(a.rewards + env0, rw);
-        st_u32_stream(a.flags + env0, fl);
-        cur = nxt;
+        rw = make_int4(rws[0], rws[1], rws[2], rws[3]);
+        return;
+    }
+    const u32 act4 = (actions << 1) & 0x06060606u;     // byte k = 2 * action_k (uint4 index)
+    const u32 rank4 = spawns & 0x0F0F0F0Fu;            // byte k = spawn rank
+    const u32 exp4 = fast::shr<4>(spawns & 0x10101010u) + 0x01010101u;  // byte k = exponent (1 or 2)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const u32 oi = fast::prmt(act4, 0u, 0x4440u + k);
+        const uint4 o0 = s_orient[oi], o1 = s_orient[oi + 1];
+        fast::Orient o;
+        o.mt = o0.x; o.mr = o0.y; o.f_lo = o0.z; o.f_hi = o0.w; o.b_lo = o1.x; o.b_hi = o1.y;
+        u32 rank = 0, exp, w0 = 0;
+        if (kPhilox) {
+            const Philox4 p = philox_env(a.seed, env0 + k, a.step_base, G2048_PHILOX_TAG_STEP);
+            w0 = p.x;
+            // word1 < 0x1999999A  <=>  mulhi(word1, 10) == 0   (0x1999999A * 10 = 2^32 + 4)
+            exp = 2u - fast::nonzero01(__umulhi(p.y, 10u));
+        } else {
+            rank = fast::prmt(rank4, 0u, 0x4440u + k);
+            exp = fast::prmt(exp4, 0u, 0x4440u + k);
+        }
+        const fast::FastOut r = fast::transition_fast<kPhilox>((u32)in.b[k], (u32)(in.b[k] >> 32), o,
+                                                               rank, exp, w0, lut, a.one);
+        ob.b[k] = ((u64)r.hi << 32) | r.lo;
+        rws[k] = (int)r.reward;
+        fl = fast::add(r.flags << (8 * k), fl, a.one);
+    }
+    rw = make_int4(rws[0], rws[1], rws[2], rws[3]);
+}
+
+constexpr u32 kStepSmemBytes = kSmemTableBytes + 64u + 4u * (u32)sizeof(fast::Orient);
+
+// Persistent CTA (one per SM).  Each CTA owns a CONTIGUOUS range of tiles so that the next tile
+// of every stream is a compile-time offset away; the loop is unrolled by two tiles that ping-pong
+// between two register buffers (the loads of one tile are in flight while the other computes).
+template <bool kPhilox, int kThreads>
+__global__ void __launch_bounds__(kThreads, 1) step_lut_kernel(const StepArgs a) {
+    extern __shared__ __align__(128) u32 smem_words[];
+    u32* smem_tab = smem_words;
+    u64* bar = reinterpret_cast<u64*>(smem_words + kSmemRows);
+    uint4* s_orient = reinterpret_cast<uint4*>(smem_words + kSmemRows + 16);
+    constexpr size_t kTile = (size_t)kThreads * kEnvsPerThread;
+
+    table_stage_begin(smem_tab, bar, a.table_hashed);
+    if (threadIdx.x < 32)
+        reinterpret_cast<u32*>(s_orient)[threadIdx.x] = reinterpret_cast<const u32*>(c_orient)[threadIdx.x];
+
+    const size_t full_tiles = a.n / kTile;
+    const size_t t_begin = full_tiles * blockIdx.x / gridDim.x;
+    const size_t t_end = full_tiles * (blockIdx.x + 1) / gridDim.x;
+    size_t env0 = t_begin * kTile + threadIdx.x * kEnvsPerThread;
+    const size_t env_end = t_end * kTile;
+
+    TileIn bufA, bufB;
+    if (env0 < env_end) bufA = load_tile<kPhilox>(a, env0);
+
+    table_stage_wait(bar);  // __syncthreads inside also publishes s_orient
+    const SmemLut lut{smem_tab};
+
+    while (env0 < env_end) {
+        // tile A computes while tile B loads
+        const bool hasB = env0 + kTile < env_end;
+        if (hasB) bufB = load_tile<kPhilox>(a, env0 + kTile);
+        {
+            Boards4 ob;
+            int4 rw;
+            u32 fl;
+            step_tile4<kPhilox>(bufA.boards, bufA.actions, bufA.spawns, a, a.env_offset + env0, lut,
+                                s_orient, ob, rw, fl);
+            st_boards4(a.boards_out + env0, ob);
+            st_int4_stream(a.rewards + env0, rw);
+            st_u32_stream(a.flags + env0, fl);
+        }
+        if (!hasB) break;
+        // tile B computes while the next tile A loads
+        if (env0 + 2 * kTile < env_end) bufA = load_tile<kPhilox>(a, env0 + 2 * kTile);
+        {
+            Boards4 ob;
+            int4 rw;
+            u32 fl;
+            step_tile4<kPhilox>(bufB.boards, bufB.actions, bufB.spawns, a, a.env_offset + env0 + kTile,
+                                lut, s_orient, ob, rw, fl);
+            st_boards4(a.boards_out + env0 + kTile, ob);
+            st_int4_stream(a.rewards + env0 + kTile, rw);
+            st_u32_stream(a.flags + env0 + kTile, fl);
+        }
+        env0 += 2 * kTile;
     }
 
-    // ragged tail (< one tile): CTA 0, one env per thread-iteration
+    // ragged tail (< one tile): CTA 0, one env per thread-iteration through the exact path
     if (blockIdx.x == 0) {
-        for (size_t i = full_tiles * kTileEnvs + threadIdx.x; i < a.n; i += kStepThreads) {
-            Board nb;
-            u32 r, f;
-            transition<SmemTable, kPhilox>(split(a.boards_in[i]), a.actions[i],
-                                           kPhilox ? 0u : a.spawns[i], a.seed, a.env_offset + i,
-                                           a.step_base, T, nb, r, f);
-            a.boards_out[i] = join(nb);
-            a.rewards[i] = (int)r;
-            a.flags[i] = (uint8_t)f;
+        for (size_t i = full_tiles * kTile + threadIdx.x; i < a.n; i += kThreads) {
+            const uint4 r = transition_slow<kPhilox>(a.boards_in[i], a.actions[i],
+                                                     kPhilox ? 0u : a.spawns[i], a.seed,
+                                                     a.env_offset + i, a.step_base, a.table);
+            a.boards_out[i] = ((u64)r.y << 32) | r.x;
+            a.rewards[i] = (int)r.z;
+            a.flags[i] = (uint8_t)r.w;
         }
     }
 }
@@ -390,26 +495,36 @@ extern "C" int g2048_step(const uint64_t* boards_in, const uint8_t* actions, con
     cudaStream_t st = (cudaStream_t)stream;
     StepArgs a{reinterpret_cast<const u64*>(boards_in), actions, spawns, seed, env_offset, step_ctr,
                step_base, reinterpret_cast<const u64*>(env_keys), done_in,
-               reinterpret_cast<u64*>(boards_out), rewards, flags, n, s->table};
+               reinterpret_cast<u64*>(boards_out), rewards, flags, n, s->table, s->table_hashed, 1u};
 
     const bool plain = !step_ctr && !env_keys && !done_in;
     const bool vec_ok = aligned(boards_in, 32) && aligned(boards_out, 32) && aligned(rewards, 16) &&
                         aligned(actions, 4) && aligned(flags, 4) && (!spawns || aligned(spawns, 4));
-    bool use_lut = plain && vec_ok && s->smem_optin >= kSmemTableBytes + 64;
+    bool use_lut = plain && vec_ok && s->smem_optin >= kStepSmemBytes;
     if (g_impl == G2048_IMPL_AUTO) use_lut = use_lut && n >= kLutMinEnvs;
     if (g_impl == G2048_IMPL_REGISTER) use_lut = false;
 
     if (use_lut) {
-        const int smem = (int)kSmemTableBytes + 64;
-        size_t tiles = n / kTileEnvs;
-        int grid = (int)(tiles < (size_t)s->sms ? (tiles ? tiles : 1) : (size_t)s->sms);
+        const int smem = (int)kStepSmemBytes;
+        const int threads = g_step_threads;
+        const size_t tiles = n / ((size_t)threads * kEnvsPerThread);
+        const int grid = (int)(tiles < (size_t)s->sms ? (tiles ? tiles : 1) : (size_t)s->sms);
+#define G2048_LAUNCH_STEP(PH, TH)                                                                     \
+    do {                                                                                              \
+        CU(cudaFuncSetAttribute(step_lut_kernel<PH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                smem));                                                               \
+        step_lut_kernel<PH, TH><<<grid, TH, smem, st>>>(a);                                           \
+    } while (0)
         if (spawns) {
-            CU(cudaFuncSetAttribute(step_lut_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            step_lut_kernel<false><<<grid, kStepThreads, smem, st>>>(a);
+            if (threads == 512) G2048_LAUNCH_STEP(false, 512);
+            else if (threads == 768) G2048_LAUNCH_STEP(false, 768);
+            else G2048_LAUNCH_STEP(false, 1024);
         } else {
-            CU(cudaFuncSetAttribute(step_lut_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            step_lut_kernel<true><<<grid, kStepThreads, smem, st>>>(a);
+            if (threads == 512) G2048_LAUNCH_STEP(true, 512);
+            else if (threads == 768) G2048_LAUNCH_STEP(true, 768);
+            else G2048_LAUNCH_STEP(true, 1024);
         }
+#undef G2048_LAUNCH_STEP
     } else {
         int grid = grid_for(n, 256, s->sms, 8);
         if (spawns) step_general_kernel<false><<<grid, 256, 0, st>>>(a);
@@ -1042,7 +1157,7 @@ extern "C" int g2048_row_table_host(uint16_t* result, uint32_t* reward, uint8_t*
     cudaFree(d_rew);
     cudaFree(d_mv);
     for (u32 r = 0; r < kRows; ++r)
-        if ((h_tab[r] & 0xFFFFu) != result[r] || (h_tab[r] >> 16) != (reward[r] >> 2)) {
+        if ((h_tab[r] >> 16) != result[r] || (h_tab[r] & 0xFFFFu) != (reward[r] >> 2)) {
             snprintf(g_cuda_err, sizeof g_cuda_err, "row table entry %u inconsistent", r);
             return G2048_ECUDA;
         }

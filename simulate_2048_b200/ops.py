@@ -19,7 +19,7 @@ from ._cabi import check, lib
 
 __all__ = [
     'StepOut', 'ExpandOut', 'RolloutOut', 'step', 'env_step', 'legal_flags', 'expand', 'reset',
-    'observe', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'step_host', 'row_table', 'set_impl', 'init',
+    'observe', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'step_host', 'row_table', 'set_impl', 'set_tuning', 'init',
     'pinned_empty',
 ]
 
@@ -64,6 +64,10 @@ def init(device: Optional[int] = None) -> None:
 
 def set_impl(impl: int) -> None:
     check(lib().g2048_set_impl(int(impl)))
+
+
+def set_tuning(step_threads: int) -> None:
+    check(lib().g2048_set_tuning(int(step_threads)))
 
 
 class StepOut(NamedTuple):

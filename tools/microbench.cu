@@ -39,6 +39,21 @@ __global__ void __launch_bounds__(1024, 1) probe(uint32_t* out, long long* cycle
                 else { float f = __uint_as_float(a[c]); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f) : "f"(1.0001f), "f"(0.5f)); a[c] = __float_as_uint(f); }
             }
             if (OP == 13) asm volatile("vabsdiff4.u32.u32.u32.add %0, %0, %1, %2;" : "+r"(a[c]) : "r"(y), "r"(z));
+            if (OP == 14) asm volatile("add.u32 %0, %0, 0x77777777;" : "+r"(a[c]));                       // VIADD?
+            if (OP == 15) { if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[c]) : "r"(y), "r"(z));
+                            else asm volatile("add.u32 %0, %0, 0x77777777;" : "+r"(a[c])); }             // LOP3 + VIADD
+            if (OP == 16) { if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[c]) : "r"(y), "r"(z));
+                            else asm volatile("add.u32 %0, %0, %1;" : "+r"(a[c]) : "r"(y)); }            // LOP3 + IADD3
+            if (OP == 17) { if (c & 1) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[c]) : "r"(y), "r"(z));
+                            else asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(a[c]) : "r"(y)); }         // LOP3 + IMAD.HI
+            if (OP == 18) asm volatile("min.u32 %0, %0, %1;" : "+r"(a[c]) : "r"(y));                       // VIMNMX
+            if (OP == 19) asm volatile("{.reg .pred p; setp.lt.u32 p, %0, %1; @p add.u32 %0, %0, %2;}" : "+r"(a[c]) : "r"(y), "r"(z));
+            if (OP == 20) asm volatile("shf.r.wrap.b32 %0, %0, %1, 7;" : "+r"(a[c]) : "r"(y));
+            if (OP == 21) { unsigned long long w; asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(w) : "r"(a[c]), "r"(y)); a[c] = (uint32_t)w ^ (uint32_t)(w >> 32); }
+            if (OP == 22) { if ((c & 3) == 0) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a[c]) : "r"(y), "r"(z));
+                            else if ((c & 3) == 1) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[c]) : "r"(y));
+                            else asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[c]) : "r"(y), "r"(z)); } // 2 LOP3 : 1 IMAD : 1 IADD
+            if (OP == 23) asm volatile("mad.lo.u32 %0, %0, 1, %1;" : "+r"(a[c]) : "r"(y));                 // IMAD.IADD
         }
     }
     long long t1 = clock64();
@@ -103,6 +118,16 @@ int main() {
     run<11>("ISETP+SEL pair (x2 instr)", d_out, d_cyc);
     run<12>("LOP3+FFMA alternating", d_out, d_cyc);
     run<13>("vabsdiff4 (emulated?)", d_out, d_cyc);
+    run<14>("add imm (VIADD?)", d_out, d_cyc);
+    run<15>("LOP3 + add-imm alternating", d_out, d_cyc);
+    run<16>("LOP3 + add-reg alternating", d_out, d_cyc);
+    run<17>("LOP3 + IMAD.HI alternating", d_out, d_cyc);
+    run<18>("min.u32 (VIMNMX)", d_out, d_cyc);
+    run<19>("setp + predicated add (x2)", d_out, d_cyc);
+    run<20>("SHF.R funnel", d_out, d_cyc);
+    run<21>("IMAD.WIDE + xor (x2)", d_out, d_cyc);
+    run<22>("2 LOP3 : 1 IMAD : 1 IADD mix", d_out, d_cyc);
+    run<23>("mad.lo x,1,y (IMAD.IADD)", d_out, d_cyc);
     {
         constexpr int WORDS = 57344;
         CK(cudaFuncSetAttribute(lds_probe<WORDS>, cudaFuncAttributeMaxDynamicSharedMemorySize, WORDS * 4));
