@@ -90,7 +90,7 @@ REASONS = {0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_c
 
 
 class ClockSampler:
-    def __init__(self, index: int, period: float = 0.05):
+    def __init__(self, index: int, period: float = 0.004):
         self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
         self._stop = threading.Event()
         self._t = None
@@ -324,6 +324,13 @@ def run_ours(args):
     value = world * B * args.steps / total
     peak, peak_src = measured_peak()
     achieved = BYTES_INJECTED * B / mean_launch / 1e9
+    traffic = args.ncu_traffic
+    if traffic is None:
+        try:  # dram bytes per env measured by `ncu --set full` (profiles/r01_traffic.json)
+            with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+                traffic = json.load(f)['dram_bytes_per_env'] * B
+        except Exception:
+            traffic = None
 
     p_total, p_mean, _ = timed(step_phx, max(args.steps // 2, 5), 3)
     philox = {'value': world * B * max(args.steps // 2, 5) / p_total, 'unit': UNIT,
@@ -343,8 +350,8 @@ def run_ours(args):
             'parallelism': f'env-sharded x{world}, no collective on the step path',
         },
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                     'frac': achieved / peak, 'traffic': args.ncu_traffic, 'peak_source': peak_src,
-                     'kernel': 'step_lut_kernel<false>', 'mean_launch_ms': mean_launch * 1e3,
+                     'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                     'kernel': 'step_lut_kernel<false, 512>', 'mean_launch_ms': mean_launch * 1e3,
                      'best_launch_ms': best_launch * 1e3,
                      'algorithmic_bytes_per_launch': BYTES_INJECTED * B},
         'clocks': clocks.summary(),
@@ -391,10 +398,32 @@ def run_ours(args):
             b_, a_, s_, o_ = views[k[0] % len(views)]
             k[0] += 1
             ops.step(b_, a_, s_, out=o_)
-        _, lat_mean, lat_min = timed(one_m, 256, 64)
+        # back-to-back launches replayed from a CUDA graph, so the figure is device time per launch
+        # (Python/ctypes call overhead is ~20 us per call and would otherwise dominate)
+        for _ in range(len(views)):
+            one_m()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for _ in range(len(views)):
+                    one_m()
+        torch.cuda.synchronize()
+        _, g_mean, g_min = timed(graph.replay, 20, 3)
+        lat_mean, lat_min = g_mean / len(views), g_min / len(views)
         extra['latency_1m'] = {'boards': m1, 'us_per_launch_mean': lat_mean * 1e6,
                                'us_per_launch_min': lat_min * 1e6, 'env_steps_per_sec': m1 / lat_mean,
-                               'note': '2^20-board launches over 64 rotating slices (BASELINE configs[1] as written)'}
+                               'achieved_gbs': BYTES_INJECTED * m1 / lat_mean / 1e9,
+                               'note': f'2^20-board launches (BASELINE configs[1] as written), {len(views)} rotating '
+                                       'slices replayed back to back from one CUDA graph'}
+        # LUT-in-shared-memory vs pure register arithmetic (north star: "the choice evidenced by ncu")
+        ops.set_impl(2)
+        r_total, r_mean, _ = timed(step_inj, 10, 3)
+        ops.set_impl(0)
+        extra['register_arithmetic_variant'] = {'env_steps_per_sec': B / r_mean,
+                                                'achieved_gbs': BYTES_INJECTED * B / r_mean / 1e9,
+                                                'frac': BYTES_INJECTED * B / r_mean / 1e9 / peak}
         # config 3: MCTS leaf expansion, 65536 boards, compact children
         eb = boards[:65536].contiguous()
         ex = ops.expand(eb, children='compact')

@@ -169,6 +169,58 @@ __device__ __forceinline__ MoveResult move_left(Board x, const Table& T) {
     return move_left_slow(x);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Pure register-arithmetic row move (no table): the comparison variant the north star asks for
+// (G2048_IMPL_REGISTER).  Branch-free per row: six conditional "close the gap" steps compact the
+// four cells, three compare-and-merge steps apply the greedy left-to-right pairing
+// (gameboard.py:56-64), two more steps close the holes the merges leave.  About 70 select /
+// compare / shift instructions per row — see DESIGN.md for the measured comparison.
+// ---------------------------------------------------------------------------------------------
+struct RegisterTable {
+    __device__ __forceinline__ bool covers(Board) const { return true; }
+};
+
+__device__ __forceinline__ u32 row_left_register(u32 row, u32& score, bool& overflow) {
+    u32 a = row & 0xFu, b = (row >> 4) & 0xFu, c = (row >> 8) & 0xFu, d = (row >> 12) & 0xFu;
+#define G2048_CLOSE0 { const bool z = (a == 0u); a = z ? b : a; b = z ? c : b; c = z ? d : c; d = z ? 0u : d; }
+#define G2048_CLOSE1 { const bool z = (b == 0u); b = z ? c : b; c = z ? d : c; d = z ? 0u : d; }
+#define G2048_CLOSE2 { const bool z = (c == 0u); c = z ? d : c; d = z ? 0u : d; }
+    G2048_CLOSE0 G2048_CLOSE0 G2048_CLOSE0 G2048_CLOSE1 G2048_CLOSE1 G2048_CLOSE2
+    const bool m0 = (a != 0u) & (a == b);
+    const bool m1 = (b != 0u) & (b == c) & !m0;
+    const bool m2 = (c != 0u) & (c == d) & !m1;
+    score = (m0 ? (2u << a) : 0u) + (m1 ? (2u << b) : 0u) + (m2 ? (2u << c) : 0u);
+    overflow = (m0 & (a == 15u)) | (m1 & (b == 15u)) | (m2 & (c == 15u));
+    a = m0 ? (a + 1u) & 0xFu : a;
+    if (m0) b = 0u;
+    b = m1 ? (b + 1u) & 0xFu : b;
+    if (m1) c = 0u;
+    c = m2 ? (c + 1u) & 0xFu : c;
+    if (m2) d = 0u;
+    // holes are closed by POSITION, not by value: an overflowed 15+15 merge wraps to nibble 0
+    // but keeps its place, exactly as the packed format defines (include/g2048.h)
+    if (m0) { b = c; c = d; d = 0u; }       // hole at 1
+    if (m1) { c = d; d = 0u; }              // hole at 2
+    if (m0 & m2) { c = 0u; }                // second merge landed at 1, its partner hole at 2
+    return a | (b << 4) | (c << 8) | (d << 12);
+#undef G2048_CLOSE0
+#undef G2048_CLOSE1
+#undef G2048_CLOSE2
+}
+
+__device__ __forceinline__ MoveResult move_left(Board x, const RegisterTable&) {
+    MoveResult r;
+    u32 s0, s1, s2, s3;
+    bool o0, o1, o2, o3;
+    const u32 r0 = row_left_register(x.lo & 0xFFFFu, s0, o0), r1 = row_left_register(x.lo >> 16, s1, o1);
+    const u32 r2 = row_left_register(x.hi & 0xFFFFu, s2, o2), r3 = row_left_register(x.hi >> 16, s3, o3);
+    r.after.lo = r0 | (r1 << 16);
+    r.after.hi = r2 | (r3 << 16);
+    r.score = s0 + s1 + s2 + s3;
+    r.overflow = o0 | o1 | o2 | o3;
+    return r;
+}
+
 // Afterstate of `b` under `action` (0 left, 1 up, 2 right, 3 down): orient so that the move is
 // a left move (transpose for vertical, mirror for right/down), move, undo.
 template <class Table>

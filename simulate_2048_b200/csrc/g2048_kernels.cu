@@ -75,7 +75,7 @@ struct DeviceState {
 };
 static DeviceState g_dev[64];
 static int g_impl = G2048_IMPL_AUTO;
-static int g_step_threads = 1024;  // tuning knob (g2048_set_tuning)
+static int g_step_threads = 512;  // tuning knob (g2048_set_tuning)
 
 static int current_state(DeviceState** out) {
     int dev = 0;
@@ -445,9 +445,16 @@ __global__ void __launch_bounds__(kThreads, 1) step_lut_kernel(const StepArgs a)
 // general step kernel: every optional input, any alignment, table gathered from global/L2.
 // Used for small batches (no 224 KiB staging) and for the rarely used options.
 // ---------------------------------------------------------------------------------------------
-template <bool kPhilox>
+template <class Table>
+__device__ __forceinline__ Table make_table(const u32* tab);
+template <>
+__device__ __forceinline__ GlobalTable make_table<GlobalTable>(const u32* tab) { return GlobalTable{tab}; }
+template <>
+__device__ __forceinline__ RegisterTable make_table<RegisterTable>(const u32*) { return RegisterTable{}; }
+
+template <bool kPhilox, class Table>
 __global__ void __launch_bounds__(256) step_general_kernel(const StepArgs a) {
-    const GlobalTable T{a.table};
+    const Table T = make_table<Table>(a.table);
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n;
          i += (size_t)gridDim.x * blockDim.x) {
         const Board b = split(a.boards_in[i]);
@@ -459,9 +466,9 @@ __global__ void __launch_bounds__(256) step_general_kernel(const StepArgs a) {
         }
         Board nb;
         u32 r, f;
-        transition<GlobalTable, kPhilox>(b, a.actions[i], kPhilox ? 0u : a.spawns[i],
-                                         a.env_keys ? a.env_keys[i] : a.seed, a.env_offset + i,
-                                         a.step_ctr ? a.step_ctr[i] : a.step_base, T, nb, r, f);
+        transition<Table, kPhilox>(b, a.actions[i], kPhilox ? 0u : a.spawns[i],
+                                   a.env_keys ? a.env_keys[i] : a.seed, a.env_offset + i,
+                                   a.step_ctr ? a.step_ctr[i] : a.step_base, T, nb, r, f);
         a.boards_out[i] = join(nb);
         a.rewards[i] = (int)r;
         a.flags[i] = (uint8_t)f;
@@ -527,8 +534,13 @@ extern "C" int g2048_step(const uint64_t* boards_in, const uint8_t* actions, con
 #undef G2048_LAUNCH_STEP
     } else {
         int grid = grid_for(n, 256, s->sms, 8);
-        if (spawns) step_general_kernel<false><<<grid, 256, 0, st>>>(a);
-        else step_general_kernel<true><<<grid, 256, 0, st>>>(a);
+        if (g_impl == G2048_IMPL_REGISTER) {
+            if (spawns) step_general_kernel<false, RegisterTable><<<grid, 256, 0, st>>>(a);
+            else step_general_kernel<true, RegisterTable><<<grid, 256, 0, st>>>(a);
+        } else {
+            if (spawns) step_general_kernel<false, GlobalTable><<<grid, 256, 0, st>>>(a);
+            else step_general_kernel<true, GlobalTable><<<grid, 256, 0, st>>>(a);
+        }
     }
     CU(cudaGetLastError());
     return G2048_OK;
@@ -1169,8 +1181,8 @@ extern "C" int g2048_row_table_host(uint16_t* result, uint32_t* reward, uint8_t*
 // ---------------------------------------------------------------------------------------------
 namespace {
 struct HostPipe {
-    static constexpr int kSlots = 3;
-    static constexpr size_t kChunk = (size_t)1 << 22;  // 4 Mi envs / chunk: 40 MB in, 52 MB out
+    static constexpr int kSlots = 4;
+    static constexpr size_t kChunk = (size_t)1 << 20;  // 1 Mi envs / chunk: 10 MB in, 13 MB out
     bool ready = false;
     cudaStream_t stream[kSlots];
     uint64_t *d_in[kSlots], *d_out[kSlots];

@@ -94,11 +94,11 @@ def test_mask_matches_reference(T, ops, golden):
 
 # ------------------------------------------------------------------ oracle parity, every code path
 
-@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('impl', [0, 1, 2])
 @pytest.mark.parametrize('n', [1, 5, 4096, 4096 * 3 + 17, (1 << 20) + 37])
 def test_step_injected_vs_oracle(T, ops, oracle, n, impl):
     """impl 0 = auto (general kernel below 2^18 envs, smem-table kernel above), 1 = smem table
-    forced (covers its ragged tail at every size)."""
+    forced (covers its ragged tail at every size), 2 = pure register arithmetic (no table)."""
     boards = synthetic_packed(n, seed=100 + n % 7)
     rng = np.random.default_rng(n)
     actions = rng.integers(0, 4, n).astype(np.uint8)
@@ -114,7 +114,7 @@ def test_step_injected_vs_oracle(T, ops, oracle, n, impl):
     np.testing.assert_array_equal(fl, o_fl)
 
 
-@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('impl', [0, 1, 2])
 @pytest.mark.parametrize('n', [3, 4096 + 5, (1 << 19) + 3])
 def test_step_philox_vs_oracle(T, ops, oracle, n, impl):
     boards = synthetic_packed(n, seed=55)
@@ -153,7 +153,7 @@ def test_step_optional_inputs_vs_oracle(T, ops, oracle):
 
 def test_step_big_tiles_overflow_and_slow_path(T, ops, oracle):
     """Exponents up to 15: rows outside the staged table window and 15+15 merges must be exact,
-    in both the general and the smem-table kernel."""
+    in the general, the smem-table and the register-arithmetic kernel."""
     n = (1 << 18) + 11
     boards = synthetic_packed(n, seed=9, max_exp=15)
     # force plenty of 15+15 pairs
@@ -162,7 +162,7 @@ def test_step_big_tiles_overflow_and_slow_path(T, ops, oracle):
     spawns = valid_spawn_bytes(afterstates(oracle, boards, actions), seed=4)
     o = oracle.step(boards, actions, spawns)
     assert (o[2] & FLAG_OVERFLOW).any()
-    for impl in (0, 1):
+    for impl in (0, 1, 2):
         ops.set_impl(impl)
         try:
             got = run_step(T, ops, boards, actions, spawns)
