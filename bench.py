@@ -260,7 +260,7 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     ops.init(local)
     if os.environ.get('G2048_STEP_THREADS'):
-        ops.set_tuning(int(os.environ['G2048_STEP_THREADS']))
+        ops.set_tuning(int(os.environ['G2048_STEP_THREADS']), int(os.environ.get('G2048_STEP_ENVS', '4')))
 
     def barrier():
         if world > 1:
@@ -465,7 +465,24 @@ def run_ours(args):
     return 0
 
 
+def _quiet_stdout():
+    """Route fd 1 to stderr (NCCL prints a version banner on stdout) and return a file object on
+    the real stdout for the single JSON line."""
+    real = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    global print
+    real_stdout = _quiet_stdout()
+    import builtins
+
+    def print(*a, **kw):  # noqa: A001 - only the JSON line reaches the real stdout
+        if kw.get('file') is None:
+            kw['file'] = real_stdout
+        builtins.print(*a, **kw)
+
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)

@@ -96,8 +96,9 @@ const char* g2048_last_cuda_error(void); /* thread-local text of the last CUDA f
 int g2048_init(int device);
 /* Select the row-move implementation used by g2048_step/g2048_env_step (process-wide). */
 int g2048_set_impl(int impl);
-/* Tuning knob: threads per CTA of the smem-table step kernel (512, 768 or 1024; one CTA per SM). */
-int g2048_set_tuning(int step_threads);
+/* Tuning knobs of the smem-table step kernel: threads per CTA (512, 768 or 1024; one CTA per
+ * SM) and consecutive envs per thread (4 or 8). */
+int g2048_set_tuning(int step_threads, int envs_per_thread);
 
 /*
  * Raw transition: replaces gameboard.py:291 next_state (+ is_done :328, gamemove.py:45

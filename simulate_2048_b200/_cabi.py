@@ -32,7 +32,7 @@ PROTOTYPES = {
     'g2048_last_cuda_error': (C.c_char_p, []),
     'g2048_init': (C.c_int, [C.c_int]),
     'g2048_set_impl': (C.c_int, [C.c_int]),
-    'g2048_set_tuning': (C.c_int, [C.c_int]),
+    'g2048_set_tuning': (C.c_int, [C.c_int, C.c_int]),
     'g2048_step': (C.c_int, [_P, _P, _P, _U64, _U64, _P, _U32, _P, _P, _P, _P, _P, _SZ, _P]),
     'g2048_env_step': (C.c_int, [_P, _P, _P, _P, _P, _P, _U64, _U64, _P, _P, _P, _P, _P, _SZ, _P]),
     'g2048_mask': (C.c_int, [_P, _P, _SZ, _P]),

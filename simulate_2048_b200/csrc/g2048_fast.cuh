@@ -231,34 +231,54 @@ struct FastOut {
 //   Preconditions (checked by the caller): !has_big_tile(lo, hi).
 //   rank = spawn rank among the empties (injected) — ignored when kPhilox (then w0 draws it);
 //   exp  = spawned exponent (1 or 2);  one = the run-time constant 1 (see add()).
-template <bool kPhilox, class Lut>
-G2048_HD FastOut transition_fast(u32 lo, u32 hi, const Orient& o, u32 rank, u32 exp, u32 w0,
-                                 const Lut& lut, u32 one) {
-    // ---- move: orient, hash, 4 row lookups, un-orient ----
+// ---- building blocks (also used by the fused rollout kernel) ---------------------------------
+
+// Afterstate of (lo,hi) under the action whose orientation words are `o`.  Returns the merge
+// score; `moved` is evaluated in the oriented frame (core.py:258).
+template <class Lut>
+G2048_HD u32 move_fast(u32 lo, u32 hi, const Orient& o, const Lut& lut, u32 one, u32& al, u32& ah,
+                       bool& moved) {
     u32 xl = lo, xh = hi;
     orient_forward(xl, xh, o);
     const u32 yl = hash_rows(xl), yh = hash_rows(xh);
     const u32 e0 = lut(yl & 0xFFFFu), e1 = lut(prmt(yl, 0u, 0x4432u));
     const u32 e2 = lut(yh & 0xFFFFu), e3 = lut(prmt(yh, 0u, 0x4432u));
-    u32 al = prmt(e0, e1, 0x7632), ah = prmt(e2, e3, 0x7632);
-    const bool moved = (al != xl) | (ah != xh);  // core.py:258, tested before un-orienting
+    al = prmt(e0, e1, 0x7632);
+    ah = prmt(e2, e3, 0x7632);
+    moved = (al != xl) | (ah != xh);
     const u32 reward = (add(add(e0, e1, one), add(e2, e3, one), one) << 2) & 0x3FFFCu;
     orient_backward(al, ah, o);
+    return reward;
+}
 
-    // ---- spawn on the rank-th empty cell (row-major) of the afterstate ----
-    // Inclusive prefix count of EMPTY cells at nibble k of a half = (k + 1) - prefix(tiles), so
-    // with t = tiles indicator at bit 0:  g = 0x87654321 + (7 - r)*0x11111111 - t*0x11111111
-    // has bit 3 set exactly in the nibbles whose empty-count exceeds r (all nibbles stay <= 15).
-    u32 nlo = nz8(al, one), nhi = nz8(ah, one);
-    const u32 tiles_lo = popc(nlo), tiles = tiles_lo + popc(nhi);
-    const u32 clo = 8u - tiles_lo, ne = 16u - tiles;
-    if (kPhilox) rank = mulhi(w0, ne);
-    const bool ok = rank < ne;
-    const bool in_hi = rank >= clo;
+// Marker (bit 3 of the target nibble, in the half `in_hi` selects) of the rank-th empty cell in
+// row-major order, given the non-empty indicators and tile counts of the two halves.
+// Inclusive prefix count of EMPTY cells at nibble k of a half = (k + 1) - prefix(tiles), so with
+// t = tile indicators at bit 0:  g = 0x87654321 + (7 - r)*0x11111111 - t*0x11111111  has bit 3
+// set exactly in the nibbles whose empty-count exceeds r (every nibble stays <= 15).
+G2048_HD u32 spawn_marker(u32 nlo, u32 nhi, u32 tiles_lo, u32 rank, bool& in_hi) {
+    const u32 clo = 8u - tiles_lo;
+    in_hi = rank >= clo;
     const u32 nsel = in_hi ? nhi : nlo;
     const u32 r = in_hi ? rank - clo : rank;
     const u32 g = mad(shr<3>(nsel), 0xEEEEEEEFu, mad(r, 0xEEEEEEEFu, 0xFEDCBA98u)) & 0x88888888u;
-    const u32 bit3 = g & (0u - g);               // bit 3 of the target nibble
+    return g & (0u - g);
+}
+
+template <bool kPhilox, class Lut>
+G2048_HD FastOut transition_fast(u32 lo, u32 hi, const Orient& o, u32 rank, u32 exp, u32 w0,
+                                 const Lut& lut, u32 one) {
+    u32 al, ah;
+    bool moved;
+    const u32 reward = move_fast(lo, hi, o, lut, one, al, ah, moved);
+
+    // ---- spawn on the rank-th empty cell (row-major) of the afterstate ----
+    u32 nlo = nz8(al, one), nhi = nz8(ah, one);
+    const u32 tiles_lo = popc(nlo), ne = 16u - (tiles_lo + popc(nhi));
+    if (kPhilox) rank = mulhi(w0, ne);
+    const bool ok = rank < ne;
+    bool in_hi;
+    const u32 bit3 = spawn_marker(nlo, nhi, tiles_lo, rank, in_hi);
     const u32 tile = shr<3>(bit3) * exp;         // exponent 1 or 2 at bit 0 of that nibble
     if (moved & ok) {
         if (in_hi) { ah += tile; nhi += bit3; } else { al += tile; nlo += bit3; }

@@ -23,6 +23,8 @@
 
 using namespace g2048;
 
+__constant__ g2048::fast::Orient c_orient[4] = G2048_ORIENT_TABLE;
+
 // ---------------------------------------------------------------------------------------------
 // error plumbing
 // ---------------------------------------------------------------------------------------------
@@ -75,7 +77,8 @@ struct DeviceState {
 };
 static DeviceState g_dev[64];
 static int g_impl = G2048_IMPL_AUTO;
-static int g_step_threads = 512;  // tuning knob (g2048_set_tuning)
+static int g_step_threads = 512;
+static int g_step_groups = 1;   // groups of 4 envs per thread (1 or 2)  // tuning knob (g2048_set_tuning)
 
 static int current_state(DeviceState** out) {
     int dev = 0;
@@ -116,9 +119,11 @@ extern "C" int g2048_init(int device) {
     return current_state(&s);
 }
 
-extern "C" int g2048_set_tuning(int step_threads) {
+extern "C" int g2048_set_tuning(int step_threads, int envs_per_thread) {
     if (step_threads != 512 && step_threads != 768 && step_threads != 1024) return G2048_EINVAL;
+    if (envs_per_thread != 4 && envs_per_thread != 8) return G2048_EINVAL;
     g_step_threads = step_threads;
+    g_step_groups = envs_per_thread / 4;
     return G2048_OK;
 }
 
@@ -278,7 +283,6 @@ struct StepArgs {
 // ---------------------------------------------------------------------------------------------
 // fast step kernel: smem table, 4 envs / thread, persistent, double buffered
 // ---------------------------------------------------------------------------------------------
-constexpr int kEnvsPerThread = 4;
 
 struct TileIn {
     Boards4 boards;
@@ -306,7 +310,6 @@ __device__ __noinline__ uint4 transition_slow(u64 board, u32 action, u32 spawn, 
     return make_uint4(nb.lo, nb.hi, reward, flags);
 }
 
-__constant__ fast::Orient c_orient[4] = G2048_ORIENT_TABLE;
 
 struct SmemLut {
     const u32* tab;  // staged table in shared memory, indexed by WORD: LDS R, [R*4 + UR]
@@ -371,16 +374,49 @@ __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 s
 
 constexpr u32 kStepSmemBytes = kSmemTableBytes + 64u + 4u * (u32)sizeof(fast::Orient);
 
+// kGroups groups of four consecutive envs per thread (4 or 8 envs): more independent work per
+// warp for the scheduler and less per-env decode / address / loop overhead.
+template <bool kPhilox, int kGroups>
+struct TileBuf {
+    TileIn g[kGroups];
+};
+
+template <bool kPhilox, int kGroups>
+__device__ __forceinline__ void load_tiles(TileBuf<kPhilox, kGroups>& t, const StepArgs& a, size_t env0) {
+#pragma unroll
+    for (int j = 0; j < kGroups; ++j) t.g[j] = load_tile<kPhilox>(a, env0 + 4 * j);
+}
+
+template <bool kPhilox, int kGroups>
+__device__ __forceinline__ void compute_store_tiles(const TileBuf<kPhilox, kGroups>& t, const StepArgs& a,
+                                                    size_t env0, const SmemLut& lut,
+                                                    const uint4* __restrict__ s_orient) {
+    Boards4 ob[kGroups];
+    int4 rw[kGroups];
+    u32 fl[kGroups];
+#pragma unroll
+    for (int j = 0; j < kGroups; ++j)
+        step_tile4<kPhilox>(t.g[j].boards, t.g[j].actions, t.g[j].spawns, a, a.env_offset + env0 + 4 * j,
+                            lut, s_orient, ob[j], rw[j], fl[j]);
+#pragma unroll
+    for (int j = 0; j < kGroups; ++j) {
+        st_boards4(a.boards_out + env0 + 4 * j, ob[j]);
+        st_int4_stream(a.rewards + env0 + 4 * j, rw[j]);
+        st_u32_stream(a.flags + env0 + 4 * j, fl[j]);
+    }
+}
+
 // Persistent CTA (one per SM).  Each CTA owns a CONTIGUOUS range of tiles so that the next tile
 // of every stream is a compile-time offset away; the loop is unrolled by two tiles that ping-pong
 // between two register buffers (the loads of one tile are in flight while the other computes).
-template <bool kPhilox, int kThreads>
+template <bool kPhilox, int kThreads, int kGroups>
 __global__ void __launch_bounds__(kThreads, 1) step_lut_kernel(const StepArgs a) {
     extern __shared__ __align__(128) u32 smem_words[];
     u32* smem_tab = smem_words;
     u64* bar = reinterpret_cast<u64*>(smem_words + kSmemRows);
     uint4* s_orient = reinterpret_cast<uint4*>(smem_words + kSmemRows + 16);
-    constexpr size_t kTile = (size_t)kThreads * kEnvsPerThread;
+    constexpr size_t kPerThread = 4 * kGroups;
+    constexpr size_t kTile = (size_t)kThreads * kPerThread;
 
     table_stage_begin(smem_tab, bar, a.table_hashed);
     if (threadIdx.x < 32)
@@ -389,55 +425,33 @@ __global__ void __launch_bounds__(kThreads, 1) step_lut_kernel(const StepArgs a)
     const size_t full_tiles = a.n / kTile;
     const size_t t_begin = full_tiles * blockIdx.x / gridDim.x;
     const size_t t_end = full_tiles * (blockIdx.x + 1) / gridDim.x;
-    size_t env0 = t_begin * kTile + threadIdx.x * kEnvsPerThread;
+    size_t env0 = t_begin * kTile + threadIdx.x * kPerThread;
     const size_t env_end = t_end * kTile;
 
-    TileIn bufA, bufB;
-    if (env0 < env_end) bufA = load_tile<kPhilox>(a, env0);
+    TileBuf<kPhilox, kGroups> bufA, bufB;
+    if (env0 < env_end) load_tiles(bufA, a, env0);
 
     table_stage_wait(bar);  // __syncthreads inside also publishes s_orient
     const SmemLut lut{smem_tab};
 
     while (env0 < env_end) {
-        // tile A computes while tile B loads
         const bool hasB = env0 + kTile < env_end;
-        if (hasB) bufB = load_tile<kPhilox>(a, env0 + kTile);
-        {
-            Boards4 ob;
-            int4 rw;
-            u32 fl;
-            step_tile4<kPhilox>(bufA.boards, bufA.actions, bufA.spawns, a, a.env_offset + env0, lut,
-                                s_orient, ob, rw, fl);
-            st_boards4(a.boards_out + env0, ob);
-            st_int4_stream(a.rewards + env0, rw);
-            st_u32_stream(a.flags + env0, fl);
-        }
+        if (hasB) load_tiles(bufB, a, env0 + kTile);          // tile B loads while tile A computes
+        compute_store_tiles(bufA, a, env0, lut, s_orient);
         if (!hasB) break;
-        // tile B computes while the next tile A loads
-        if (env0 + 2 * kTile < env_end) bufA = load_tile<kPhilox>(a, env0 + 2 * kTile);
-        {
-            Boards4 ob;
-            int4 rw;
-            u32 fl;
-            step_tile4<kPhilox>(bufB.boards, bufB.actions, bufB.spawns, a, a.env_offset + env0 + kTile,
-                                lut, s_orient, ob, rw, fl);
-            st_boards4(a.boards_out + env0 + kTile, ob);
-            st_int4_stream(a.rewards + env0 + kTile, rw);
-            st_u32_stream(a.flags + env0 + kTile, fl);
-        }
+        if (env0 + 2 * kTile < env_end) load_tiles(bufA, a, env0 + 2 * kTile);
+        compute_store_tiles(bufB, a, env0 + kTile, lut, s_orient);
         env0 += 2 * kTile;
     }
 
-    // ragged tail (< one tile): CTA 0, one env per thread-iteration through the exact path
-    if (blockIdx.x == 0) {
-        for (size_t i = full_tiles * kTile + threadIdx.x; i < a.n; i += kThreads) {
-            const uint4 r = transition_slow<kPhilox>(a.boards_in[i], a.actions[i],
-                                                     kPhilox ? 0u : a.spawns[i], a.seed,
-                                                     a.env_offset + i, a.step_base, a.table);
-            a.boards_out[i] = ((u64)r.y << 32) | r.x;
-            a.rewards[i] = (int)r.z;
-            a.flags[i] = (uint8_t)r.w;
-        }
+    // ragged tail (< one tile): spread over the CTAs, one env per thread through the exact path
+    for (size_t i = full_tiles * kTile + blockIdx.x * (size_t)kThreads + threadIdx.x; i < a.n;
+         i += (size_t)gridDim.x * kThreads) {
+        const uint4 r = transition_slow<kPhilox>(a.boards_in[i], a.actions[i], kPhilox ? 0u : a.spawns[i],
+                                                 a.seed, a.env_offset + i, a.step_base, a.table);
+        a.boards_out[i] = ((u64)r.y << 32) | r.x;
+        a.rewards[i] = (int)r.z;
+        a.flags[i] = (uint8_t)r.w;
     }
 }
 
@@ -513,24 +527,30 @@ extern "C" int g2048_step(const uint64_t* boards_in, const uint8_t* actions, con
 
     if (use_lut) {
         const int smem = (int)kStepSmemBytes;
-        const int threads = g_step_threads;
-        const size_t tiles = n / ((size_t)threads * kEnvsPerThread);
+        const int threads = g_step_threads, groups = g_step_groups;
+        const size_t tiles = n / ((size_t)threads * 4 * groups);
         const int grid = (int)(tiles < (size_t)s->sms ? (tiles ? tiles : 1) : (size_t)s->sms);
-#define G2048_LAUNCH_STEP(PH, TH)                                                                     \
-    do {                                                                                              \
-        CU(cudaFuncSetAttribute(step_lut_kernel<PH, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                smem));                                                               \
-        step_lut_kernel<PH, TH><<<grid, TH, smem, st>>>(a);                                           \
+#define G2048_LAUNCH_STEP(PH, TH, GR)                                                                     \
+    do {                                                                                                  \
+        CU(cudaFuncSetAttribute(step_lut_kernel<PH, TH, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                smem));                                                                   \
+        step_lut_kernel<PH, TH, GR><<<grid, TH, smem, st>>>(a);                                           \
     } while (0)
-        if (spawns) {
-            if (threads == 512) G2048_LAUNCH_STEP(false, 512);
-            else if (threads == 768) G2048_LAUNCH_STEP(false, 768);
-            else G2048_LAUNCH_STEP(false, 1024);
-        } else {
-            if (threads == 512) G2048_LAUNCH_STEP(true, 512);
-            else if (threads == 768) G2048_LAUNCH_STEP(true, 768);
-            else G2048_LAUNCH_STEP(true, 1024);
-        }
+#define G2048_LAUNCH_STEP_T(PH)                                          \
+    do {                                                                 \
+        if (groups == 2) {                                               \
+            if (threads == 512) G2048_LAUNCH_STEP(PH, 512, 2);           \
+            else if (threads == 768) G2048_LAUNCH_STEP(PH, 768, 2);      \
+            else G2048_LAUNCH_STEP(PH, 1024, 2);                         \
+        } else {                                                         \
+            if (threads == 512) G2048_LAUNCH_STEP(PH, 512, 1);           \
+            else if (threads == 768) G2048_LAUNCH_STEP(PH, 768, 1);      \
+            else G2048_LAUNCH_STEP(PH, 1024, 1);                         \
+        }                                                                \
+    } while (0)
+        if (spawns) G2048_LAUNCH_STEP_T(false);
+        else G2048_LAUNCH_STEP_T(true);
+#undef G2048_LAUNCH_STEP_T
 #undef G2048_LAUNCH_STEP
     } else {
         int grid = grid_for(n, 256, s->sms, 8);
@@ -983,6 +1003,8 @@ struct RolloutArgs {
     uint8_t* trace;
     u32 trace_stride;
     const u32* table;
+    const u32* table_hashed;
+    u32 one;
 };
 
 // idx-th set bit (0-based) of a 4-bit mask
@@ -995,16 +1017,34 @@ __device__ __forceinline__ u32 pick_action(u32 mask, u32 idx) {
 // game, so the step code runs convergent; lanes whose game ended pull the next env id at the
 // top of the loop (one warp-aggregated atomic for all lanes that need one).  Results are
 // keyed by the global env id and step, so they do not depend on which lane played the game.
-template <class Table>
-__device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const Table& T, u64* sh_stats,
+//
+// The step itself is the fast transition of g2048_fast.cuh (hashed table + per-action
+// orientation words in shared memory); boards holding a tile >= 16384 take the exact path.
+// pick[mask * 4 + k] = k-th legal action of `mask` (64-byte table, branch-free policy).
+struct RolloutSmem {
+    const u32* tab;          // hashed row table (fast path)
+    const uint4* orient;     // per-action orientation words
+    const uint8_t* pick;     // action pick table
+    u64* stats;              // per-CTA statistics (or nullptr)
+};
+
+__device__ __noinline__ uint4 rollout_move_slow(u64 board, u32 action, const u32* __restrict__ table) {
+    MoveResult m = move_action(split(board), action, GlobalTable{table});
+    return make_uint4(m.after.lo, m.after.hi, m.score, m.overflow ? 1u : 0u);
+}
+
+template <bool kFast>
+__device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RolloutSmem& sm,
                                              unsigned long long* next) {
     const u32 lane = threadIdx.x & 31u;
     const u32 FULL = 0xFFFFFFFFu;
+    const u32 one = a.one;
     bool active = false, exhausted = false;
     size_t i = 0;
     u64 env = 0, score = 0;
-    Board b{0u, 0u};
+    u32 lo = 0, hi = 0;
     u32 step = 0, ovf = 0, mask = 0, nlo = 0, nhi = 0;
+    const SmemLut lut{sm.tab};
     for (;;) {
         const u32 need = __ballot_sync(FULL, !active && !exhausted);
         if (need) {
@@ -1016,13 +1056,15 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const Table& 
                 i = (size_t)base + __popc(need & ((1u << lane) - 1u));
                 if (i < a.n) {
                     env = a.env_offset + i;
-                    b = a.from_reset ? reset_board(a.seed, env, nullptr) : split(a.boards_io[i]);
+                    const Board b = a.from_reset ? reset_board(a.seed, env, nullptr) : split(a.boards_io[i]);
+                    lo = b.lo;
+                    hi = b.hi;
                     score = 0;
                     step = 0;
                     ovf = 0;
-                    nlo = nz8(b.lo);
-                    nhi = nz8(b.hi);
-                    mask = legal_mask(b, nlo, nhi);
+                    nlo = fast::nz8(lo, one);
+                    nhi = fast::nz8(hi, one);
+                    mask = fast::legal_mask(lo, hi, nlo, nhi, one);
                     active = true;
                 } else {
                     exhausted = true;
@@ -1033,65 +1075,79 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const Table& 
         if (!active) continue;
         if (mask == 0u || step >= a.max_steps) {  // game over: emit the episode
             if (a.trace) a.trace[i * a.trace_stride + min(step, a.trace_stride - 1u)] = 0;
-            const u32 mx = max_exponent(b);
-            if (a.boards_io) a.boards_io[i] = join(b);
+            const u32 mx = max_exponent(Board{lo, hi});
+            if (a.boards_io) a.boards_io[i] = ((u64)hi << 32) | lo;
             if (a.score_out) a.score_out[i] = (int64_t)score;
             if (a.steps_out) a.steps_out[i] = (int32_t)step;
             if (a.maxexp_out) a.maxexp_out[i] = (uint8_t)mx;
-            if (sh_stats) {
-                atomicAdd(&sh_stats[0], 1ull);
-                atomicAdd(&sh_stats[1], (u64)step);
-                atomicAdd(&sh_stats[2], score);
-                atomicMax(&sh_stats[3], score);
-                atomicMax(&sh_stats[4], (u64)step);
-                if (mask != 0u) atomicAdd(&sh_stats[5], 1ull);
-                if (ovf) atomicAdd(&sh_stats[6], 1ull);
-                atomicAdd(&sh_stats[8 + mx], 1ull);
+            if (sm.stats) {
+                atomicAdd(&sm.stats[0], 1ull);
+                atomicAdd(&sm.stats[1], (u64)step);
+                atomicAdd(&sm.stats[2], score);
+                atomicMax(&sm.stats[3], score);
+                atomicMax(&sm.stats[4], (u64)step);
+                if (mask != 0u) atomicAdd(&sm.stats[5], 1ull);
+                if (ovf) atomicAdd(&sm.stats[6], 1ull);
+                atomicAdd(&sm.stats[8 + mx], 1ull);
             }
             active = false;
             continue;
         }
         // one step: uniform-legal action (word2), move, spawn (words 0/1), new mask
         const Philox4 p = philox_env(a.seed, env, step, G2048_PHILOX_TAG_STEP);
-        const u32 action = pick_action(mask, __umulhi(p.z, (u32)__popc(mask)));
-        MoveResult m = move_action(b, action, T);
-        b = m.after;
-        score += m.score;
-        ovf |= m.overflow ? 1u : 0u;
-        nlo = nz8(b.lo);
-        nhi = nz8(b.hi);
-        const u32 zlo = (~nlo >> 3) & 0x11111111u, zhi = (~nhi >> 3) & 0x11111111u;
-        const u32 clo = __popc(zlo), ne = clo + __popc(zhi);
-        const u32 rank = __umulhi(p.x, ne);
-        const u32 exp = p.y < G2048_PHILOX_FOUR_THRESHOLD ? 2u : 1u;
-        const bool in_hi = rank >= clo;
-        const u32 z = in_hi ? zhi : zlo, r = in_hi ? rank - clo : rank;
-        const u32 g = (z * 0x11111111u + (0x77777777u - r * 0x11111111u)) & 0x88888888u;
-        const u32 bit3 = g & (0u - g);
-        const u32 tile = (bit3 >> 3) * exp;
-        if (in_hi) { b.hi |= tile; nhi |= bit3; } else { b.lo |= tile; nlo |= bit3; }
+        const u32 action = sm.pick[mask * 4u + __umulhi(p.z, (u32)__popc(mask))];
+        u32 al, ah, reward;
+        if (kFast && !fast::has_big_tile(lo, hi)) {
+            const uint4 o0 = sm.orient[2u * action], o1 = sm.orient[2u * action + 1u];
+            fast::Orient o;
+            o.mt = o0.x; o.mr = o0.y; o.f_lo = o0.z; o.f_hi = o0.w; o.b_lo = o1.x; o.b_hi = o1.y;
+            bool moved;
+            reward = fast::move_fast(lo, hi, o, lut, one, al, ah, moved);
+        } else {
+            const uint4 r = rollout_move_slow(((u64)hi << 32) | lo, action, a.table);
+            al = r.x; ah = r.y; reward = r.z; ovf |= r.w;
+        }
+        score += reward;
+        nlo = fast::nz8(al, one);
+        nhi = fast::nz8(ah, one);
+        const u32 tiles_lo = fast::popc(nlo), ne = 16u - (tiles_lo + fast::popc(nhi));
+        bool in_hi;
+        const u32 bit3 = fast::spawn_marker(nlo, nhi, tiles_lo, __umulhi(p.x, ne), in_hi);
+        const u32 exp = 2u - fast::nonzero01(__umulhi(p.y, 10u));  // word1 < 0x1999999A -> 4
+        const u32 tile = fast::shr<3>(bit3) * exp;
+        if (in_hi) { ah += tile; nhi += bit3; } else { al += tile; nlo += bit3; }
+        lo = al;
+        hi = ah;
         if (a.trace && step + 1u < a.trace_stride) {
             const u32 cell = ((__ffs(bit3) - 1u) >> 2) + (in_hi ? 8u : 0u);
             a.trace[i * a.trace_stride + step] =
                 (uint8_t)(0x80u | action | (cell << 2) | ((exp - 1u) << 6));
         }
         ++step;
-        mask = legal_mask(b, nlo, nhi);
+        mask = fast::legal_mask(lo, hi, nlo, nhi, one);
     }
 }
 
+// pick[mask * 4 + k] = k-th set bit of the 4-bit mask
+__constant__ uint8_t c_pick[64] = {
+    0, 0, 0, 0,  0, 0, 0, 0,  1, 0, 0, 0,  0, 1, 0, 0,  2, 0, 0, 0,  0, 2, 0, 0,  1, 2, 0, 0,  0, 1, 2, 0,
+    3, 0, 0, 0,  0, 3, 0, 0,  1, 3, 0, 0,  0, 1, 3, 0,  2, 3, 0, 0,  0, 2, 3, 0,  1, 2, 3, 0,  0, 1, 2, 3};
+
 template <bool kSmem>
-__global__ void __launch_bounds__(512, 1) rollout_kernel(const RolloutArgs a, unsigned long long* next) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+__global__ void __launch_bounds__(1024, 1) rollout_kernel(const RolloutArgs a, unsigned long long* next) {
+    extern __shared__ __align__(128) u32 smem_words[];
     __shared__ u64 sh_stats[G2048_STATS_WORDS];
-    u32* smem_tab = reinterpret_cast<u32*>(smem_raw);
-    u64* bar = reinterpret_cast<u64*>(smem_raw + kSmemTableBytes);
-    if (kSmem) table_stage_begin(smem_tab, bar, a.table);
+    __shared__ __align__(16) uint4 sh_orient[8];
+    __shared__ uint8_t sh_pick[64];
+    u64* bar = reinterpret_cast<u64*>(smem_words + kSmemRows);
+    if (kSmem) table_stage_begin(smem_words, bar, a.table_hashed);
     if (threadIdx.x < G2048_STATS_WORDS) sh_stats[threadIdx.x] = 0;
+    if (threadIdx.x < 32) reinterpret_cast<u32*>(sh_orient)[threadIdx.x] = reinterpret_cast<const u32*>(c_orient)[threadIdx.x];
+    if (threadIdx.x < 64) sh_pick[threadIdx.x] = c_pick[threadIdx.x];
     if (kSmem) table_stage_wait(bar); else __syncthreads();
 
-    if (kSmem) rollout_loop(a, SmemTable{smem_tab, a.table}, a.stats ? sh_stats : nullptr, next);
-    else rollout_loop(a, GlobalTable{a.table}, a.stats ? sh_stats : nullptr, next);
+    const RolloutSmem sm{smem_words, sh_orient, sh_pick, a.stats ? sh_stats : nullptr};
+    rollout_loop<kSmem>(a, sm, next);
 
     __syncthreads();
     if (a.stats && threadIdx.x < G2048_STATS_WORDS) {
@@ -1114,7 +1170,7 @@ extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint3
     cudaStream_t st = (cudaStream_t)stream;
     RolloutArgs a{seed, env_offset, n, max_steps, from_reset, reinterpret_cast<u64*>(boards_io),
                   score_out, steps_out, maxexp_out, reinterpret_cast<u64*>(stats_out), trace,
-                  trace_stride, s->table};
+                  trace_stride, s->table, s->table_hashed, 1u};
     unsigned long long* next = nullptr;
     CU(cudaMallocAsync(&next, sizeof(unsigned long long), st));
     CU(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
@@ -1122,7 +1178,7 @@ extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint3
     if (smem) {
         const int bytes = (int)kSmemTableBytes + 64;
         CU(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        rollout_kernel<true><<<s->sms, 512, bytes, st>>>(a, next);
+        rollout_kernel<true><<<s->sms, 1024, bytes, st>>>(a, next);
     } else {
         int grid = grid_for(n, 512, s->sms, 1);
         rollout_kernel<false><<<grid, 512, 0, st>>>(a, next);

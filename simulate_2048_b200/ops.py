@@ -66,8 +66,8 @@ def set_impl(impl: int) -> None:
     check(lib().g2048_set_impl(int(impl)))
 
 
-def set_tuning(step_threads: int) -> None:
-    check(lib().g2048_set_tuning(int(step_threads)))
+def set_tuning(step_threads: int, envs_per_thread: int = 4) -> None:
+    check(lib().g2048_set_tuning(int(step_threads), int(envs_per_thread)))
 
 
 class StepOut(NamedTuple):
