@@ -424,13 +424,27 @@ def run_ours(args):
         extra['register_arithmetic_variant'] = {'env_steps_per_sec': B / r_mean,
                                                 'achieved_gbs': BYTES_INJECTED * B / r_mean / 1e9,
                                                 'frac': BYTES_INJECTED * B / r_mean / 1e9 / peak}
-        # config 3: MCTS leaf expansion, 65536 boards, compact children
-        eb = boards[:65536].contiguous()
-        ex = ops.expand(eb, children='compact')
-        n_children = int(ex.children.numel())
-        _, ex_mean, _ = timed(lambda: ops.expand(eb, children='dense'), 50, 5)
-        extra['expand_65536'] = {'boards_per_sec': 65536 / ex_mean, 'children_per_board': n_children / 65536,
-                                 'us_per_call': ex_mean * 1e6, 'layout': 'dense [N,4,16,2]'}
+        # config 3: MCTS leaf expansion (mask + 4 afterstates + all chance children), 65536 boards and 1M
+        exp_out = {}
+        for n_e in (65536, 1 << 20):
+            eb = boards[:n_e].contiguous()
+            ex_c = ops.expand(eb, children='compact')
+            ex_d = ops.expand(eb, children='dense', zero_fill=False)
+            n_children = int(ex_c.children.numel())
+            reps = 40 if n_e == 65536 else 10
+            _, t_c, _ = timed(lambda: ops.expand(eb, children='compact', out=ex_c), reps, 3)
+            _, t_d, _ = timed(lambda: ops.expand(eb, children='dense', out=ex_d), reps, 3)
+            bytes_c = n_e * (8 + 8 + 1 + 32 + 16 + 4 + 4) + 8 * n_children
+            exp_out[str(n_e)] = {
+                'children_per_board': n_children / n_e,
+                'compact': {'us_per_launch': t_c * 1e6, 'boards_per_sec': n_e / t_c, 'children_per_sec': n_children / t_c,
+                            'algorithmic_gbs': bytes_c / t_c / 1e9, 'frac_of_hbm_peak': bytes_c / t_c / 1e9 / peak},
+                'dense': {'us_per_launch': t_d * 1e6, 'boards_per_sec': n_e / t_d},
+            }
+            del ex_c, ex_d
+        exp_out['note'] = ('g2048_expand into preallocated outputs; compact = children packed at child_offsets '
+                           '(offsets from a count pass + cumsum, not timed), dense = [N,4,16,2] slots')
+        extra['expand'] = exp_out
         # config 4: fused rollouts to termination
         n_roll = 1 << 20
         ro = ops.rollout(n_roll, seed=1, per_env=False)

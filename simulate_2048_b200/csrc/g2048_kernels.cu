@@ -849,12 +849,6 @@ struct ExpandArgs {
     const u32* table;
 };
 
-// position (0..15) of the k-th set bit of a 16-bit cell mask
-__device__ __forceinline__ u32 kth_set_bit16(u32 m, u32 k) {
-    for (u32 i = 0; i < k; ++i) m &= m - 1u;
-    return __ffs(m) - 1u;
-}
-
 __device__ __forceinline__ u32 empty_cells16(Board b) {
     // one bit per cell: gather bit 3 of every nibble of ~nz8
     const u32 zlo = (~nz8(b.lo)) & 0x88888888u, zhi = (~nz8(b.hi)) & 0x88888888u;
@@ -867,19 +861,31 @@ __device__ __forceinline__ u32 empty_cells16(Board b) {
     return m;
 }
 
-__global__ void __launch_bounds__(256) expand_kernel(const ExpandArgs a) {
+// Two phases per warp-tile of 32 boards.
+//   1. lane = board: the four afterstates (the transposed board is shared by up and down),
+//      rewards, counts, mask; the fixed-size outputs are written with 128-bit stores and a
+//      16-byte record {after.lo, after.hi, n_lo, n_hi} per (board, action) goes to shared memory.
+//   2. lane = child: for every legal (board, action) the warp writes the child segment
+//      coalesced; lane j builds child j (empty cell j/2 in row-major order, tile 2 then 4:
+//      gameboard.py:154,162) with the branch-free rank select of g2048_fast.cuh.
+constexpr int kExpandWarps = 8;
+
+__global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(const ExpandArgs a) {
+    __shared__ uint4 s_rec[kExpandWarps][128];
+    __shared__ long long s_off[kExpandWarps][128];
+    __shared__ uint8_t s_cc[kExpandWarps][128];
     const GlobalTable T{a.table};
-    const u32 lane = threadIdx.x & 31u;
-    const size_t warp_base0 = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) - lane;
-    for (size_t wb = warp_base0; wb < a.n; wb += (size_t)gridDim.x * blockDim.x) {
+    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const size_t warp_stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t wb = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) - lane; wb < a.n; wb += warp_stride) {
         const size_t i = wb + lane;
         const bool live = i < a.n;
-        Board b = live ? split(a.boards[i]) : Board{0u, 0u};
-        u64 aft[4];
-        u32 cc[4], em[4];
-        u32 m = 0, ovf = 0;
-        // shared work: the transposed board serves up and down
-        const Board bt = transpose(b);
+        const Board b = live ? split(a.boards[i]) : Board{0u, 0u};
+        const Board bt = transpose(b);  // shared by up and down
+        u32 m = 0, ovf = 0, ne4 = 0, cc4 = 0;
+        long long off = (live && a.layout == G2048_CHILDREN_COMPACT) ? a.child_offsets[i] : 0;
+        uint2 after4[4];
+        int rew4[4];
 #pragma unroll
         for (u32 act = 0; act < 4; ++act) {
             Board x = (act & 1u) ? bt : b;
@@ -887,48 +893,50 @@ __global__ void __launch_bounds__(256) expand_kernel(const ExpandArgs a) {
             MoveResult r = move_left(x, T);
             if (act & 2u) r.after = reverse_rows(r.after);
             if (act & 1u) r.after = transpose(r.after);
-            const bool moved = (r.after.lo != b.lo) | (r.after.hi != b.hi);
+            const bool moved = live & ((r.after.lo != b.lo) | (r.after.hi != b.hi));
             m |= moved ? (1u << act) : 0u;
             ovf |= r.overflow ? 1u : 0u;
-            aft[act] = join(r.after);
-            em[act] = empty_cells16(r.after);
-            const u32 ne = __popc(em[act]);
-            cc[act] = moved ? (ne ? 2u * ne : 1u) : 0u;
-            if (live) {
-                if (a.after) a.after[i * 4 + act] = aft[act];
-                if (a.rewards) a.rewards[i * 4 + act] = (int32_t)r.score;
-                if (a.num_empty) a.num_empty[i * 4 + act] = (uint8_t)ne;
-                if (a.child_count) a.child_count[i * 4 + act] = (uint8_t)cc[act];
-            }
+            const u32 nlo = nz8(r.after.lo), nhi = nz8(r.after.hi);
+            const u32 ne = 16u - __popc(nlo) - __popc(nhi);
+            const u32 cc = moved ? (ne ? 2u * ne : 1u) : 0u;
+            after4[act] = make_uint2(r.after.lo, r.after.hi);
+            rew4[act] = (int)r.score;
+            ne4 |= ne << (8 * act);
+            cc4 |= cc << (8 * act);
+            s_rec[w][lane * 4 + act] = make_uint4(r.after.lo, r.after.hi, nlo, nhi);
+            s_cc[w][lane * 4 + act] = (uint8_t)cc;
+            s_off[w][lane * 4 + act] = (a.layout == G2048_CHILDREN_DENSE) ? (long long)((i * 4 + act) * 32) : off;
+            off += cc;
         }
-        if (live && a.mask)
-            a.mask[i] = (uint8_t)(board_flags(m) | (ovf ? G2048_FLAG_OVERFLOW : 0u));
-
-        if (a.layout == G2048_CHILDREN_NONE || !a.children) continue;
-        // warp-cooperative child generation
-        int64_t off = (a.layout == G2048_CHILDREN_COMPACT && live) ? a.child_offsets[i] : 0;
-        for (u32 src = 0; src < 32u; ++src) {
-            if (wb + src >= a.n) break;
-            int64_t o = __shfl_sync(0xFFFFFFFFu, off, src);
-#pragma unroll
-            for (u32 act = 0; act < 4; ++act) {
-                const u64 p = __shfl_sync(0xFFFFFFFFu, aft[act], src);
-                const u32 e = __shfl_sync(0xFFFFFFFFu, em[act], src);
-                const u32 c = __shfl_sync(0xFFFFFFFFu, cc[act], src);
-                u64* dst = (a.layout == G2048_CHILDREN_DENSE)
-                               ? a.children + ((wb + src) * 4 + act) * 32
-                               : a.children + o;
-                if (lane < c) {
-                    u64 child = p;  // full afterstate: [(state, 1.0)] (gameboard.py:158-159)
-                    if (e) {
-                        const u32 cell = kth_set_bit16(e, lane >> 1);
-                        child = p | ((u64)(1u + (lane & 1u)) << (4 * cell));  // 2 first, then 4
-                    }
-                    dst[lane] = child;
+        if (live) {
+            if (a.after) {
+                uint4* o = reinterpret_cast<uint4*>(a.after + i * 4);
+                o[0] = make_uint4(after4[0].x, after4[0].y, after4[1].x, after4[1].y);
+                o[1] = make_uint4(after4[2].x, after4[2].y, after4[3].x, after4[3].y);
+            }
+            if (a.rewards) *reinterpret_cast<int4*>(a.rewards + i * 4) = make_int4(rew4[0], rew4[1], rew4[2], rew4[3]);
+            if (a.num_empty) *reinterpret_cast<u32*>(a.num_empty + i * 4) = ne4;
+            if (a.child_count) *reinterpret_cast<u32*>(a.child_count + i * 4) = cc4;
+            if (a.mask) a.mask[i] = (uint8_t)(board_flags(m) | (ovf ? G2048_FLAG_OVERFLOW : 0u));
+        }
+        if (a.layout == G2048_CHILDREN_NONE) continue;
+        __syncwarp();
+        for (u32 seg = 0; seg < 128u; ++seg) {
+            const u32 cc = s_cc[w][seg];  // warp-uniform
+            if (cc == 0u) continue;
+            const uint4 rec = s_rec[w][seg];
+            if (lane < cc) {
+                u32 lo = rec.x, hi = rec.y;
+                if (cc > 1u) {  // cc == 1: full afterstate, the child is the state itself
+                    bool in_hi;
+                    const u32 bit3 = fast::spawn_marker(rec.z, rec.w, __popc(rec.z), lane >> 1, in_hi);
+                    const u32 tile = (bit3 >> 3) << (lane & 1u);
+                    if (in_hi) hi |= tile; else lo |= tile;
                 }
-                o += c;
+                a.children[s_off[w][seg] + lane] = ((u64)hi << 32) | lo;
             }
         }
+        __syncwarp();
     }
 }
 
@@ -941,6 +949,9 @@ extern "C" int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* re
     if (child_layout < G2048_CHILDREN_NONE || child_layout > G2048_CHILDREN_COMPACT) return G2048_EINVAL;
     if (child_layout != G2048_CHILDREN_NONE && !children) return G2048_EINVAL;
     if (child_layout == G2048_CHILDREN_COMPACT && !child_offsets) return G2048_EINVAL;
+    if (!aligned(after, 16) || !aligned(rewards, 16) || !aligned(num_empty, 4) || !aligned(child_count, 4) ||
+        !aligned(children, 16))
+        return G2048_EINVAL;
     DeviceState* s;
     int rc = current_state(&s);
     if (rc) return rc;

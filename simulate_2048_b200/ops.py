@@ -149,15 +149,25 @@ class ExpandOut(NamedTuple):
     child_offsets: Optional[torch.Tensor]  # int64[N] (compact)
 
 
-def expand(boards: torch.Tensor, children: str = 'none') -> ExpandOut:
+def expand(boards: torch.Tensor, children: str = 'none', zero_fill: bool = True,
+           out: Optional[ExpandOut] = None) -> ExpandOut:
     """MCTS leaf expansion (g2048_expand): mask, the four afterstates + rewards and every chance
     child of each legal afterstate (gameboard.py:132 after_state order: cell-major, 2 then 4;
-    probability of a child = {0.9, 0.1} / num_empty)."""
+    probability of a child = {0.9, 0.1} / num_empty).  Dense slots beyond ``child_count`` are
+    zero when ``zero_fill`` (a 64 MB memset per 65536 boards) and unspecified otherwise."""
     _req(boards, torch.int64, 'boards')
     n = boards.numel()
     dev = boards.device
     layout = {'none': _cabi.CHILDREN_NONE, 'dense': _cabi.CHILDREN_DENSE,
               'compact': _cabi.CHILDREN_COMPACT}[children]
+    if out is not None:  # reuse a previous result's buffers (same n and layout): no allocation
+        if out.after.shape[0] != n or (layout != _cabi.CHILDREN_NONE and out.children is None):
+            raise ValueError('out: buffers do not match this call')
+        with torch.cuda.device(dev):
+            check(lib().g2048_expand(_ptr(boards), _ptr(out.after), _ptr(out.rewards), _ptr(out.mask),
+                                     _ptr(out.num_empty), _ptr(out.child_count), _ptr(out.children),
+                                     _ptr(out.child_offsets), layout, n, _stream()))
+        return out
     after = torch.empty((n, 4), dtype=torch.int64, device=dev)
     rewards = torch.empty((n, 4), dtype=torch.int32, device=dev)
     mask = torch.empty(n, dtype=torch.uint8, device=dev)
@@ -175,7 +185,7 @@ def expand(boards: torch.Tensor, children: str = 'none') -> ExpandOut:
             total = int(incl[-1].item()) if n else 0
             ch = torch.empty(total, dtype=torch.int64, device=dev)
         elif layout == _cabi.CHILDREN_DENSE:
-            ch = torch.zeros((n, 4, 16, 2), dtype=torch.int64, device=dev)
+            ch = (torch.zeros if zero_fill else torch.empty)((n, 4, 16, 2), dtype=torch.int64, device=dev)
         check(lib().g2048_expand(_ptr(boards), _ptr(after), _ptr(rewards), _ptr(mask),
                                  _ptr(num_empty), _ptr(child_count), _ptr(ch), _ptr(off), layout, n,
                                  _stream()))
