@@ -465,7 +465,23 @@ def run_ours(args):
             st, _, _, _ = game.batched_step(st, acts[t], 5, inplace=True)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        extra['selfplay_4096'] = {'us_per_iteration': dt / 200 * 1e6, 'env_steps_per_sec': 4096 * 200 / dt}
+        extra['selfplay_4096'] = {'us_per_iteration': dt / 200 * 1e6, 'env_steps_per_sec': 4096 * 200 / dt,
+                                  'note': 'reference call pattern: observation + legal mask + batched_step per iteration'}
+        # the same loop through BatchedEnv: one graph-replayed g2048_env_step launch per iteration
+        from simulate_2048_b200.selfplay import BatchedEnv
+        benv = BatchedEnv(4096, seed=7, device=dev, graph=True)
+        benv.reset()
+        for t in range(3):
+            benv.step(acts[t])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in range(200):
+            benv.step(acts[t])
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        extra['selfplay_4096_fused'] = {'us_per_iteration': dt / 200 * 1e6, 'env_steps_per_sec': 4096 * 200 / dt,
+                                        'note': 'BatchedEnv: next observation, legal mask, reward, done from ONE '
+                                                'graph-replayed launch per iteration'}
         line['secondary'] = extra
 
     if rank == 0 and world == 1 and not args.no_cpu:

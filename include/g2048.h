@@ -122,12 +122,15 @@ int g2048_step(const uint64_t* boards_in, const uint8_t* actions, const uint8_t*
  *   Philox counter step = step_count before the increment.
  *   Optional outputs (NULL to skip): rewards f32[n], flags u8[n], obs f32[n*16]
  *   (core.py:346 encode_observation of the new board), max_tile i32[n] (core.py:427,
- *   the tile VALUE).
+ *   the tile VALUE), legal u8[n*4] (core.py:275 legal_actions_mask of the new board as one
+ *   0/1 byte per action, i.e. a bool[n,4] array) — so that one launch yields everything the
+ *   self-play loop reads before its next step (self_play.py:316-317,354).
  */
 int g2048_env_step(uint64_t* boards, int32_t* step_count, uint8_t* done, float* total_reward,
                    const uint8_t* actions, const uint8_t* spawns, uint64_t seed,
                    uint64_t env_offset, const uint64_t* env_keys, float* rewards,
-                   uint8_t* flags, float* obs, int32_t* max_tile, size_t n, void* stream);
+                   uint8_t* flags, float* obs, int32_t* max_tile, uint8_t* legal, size_t n,
+                   void* stream);
 
 /* Legal mask + done of boards (gamemove.py:45, core.py:275/:305); flags has the LEGAL/DONE bits. */
 int g2048_mask(const uint64_t* boards, uint8_t* flags, size_t n, void* stream);

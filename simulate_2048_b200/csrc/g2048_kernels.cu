@@ -582,6 +582,7 @@ struct EnvStepArgs {
     uint8_t* flags;
     float* obs;
     int32_t* max_tile;
+    uint8_t* legal;
     size_t n;
     const u32* table;
 };
@@ -625,6 +626,8 @@ __global__ void __launch_bounds__(256) env_step_kernel(const EnvStepArgs a) {
             const u32 e = max_exponent(nb);
             a.max_tile[i] = e ? (1 << e) : 0;  // core.py:427 returns the tile value
         }
+        if (a.legal)  // bool[4] as bytes: bit k of the mask -> byte k
+            reinterpret_cast<u32*>(a.legal)[i] = (f & 1u) | ((f & 2u) << 7) | ((f & 4u) << 14) | ((f & 8u) << 21);
     }
 }
 
@@ -632,16 +635,16 @@ extern "C" int g2048_env_step(uint64_t* boards, int32_t* step_count, uint8_t* do
                               float* total_reward, const uint8_t* actions, const uint8_t* spawns,
                               uint64_t seed, uint64_t env_offset, const uint64_t* env_keys,
                               float* rewards, uint8_t* flags, float* obs, int32_t* max_tile,
-                              size_t n, void* stream) {
+                              uint8_t* legal, size_t n, void* stream) {
     if (n == 0) return G2048_OK;
     if (!boards || !step_count || !done || !total_reward || !actions) return G2048_EINVAL;
-    if (obs && !aligned(obs, 16)) return G2048_EINVAL;
+    if ((obs && !aligned(obs, 16)) || (legal && !aligned(legal, 4))) return G2048_EINVAL;
     DeviceState* s;
     int rc = current_state(&s);
     if (rc) return rc;
     EnvStepArgs a{reinterpret_cast<u64*>(boards), step_count, done, total_reward, actions, spawns,
                   seed, env_offset, reinterpret_cast<const u64*>(env_keys), rewards, flags, obs,
-                  max_tile, n, s->table};
+                  max_tile, legal, n, s->table};
     int grid = grid_for(n, 256, s->sms, 8);
     if (spawns) env_step_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
     else env_step_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);

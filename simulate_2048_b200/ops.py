@@ -109,8 +109,9 @@ def env_step(boards: torch.Tensor, step_count: torch.Tensor, done: torch.Tensor,
              spawns: Optional[torch.Tensor] = None, *, seed: int = 0, env_offset: int = 0,
              env_keys: Optional[torch.Tensor] = None, rewards: Optional[torch.Tensor] = None,
              flags: Optional[torch.Tensor] = None, obs: Optional[torch.Tensor] = None,
-             max_tile: Optional[torch.Tensor] = None) -> None:
-    """In-place GameState step (g2048_env_step; env.py:79-133)."""
+             max_tile: Optional[torch.Tensor] = None, legal: Optional[torch.Tensor] = None) -> None:
+    """In-place GameState step (g2048_env_step; env.py:79-133).  Optional outputs describe the
+    NEW state: rewards f32[N], flags u8[N], obs f32[N,16], max_tile i32[N], legal bool[N,4]."""
     n = boards.numel()
     _req(boards, torch.int64, 'boards')
     _req(step_count, torch.int32, 'step_count', n)
@@ -123,11 +124,12 @@ def env_step(boards: torch.Tensor, step_count: torch.Tensor, done: torch.Tensor,
     _opt(flags, torch.uint8, 'flags', n)
     _opt(obs, torch.float32, 'obs', n * 16)
     _opt(max_tile, torch.int32, 'max_tile', n)
+    _opt(legal, torch.bool, 'legal', n * 4)
     with torch.cuda.device(boards.device):
         check(lib().g2048_env_step(_ptr(boards), _ptr(step_count), _ptr(done), _ptr(total_reward),
                                    _ptr(actions), _ptr(spawns), seed & (2**64 - 1), env_offset,
                                    _ptr(env_keys), _ptr(rewards), _ptr(flags), _ptr(obs),
-                                   _ptr(max_tile), n, _stream()))
+                                   _ptr(max_tile), _ptr(legal), n, _stream()))
 
 
 def legal_flags(boards: torch.Tensor) -> torch.Tensor:

@@ -1,0 +1,108 @@
+"""Self-play stepping on the device (BASELINE config 5).
+
+``reinforce/training/self_play.py:314-368`` makes three calls per loop iteration —
+``batched_get_observation``, ``batched_get_legal_actions``, ``batched_step`` — plus two host syncs.
+``BatchedEnv`` gives the same information from ONE launch of ``g2048_env_step`` per iteration:
+the kernel that applies the actions also writes the observation and legal mask of the NEW state,
+which are exactly what the next iteration reads.  All buffers are allocated once; with
+``graph=True`` the launch (and the copy of the caller's actions into the static input buffer) is
+replayed from a CUDA graph, so an iteration costs one graph launch instead of ~10 torch ops.
+"""
+
+from __future__ import annotations
+
+from typing import NamedTuple, Optional
+
+import torch
+
+from . import ops
+from .game.env import GameState
+
+
+class StepResult(NamedTuple):
+    observation: torch.Tensor   # f32[N,16]  (core.py:346) of the new state
+    legal_mask: torch.Tensor    # bool[N,4]  (core.py:275) of the new state
+    reward: torch.Tensor        # f32[N]
+    done: torch.Tensor          # bool[N]
+    max_tile: torch.Tensor      # i32[N]
+
+
+class BatchedEnv:
+    """N parallel games with static device buffers.  The returned tensors are views of those
+    buffers: they are overwritten by the next ``step`` (clone what must be kept)."""
+
+    def __init__(self, n: int, seed: int = 0, device=None, graph: bool = True):
+        self.n = n
+        self.seed = seed
+        self.device = torch.device('cuda' if device is None else device)
+        dev = self.device
+        self.board = torch.empty(n, dtype=torch.int64, device=dev)
+        self.step_count = torch.zeros(n, dtype=torch.int32, device=dev)
+        self._done8 = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.total_reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self._actions = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._spawns: Optional[torch.Tensor] = None
+        self._reward = torch.empty(n, dtype=torch.float32, device=dev)
+        self._obs = torch.empty((n, 16), dtype=torch.float32, device=dev)
+        self._legal = torch.empty((n, 4), dtype=torch.bool, device=dev)
+        self._max_tile = torch.empty(n, dtype=torch.int32, device=dev)
+        self._use_graph = graph
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._episode = 0
+
+    @property
+    def state(self) -> GameState:
+        return GameState(self.board, self.step_count, self._done8.view(torch.bool), self.total_reward)
+
+    def reset(self) -> StepResult:
+        """New games (env.py:176): two tiles each, counters cleared."""
+        self._episode += 1
+        key = (self.seed + 0x9E3779B97F4A7C15 * self._episode) & (2**64 - 1)
+        self._key = key
+        self.board.copy_(ops.reset(self.n, seed=key, device=self.device))
+        self.step_count.zero_()
+        self._done8.zero_()
+        self.total_reward.zero_()
+        self._reward.zero_()
+        obs, mx = ops.observe(self.board)
+        self._obs.copy_(obs)
+        self._max_tile.copy_(torch.where(mx > 0, torch.ones_like(mx, dtype=torch.int32) << mx.to(torch.int32),
+                                         torch.zeros_like(mx, dtype=torch.int32)))
+        flags = ops.legal_flags(self.board)
+        bits = torch.tensor([1, 2, 4, 8], dtype=torch.uint8, device=self.device)
+        self._legal.copy_((flags.unsqueeze(1) & bits) != 0)
+        self._graph = None  # the Philox key changed
+        return self._result()
+
+    def _result(self) -> StepResult:
+        return StepResult(self._obs, self._legal, self._reward, self._done8.view(torch.bool), self._max_tile)
+
+    def _launch(self) -> None:
+        ops.env_step(self.board, self.step_count, self._done8, self.total_reward, self._actions,
+                     self._spawns, seed=self._key, rewards=self._reward, obs=self._obs,
+                     max_tile=self._max_tile, legal=self._legal)
+
+    def step(self, actions: torch.Tensor, spawns: Optional[torch.Tensor] = None) -> StepResult:
+        """env.py:211 batched_step + the next observation / legal mask, one launch.  ``spawns``
+        (uint8[N]) injects the tiles; otherwise Philox keyed by (episode key, env, step_count)."""
+        self._actions.copy_(actions.reshape(-1), non_blocking=True)
+        if spawns is not None:
+            if self._spawns is None:
+                self._spawns = torch.empty(self.n, dtype=torch.uint8, device=self.device)
+                self._graph = None
+            self._spawns.copy_(spawns.reshape(-1), non_blocking=True)
+        elif self._spawns is not None:
+            self._spawns = None
+            self._graph = None
+        if not self._use_graph:
+            self._launch()
+            return self._result()
+        if self._graph is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            # capture changes no state: the captured launch is only recorded, not executed
+            with torch.cuda.graph(g):
+                self._launch()
+            self._graph = g
+        self._graph.replay()
+        return self._result()
