@@ -170,6 +170,29 @@ def numpy_port_rate(packed: np.ndarray, actions: np.ndarray, per_worker: int, wo
     return total / dt, dt
 
 
+def _games_worker(args):
+    first, count = args
+    from oracle import np_engine
+    return np_engine.play_random_games(first, count)
+
+
+def config1_games(cores, n_games=1024):
+    """BASELINE configs[0]: 1024 random-policy games to game-over on the NumPy engine port
+    (reset(seed=g), uniform-legal policy), one process per core."""
+    import multiprocessing as mp
+    per = (n_games + cores - 1) // cores
+    jobs = [(g, min(per, n_games - g)) for g in range(0, n_games, per)]
+    t0 = time.perf_counter()
+    with mp.get_context('fork').Pool(cores) as pool:
+        res = pool.map(_games_worker, jobs)
+    dt = time.perf_counter() - t0
+    steps = sum(r[0] for r in res)
+    score = sum(r[1] for r in res)
+    return {'games': n_games, 'env_steps': steps, 'seconds': dt, 'env_steps_per_sec': steps / dt,
+            'mean_length': steps / n_games, 'mean_score': score / n_games, 'cores': cores,
+            'note': 'oracle/np_engine.py play_random_games (port of TwentyFortyEight.step + legal_actions)'}
+
+
 def cpu_baseline_block(packed, actions, cores):
     """Bounded sample (~10-30 s of CPU work): NumPy port on all cores + the C oracle."""
     import multiprocessing as mp
@@ -186,7 +209,9 @@ def cpu_baseline_block(packed, actions, cores):
     t0 = time.perf_counter()
     c_oracle.step(packed[: n_c // 8], actions[: n_c // 8], None, seed=2048, threads=1)
     c_rate1 = (n_c // 8) / (time.perf_counter() - t0)
+    cfg1 = config1_games(cores)
     return {
+        'config1_numpy_engine_1024_games': cfg1,
         'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
         'sample': f'NumPy port of the reference engine (oracle/np_engine.py next_state, one Python call '
                   f'per env), {per_worker} boards x {cores} processes of the config-2 set, {dt:.1f} s',

@@ -87,6 +87,7 @@ extern "C" {
 #define G2048_IMPL_AUTO 0
 #define G2048_IMPL_LUT 1      /* 57344-entry row table staged in shared memory by TMA bulk copy */
 #define G2048_IMPL_REGISTER 2 /* pure register arithmetic, no table */
+#define G2048_IMPL_GATHER 3   /* full table gathered from global memory through L1/L2 (no staging) */
 
 int g2048_abi_version(void);
 const char* g2048_error_string(int code);

@@ -18,7 +18,7 @@ FLAG_LEFT, FLAG_UP, FLAG_RIGHT, FLAG_DOWN = 1, 2, 4, 8
 FLAG_LEGAL_MASK = 0x0F
 FLAG_DONE, FLAG_MOVED, FLAG_OVERFLOW, FLAG_BADSPAWN = 0x10, 0x20, 0x40, 0x80
 CHILDREN_NONE, CHILDREN_DENSE, CHILDREN_COMPACT = 0, 1, 2
-IMPL_AUTO, IMPL_LUT, IMPL_REGISTER = 0, 1, 2
+IMPL_AUTO, IMPL_LUT, IMPL_REGISTER, IMPL_GATHER = 0, 1, 2, 3
 STATS_WORDS = 24
 
 # every symbol include/g2048.h declares: name -> (restype, argtypes)

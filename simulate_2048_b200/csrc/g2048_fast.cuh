@@ -227,7 +227,7 @@ struct FastOut {
 };
 
 // One transition on the fast path.
-//   lut(row) returns the u32 entry of the staged (hashed) row table at word index `row`.
+//   lut(off) returns the u32 entry of the staged (hashed) row table at BYTE offset `off`.
 //   Preconditions (checked by the caller): !has_big_tile(lo, hi).
 //   rank = spawn rank among the empties (injected) — ignored when kPhilox (then w0 draws it);
 //   exp  = spawned exponent (1 or 2);  one = the run-time constant 1 (see add()).
@@ -241,8 +241,9 @@ G2048_HD u32 move_fast(u32 lo, u32 hi, const Orient& o, const Lut& lut, u32 one,
     u32 xl = lo, xh = hi;
     orient_forward(xl, xh, o);
     const u32 yl = hash_rows(xl), yh = hash_rows(xh);
-    const u32 e0 = lut(yl & 0xFFFFu), e1 = lut(prmt(yl, 0u, 0x4432u));
-    const u32 e2 = lut(yh & 0xFFFFu), e3 = lut(prmt(yh, 0u, 0x4432u));
+    // byte offsets: the x4 is an IMAD.SHL (FMA pipe), one ALU op per lookup for the extraction
+    const u32 e0 = lut((yl << 2) & 0x3FFFCu), e1 = lut(prmt(yl, 0u, 0x4432u) << 2);
+    const u32 e2 = lut((yh << 2) & 0x3FFFCu), e3 = lut(prmt(yh, 0u, 0x4432u) << 2);
     al = prmt(e0, e1, 0x7632);
     ah = prmt(e2, e3, 0x7632);
     moved = (al != xl) | (ah != xh);

@@ -128,7 +128,7 @@ extern "C" int g2048_set_tuning(int step_threads, int envs_per_thread) {
 }
 
 extern "C" int g2048_set_impl(int impl) {
-    if (impl < G2048_IMPL_AUTO || impl > G2048_IMPL_REGISTER) return G2048_EINVAL;
+    if (impl < G2048_IMPL_AUTO || impl > G2048_IMPL_GATHER) return G2048_EINVAL;
     g_impl = impl;
     return G2048_OK;
 }
@@ -311,9 +311,16 @@ __device__ __noinline__ uint4 transition_slow(u64 board, u32 action, u32 spawn, 
 }
 
 
+// The dynamic shared memory of the step / rollout kernels: [row table | mbarrier | ...].
+// Indexing the extern symbol directly (instead of a generic pointer) keeps the address space
+// known to ptxas, so a lookup is `LDS R, [R + UR]` with the base in a uniform register.
+extern __shared__ __align__(128) u32 smem_words[];
+
 struct SmemLut {
-    const u32* tab;  // staged table in shared memory, indexed by WORD: LDS R, [R*4 + UR]
-    __device__ __forceinline__ u32 operator()(u32 word) const { return tab[word]; }
+    // staged (hashed) row table at the start of dynamic shared memory, indexed by BYTE offset
+    __device__ __forceinline__ u32 operator()(u32 byte_off) const {
+        return *reinterpret_cast<const u32*>(reinterpret_cast<const unsigned char*>(smem_words) + byte_off);
+    }
 };
 
 // Four consecutive envs of one thread.  The byte streams are decoded once per tile (one LOP3
@@ -344,13 +351,13 @@ __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 s
         rw = make_int4(rws[0], rws[1], rws[2], rws[3]);
         return;
     }
-    const u32 act4 = (actions << 1) & 0x06060606u;     // byte k = 2 * action_k (uint4 index)
+    const u32 act4 = (actions << 5) & 0x60606060u;     // byte k = 32 * action_k (byte offset)
     const u32 rank4 = spawns & 0x0F0F0F0Fu;            // byte k = spawn rank
     const u32 exp4 = fast::shr<4>(spawns & 0x10101010u) + 0x01010101u;  // byte k = exponent (1 or 2)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const u32 oi = fast::prmt(act4, 0u, 0x4440u + k);
-        const uint4 o0 = s_orient[oi], o1 = s_orient[oi + 1];
+        const unsigned char* op = reinterpret_cast<const unsigned char*>(s_orient) + fast::prmt(act4, 0u, 0x4440u + k);
+        const uint4 o0 = *reinterpret_cast<const uint4*>(op), o1 = *reinterpret_cast<const uint4*>(op + 16);
         fast::Orient o;
         o.mt = o0.x; o.mr = o0.y; o.f_lo = o0.z; o.f_hi = o0.w; o.b_lo = o1.x; o.b_hi = o1.y;
         u32 rank = 0, exp, w0 = 0;
@@ -411,7 +418,6 @@ __device__ __forceinline__ void compute_store_tiles(const TileBuf<kPhilox, kGrou
 // between two register buffers (the loads of one tile are in flight while the other computes).
 template <bool kPhilox, int kThreads, int kGroups>
 __global__ void __launch_bounds__(kThreads, 1) step_lut_kernel(const StepArgs a) {
-    extern __shared__ __align__(128) u32 smem_words[];
     u32* smem_tab = smem_words;
     u64* bar = reinterpret_cast<u64*>(smem_words + kSmemRows);
     uint4* s_orient = reinterpret_cast<uint4*>(smem_words + kSmemRows + 16);
@@ -432,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) step_lut_kernel(const StepArgs a)
     if (env0 < env_end) load_tiles(bufA, a, env0);
 
     table_stage_wait(bar);  // __syncthreads inside also publishes s_orient
-    const SmemLut lut{smem_tab};
+    const SmemLut lut{};
 
     while (env0 < env_end) {
         const bool hasB = env0 + kTile < env_end;
@@ -523,7 +529,7 @@ extern "C" int g2048_step(const uint64_t* boards_in, const uint8_t* actions, con
                         aligned(actions, 4) && aligned(flags, 4) && (!spawns || aligned(spawns, 4));
     bool use_lut = plain && vec_ok && s->smem_optin >= kStepSmemBytes;
     if (g_impl == G2048_IMPL_AUTO) use_lut = use_lut && n >= kLutMinEnvs;
-    if (g_impl == G2048_IMPL_REGISTER) use_lut = false;
+    if (g_impl == G2048_IMPL_REGISTER || g_impl == G2048_IMPL_GATHER) use_lut = false;
 
     if (use_lut) {
         const int smem = (int)kStepSmemBytes;
@@ -1058,7 +1064,7 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const Rollout
     u64 env = 0, score = 0;
     u32 lo = 0, hi = 0;
     u32 step = 0, ovf = 0, mask = 0, nlo = 0, nhi = 0;
-    const SmemLut lut{sm.tab};
+    const SmemLut lut{};
     for (;;) {
         const u32 need = __ballot_sync(FULL, !active && !exhausted);
         if (need) {
@@ -1149,7 +1155,6 @@ __constant__ uint8_t c_pick[64] = {
 
 template <bool kSmem>
 __global__ void __launch_bounds__(1024, 1) rollout_kernel(const RolloutArgs a, unsigned long long* next) {
-    extern __shared__ __align__(128) u32 smem_words[];
     __shared__ u64 sh_stats[G2048_STATS_WORDS];
     __shared__ __align__(16) uint4 sh_orient[8];
     __shared__ uint8_t sh_pick[64];

@@ -30,7 +30,7 @@ int main(int argc, char** argv) {
     orc_row_table(res.data(), rew.data(), mv.data());
     std::vector<uint32_t> table(65536);
     for (int r = 0; r < 65536; ++r) table[hash_row16(r)] = (rew[r] >> 2) | ((uint32_t)res[r] << 16);
-    auto lut = [&](u32 row) { return table[row]; };
+    auto lut = [&](u32 off) { return table[off >> 2]; };
     const Orient orient[4] = G2048_ORIENT_TABLE;
 
     std::vector<uint64_t> boards(n), out(n); std::vector<uint8_t> act(n), spn(n), fl(n); std::vector<int32_t> rw(n);
