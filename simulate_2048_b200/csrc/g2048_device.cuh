@@ -324,6 +324,41 @@ __device__ __forceinline__ Philox4 philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3,
     return Philox4{c0, c1, c2, c3};
 }
 
+// Same generator with the ten round keys precomputed on the host (they depend only on the seed):
+// as kernel parameters they are constant-bank operands of the xor and cost no instruction.
+struct PhiloxKeys {
+    u32 k0[10], k1[10];
+};
+
+inline PhiloxKeys philox_key_schedule(u64 key) {
+    PhiloxKeys s;
+    u32 a = (u32)key, b = (u32)(key >> 32);
+    for (int r = 0; r < 10; ++r) {
+        s.k0[r] = a;
+        s.k1[r] = b;
+        a += 0x9E3779B9u;
+        b += 0xBB67AE85u;
+    }
+    return s;
+}
+
+__device__ __forceinline__ Philox4 philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3, const PhiloxKeys& ks) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const u32 h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const u32 h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ ks.k0[r];
+        c1 = l1;
+        c2 = h0 ^ c3 ^ ks.k1[r];
+        c3 = l0;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ Philox4 philox_env(const PhiloxKeys& ks, u64 env, u32 step, u32 tag) {
+    return philox4x32_10((u32)env, (u32)(env >> 32), step, tag, ks);
+}
+
 __device__ __forceinline__ Philox4 philox_env(u64 key, u64 env, u32 step, u32 tag) {
     return philox4x32_10((u32)env, (u32)(env >> 32), step, tag, (u32)key, (u32)(key >> 32));
 }

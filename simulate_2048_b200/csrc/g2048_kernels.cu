@@ -278,6 +278,7 @@ struct StepArgs {
     const u32* table;
     const u32* table_hashed;
     u32 one;  // always 1: a run-time multiplier that keeps adds on the FMA pipe (g2048_fast.cuh)
+    PhiloxKeys keys;  // round keys of `seed`
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -362,7 +363,7 @@ __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 s
         o.mt = o0.x; o.mr = o0.y; o.f_lo = o0.z; o.f_hi = o0.w; o.b_lo = o1.x; o.b_hi = o1.y;
         u32 rank = 0, exp, w0 = 0;
         if (kPhilox) {
-            const Philox4 p = philox_env(a.seed, env0 + k, a.step_base, G2048_PHILOX_TAG_STEP);
+            const Philox4 p = philox_env(a.keys, env0 + k, a.step_base, G2048_PHILOX_TAG_STEP);
             w0 = p.x;
             // word1 < 0x1999999A  <=>  mulhi(word1, 10) == 0   (0x1999999A * 10 = 2^32 + 4)
             exp = 2u - fast::nonzero01(__umulhi(p.y, 10u));
@@ -522,7 +523,8 @@ extern "C" int g2048_step(const uint64_t* boards_in, const uint8_t* actions, con
     cudaStream_t st = (cudaStream_t)stream;
     StepArgs a{reinterpret_cast<const u64*>(boards_in), actions, spawns, seed, env_offset, step_ctr,
                step_base, reinterpret_cast<const u64*>(env_keys), done_in,
-               reinterpret_cast<u64*>(boards_out), rewards, flags, n, s->table, s->table_hashed, 1u};
+               reinterpret_cast<u64*>(boards_out), rewards, flags, n, s->table, s->table_hashed, 1u,
+               philox_key_schedule(seed)};
 
     const bool plain = !step_ctr && !env_keys && !done_in;
     const bool vec_ok = aligned(boards_in, 32) && aligned(boards_out, 32) && aligned(rewards, 16) &&
@@ -1025,6 +1027,7 @@ struct RolloutArgs {
     const u32* table;
     const u32* table_hashed;
     u32 one;
+    PhiloxKeys keys;
 };
 
 // idx-th set bit (0-based) of a 4-bit mask
@@ -1114,7 +1117,7 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const Rollout
             continue;
         }
         // one step: uniform-legal action (word2), move, spawn (words 0/1), new mask
-        const Philox4 p = philox_env(a.seed, env, step, G2048_PHILOX_TAG_STEP);
+        const Philox4 p = philox_env(a.keys, env, step, G2048_PHILOX_TAG_STEP);
         const u32 action = sm.pick[mask * 4u + __umulhi(p.z, (u32)__popc(mask))];
         u32 al, ah, reward;
         if (kFast && !fast::has_big_tile(lo, hi)) {
@@ -1189,7 +1192,7 @@ extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint3
     cudaStream_t st = (cudaStream_t)stream;
     RolloutArgs a{seed, env_offset, n, max_steps, from_reset, reinterpret_cast<u64*>(boards_io),
                   score_out, steps_out, maxexp_out, reinterpret_cast<u64*>(stats_out), trace,
-                  trace_stride, s->table, s->table_hashed, 1u};
+                  trace_stride, s->table, s->table_hashed, 1u, philox_key_schedule(seed)};
     unsigned long long* next = nullptr;
     CU(cudaMallocAsync(&next, sizeof(unsigned long long), st));
     CU(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
