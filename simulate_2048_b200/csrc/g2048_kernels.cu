@@ -1066,7 +1066,13 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const Rollout
     size_t i = 0;
     u64 env = 0, score = 0;
     u32 lo = 0, hi = 0;
-    u32 step = 0, ovf = 0, mask = 0, nlo = 0, nhi = 0;
+    // phase 0 / 1: the two reset tiles are still to be placed (Philox tags 1 / 2, no move);
+    // phase 2: playing.  A new game therefore costs two ordinary loop iterations instead of a
+    // divergent reset path, and every lane of the warp runs the same instructions.
+    u32 phase = 2, step = 0, ovf = 0, mask = 0, nlo = 0, nhi = 0;
+    // per-lane statistics, flushed once at the end (the histogram goes to shared memory)
+    u64 st_steps = 0, st_score = 0, st_maxscore = 0;
+    u32 st_eps = 0, st_maxsteps = 0, st_capped = 0, st_ovf = 0;
     const SmemLut lut{};
     for (;;) {
         const u32 need = __ballot_sync(FULL, !active && !exhausted);
@@ -1079,15 +1085,21 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const Rollout
                 i = (size_t)base + __popc(need & ((1u << lane) - 1u));
                 if (i < a.n) {
                     env = a.env_offset + i;
-                    const Board b = a.from_reset ? reset_board(a.seed, env, nullptr) : split(a.boards_io[i]);
-                    lo = b.lo;
-                    hi = b.hi;
                     score = 0;
                     step = 0;
                     ovf = 0;
-                    nlo = fast::nz8(lo, one);
-                    nhi = fast::nz8(hi, one);
-                    mask = fast::legal_mask(lo, hi, nlo, nhi, one);
+                    if (a.from_reset) {
+                        lo = hi = nlo = nhi = mask = 0u;
+                        phase = 0;
+                    } else {
+                        const Board b = split(a.boards_io[i]);
+                        lo = b.lo;
+                        hi = b.hi;
+                        nlo = fast::nz8(lo, one);
+                        nhi = fast::nz8(hi, one);
+                        mask = fast::legal_mask(lo, hi, nlo, nhi, one);
+                        phase = 2;
+                    }
                     active = true;
                 } else {
                     exhausted = true;
@@ -1096,28 +1108,27 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const Rollout
         }
         if (!__any_sync(FULL, active)) break;
         if (!active) continue;
-        if (mask == 0u || step >= a.max_steps) {  // game over: emit the episode
+        const bool playing = phase >= 2u;
+        if (playing && (mask == 0u || step >= a.max_steps)) {  // game over: emit the episode
             if (a.trace) a.trace[i * a.trace_stride + min(step, a.trace_stride - 1u)] = 0;
             const u32 mx = max_exponent(Board{lo, hi});
             if (a.boards_io) a.boards_io[i] = ((u64)hi << 32) | lo;
             if (a.score_out) a.score_out[i] = (int64_t)score;
             if (a.steps_out) a.steps_out[i] = (int32_t)step;
             if (a.maxexp_out) a.maxexp_out[i] = (uint8_t)mx;
-            if (sm.stats) {
-                atomicAdd(&sm.stats[0], 1ull);
-                atomicAdd(&sm.stats[1], (u64)step);
-                atomicAdd(&sm.stats[2], score);
-                atomicMax(&sm.stats[3], score);
-                atomicMax(&sm.stats[4], (u64)step);
-                if (mask != 0u) atomicAdd(&sm.stats[5], 1ull);
-                if (ovf) atomicAdd(&sm.stats[6], 1ull);
-                atomicAdd(&sm.stats[8 + mx], 1ull);
-            }
+            if (sm.stats) atomicAdd(&sm.stats[8 + mx], 1ull);
+            st_eps += 1u;
+            st_steps += step;
+            st_score += score;
+            st_maxscore = max(st_maxscore, score);
+            st_maxsteps = max(st_maxsteps, step);
+            st_capped += (mask != 0u) ? 1u : 0u;
+            st_ovf += ovf;
             active = false;
             continue;
         }
-        // one step: uniform-legal action (word2), move, spawn (words 0/1), new mask
-        const Philox4 p = philox_env(a.keys, env, step, G2048_PHILOX_TAG_STEP);
+        // one iteration: Philox draw; (playing) uniform-legal action + move; spawn; new mask
+        const Philox4 p = philox_env(a.keys, env, step, playing ? G2048_PHILOX_TAG_STEP : G2048_PHILOX_TAG_RESET0 + phase);
         const u32 action = sm.pick[mask * 4u + __umulhi(p.z, (u32)__popc(mask))];
         u32 al, ah, reward;
         if (kFast && !fast::has_big_tile(lo, hi)) {
@@ -1128,8 +1139,9 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const Rollout
             reward = fast::move_fast(lo, hi, o, lut, one, al, ah, moved);
         } else {
             const uint4 r = rollout_move_slow(((u64)hi << 32) | lo, action, a.table);
-            al = r.x; ah = r.y; reward = r.z; ovf |= r.w;
+            al = r.x; ah = r.y; reward = r.z; ovf |= playing ? r.w : 0u;
         }
+        if (!playing) { al = lo; ah = hi; reward = 0u; }  // reset iterations only spawn
         score += reward;
         nlo = fast::nz8(al, one);
         nhi = fast::nz8(ah, one);
@@ -1141,13 +1153,33 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const Rollout
         if (in_hi) { ah += tile; nhi += bit3; } else { al += tile; nlo += bit3; }
         lo = al;
         hi = ah;
-        if (a.trace && step + 1u < a.trace_stride) {
+        if (playing && a.trace && step + 1u < a.trace_stride) {
             const u32 cell = ((__ffs(bit3) - 1u) >> 2) + (in_hi ? 8u : 0u);
             a.trace[i * a.trace_stride + step] =
                 (uint8_t)(0x80u | action | (cell << 2) | ((exp - 1u) << 6));
         }
-        ++step;
+        if (playing) ++step; else ++phase;
         mask = fast::legal_mask(lo, hi, nlo, nhi, one);
+    }
+    if (sm.stats) {  // one flush per lane (warp-reduced first)
+        for (int off = 16; off; off >>= 1) {
+            st_eps += __shfl_xor_sync(FULL, st_eps, off);
+            st_steps += __shfl_xor_sync(FULL, st_steps, off);
+            st_score += __shfl_xor_sync(FULL, st_score, off);
+            st_capped += __shfl_xor_sync(FULL, st_capped, off);
+            st_ovf += __shfl_xor_sync(FULL, st_ovf, off);
+            st_maxscore = max(st_maxscore, (u64)__shfl_xor_sync(FULL, st_maxscore, off));
+            st_maxsteps = max(st_maxsteps, __shfl_xor_sync(FULL, st_maxsteps, off));
+        }
+        if (lane == 0) {
+            atomicAdd(&sm.stats[0], (u64)st_eps);
+            atomicAdd(&sm.stats[1], st_steps);
+            atomicAdd(&sm.stats[2], st_score);
+            atomicMax(&sm.stats[3], st_maxscore);
+            atomicMax(&sm.stats[4], (u64)st_maxsteps);
+            atomicAdd(&sm.stats[5], (u64)st_capped);
+            atomicAdd(&sm.stats[6], (u64)st_ovf);
+        }
     }
 }
 
