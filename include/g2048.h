@@ -173,6 +173,12 @@ int g2048_spawn(uint64_t* boards_io, const uint8_t* spawns, uint64_t seed, uint6
 /* Observation (core.py:346: exponent/16 as f32[16]) and max tile exponent (core.py:427). */
 int g2048_observe(const uint64_t* boards, float* obs, uint8_t* max_exp, size_t n, void* stream);
 
+/* One-hot observation (twentyfortyeight/utils/binary.py:52 encode_flatten with
+ * encodage_size = width, used by envs/twentyfortyeight.py:66-67 with width 31):
+ * out[(i*16 + c)*width + e] = 1 if log2(tile of cell c) == e (empty cell: e = 0) else 0.
+ * 16 <= width <= 64.  out is u8[n*16*width]. */
+int g2048_observe_onehot(const uint64_t* boards, uint8_t* out, int width, size_t n, void* stream);
+
 /*
  * Fused random-policy rollout to termination, board in registers:
  *   policy = uniform over legal actions (Philox word2), spawns from Philox words 0/1.

@@ -141,6 +141,22 @@ def after_state(board: np.ndarray):
     return out
 
 
+def encode_flatten(board: np.ndarray, width: int = 31) -> np.ndarray:
+    """utils/binary.py:11-86 — one-hot of log2(tile) per cell (an empty cell is index 0), flattened."""
+    flat = board.reshape(-1)
+    exps = np.zeros(flat.size, dtype=np.int64)
+    nz = flat != 0
+    exps[nz] = np.log2(flat[nz].astype(np.float64)).astype(np.int64)
+    out = np.zeros((flat.size, width), dtype=np.int64)
+    out[np.arange(flat.size), exps] = 1
+    return out.reshape(-1)
+
+
+def normalize_reward(reward: float, max_tile: int = 2 ** 16) -> float:
+    """utils/normalize.py:6-33."""
+    return 0.0 if reward == 0 else float(np.log2(reward) / np.log2(max_tile))
+
+
 class Game:
     """twentyfortyeight.py:10-140 (size 4, raw observation, raw reward)."""
 

@@ -706,6 +706,31 @@ extern "C" int g2048_observe(const uint64_t* boards, float* obs, uint8_t* max_ex
     return G2048_OK;
 }
 
+// one thread per (board, cell): `width` bytes with a single 1 (binary.py:47-49 eye(width)[log2])
+__global__ void __launch_bounds__(256) onehot_kernel(const u64* __restrict__ boards,
+                                                     uint8_t* __restrict__ out, int width, size_t n) {
+    const size_t total = n * 16;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total;
+         t += (size_t)gridDim.x * blockDim.x) {
+        const u32 e = (u32)(boards[t >> 4] >> (4 * (t & 15))) & 0xFu;
+        uint8_t* row = out + t * width;
+        for (int k = 0; k < width; ++k) row[k] = (uint8_t)(k == (int)e);
+    }
+}
+
+extern "C" int g2048_observe_onehot(const uint64_t* boards, uint8_t* out, int width, size_t n,
+                                    void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!boards || !out || width < 16 || width > 64) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    onehot_kernel<<<grid_for(n * 16, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const u64*>(boards), out, width, n);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
 __global__ void __launch_bounds__(256) pack_kernel(const int32_t* __restrict__ tiles,
                                                    u64* __restrict__ boards,
                                                    int32_t* __restrict__ status, size_t n) {

@@ -19,7 +19,7 @@ from ._cabi import check, lib
 
 __all__ = [
     'StepOut', 'ExpandOut', 'RolloutOut', 'step', 'env_step', 'legal_flags', 'expand', 'reset',
-    'observe', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'step_host', 'row_table', 'set_impl', 'set_tuning', 'init',
+    'observe', 'observe_onehot', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'step_host', 'row_table', 'set_impl', 'set_tuning', 'init',
     'pinned_empty',
 ]
 
@@ -249,6 +249,17 @@ def observe(boards: torch.Tensor, want_max: bool = True):
     with torch.cuda.device(boards.device):
         check(lib().g2048_observe(_ptr(boards), _ptr(obs), _ptr(mx), n, _stream()))
     return obs, mx
+
+
+def observe_onehot(boards: torch.Tensor, width: int = 31) -> torch.Tensor:
+    """uint8[N,16,width] one-hot of log2(tile) per cell (g2048_observe_onehot; binary.py:52
+    encode_flatten as used by TwentyFortyEight(encoded=True), width 31)."""
+    _req(boards, torch.int64, 'boards')
+    n = boards.numel()
+    out = torch.empty((n, 16, width), dtype=torch.uint8, device=boards.device)
+    with torch.cuda.device(boards.device):
+        check(lib().g2048_observe_onehot(_ptr(boards), _ptr(out), int(width), n, _stream()))
+    return out
 
 
 class RolloutOut(NamedTuple):

@@ -5,17 +5,20 @@ from __future__ import annotations
 from numpy import int64, ndarray, zeros
 
 from ..core.gameboard import fill_cells, is_done, next_state
+from ..utils.binary import encode_flatten
+from ..utils.normalize import normalize_reward
 
 
 class TwentyFortyEight:
-    """twentyfortyeight.py:10 — 4x4 game; the ``encoded`` / ``normalize`` presentation variants of
-    the reference are out of scope for the device path and raise."""
+    """twentyfortyeight.py:10 — 4x4 game with the reference's ``encoded`` (31-way one-hot
+    observation, :66-67) and ``normalize`` (log-scaled reward, :80-81) presentation options.
+    Other board sizes are out of scope for the packed device format and raise."""
 
     ACTIONS = {'left': 0, 'up': 1, 'right': 2, 'down': 3}  # twentyfortyeight.py:19
 
     def __init__(self, size: int = 4, encoded: bool = False, normalize: bool = False):
-        if size != 4 or encoded or normalize:
-            raise NotImplementedError('device path implements size=4, encoded=False, normalize=False')
+        if size != 4:
+            raise NotImplementedError('the packed device format implements the 4x4 board only')
         self.size = size
         self._encoded = encoded
         self._normalize = normalize
@@ -29,10 +32,14 @@ class TwentyFortyEight:
 
     @property
     def observation(self) -> ndarray:
+        if self._encoded:
+            return encode_flatten(self._current_state, encodage_size=31)  # twentyfortyeight.py:66-67
         return self._current_state
 
     @property
     def reward(self) -> float:
+        if self._normalize:
+            return normalize_reward(self._current_reward)  # twentyfortyeight.py:80-81
         return self._current_reward
 
     def reset(self, seed: int | None = None) -> ndarray:

@@ -17,6 +17,7 @@ Fixtures
   games.npz       48 full games of TwentyFortyEight (reset(seed=g), uniform-legal policy):
                   every (board, action, next board, reward, done)
   fill_cells.npz  fill_cells draws on a fixed board, seeds 0..63, and reset(seed) boards
+  encodings.npz   utils/binary.py encode_flatten(., 31) of 64 boards; utils/normalize.py values
 """
 
 from __future__ import annotations
@@ -204,7 +205,20 @@ def make_fill_cells() -> None:
     print('fill_cells', out[:8], [hex(int(x)) for x in resets[:2]])
 
 
+def make_encodings() -> None:
+    from twentyfortyeight.utils.binary import encode_flatten
+    from twentyfortyeight.utils.normalize import normalize_reward
+    boards = synthetic_boards(64, seed=31)
+    onehot = np.stack([encode_flatten(b, encodage_size=31) for b in boards]).astype(np.uint8)
+    rewards = np.array([0, 4, 8, 12, 20, 60, 84, 2048, 4100, 65536, 131072], dtype=np.int64)
+    norm = np.array([normalize_reward(float(r)) for r in rewards], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, 'encodings.npz'), tiles=boards.astype(np.int32), onehot=onehot,
+                        rewards=rewards, normalized=norm)
+    print('encodings', onehot.shape, norm[:4])
+
+
 if __name__ == '__main__':
+    make_encodings()
     make_rows()
     make_synthetic()
     make_games()

@@ -148,8 +148,6 @@ def test_game_reaches_termination(gm, Env):  # test_environment.py:308-328
 def test_out_of_scope_variants_raise(Env):
     with pytest.raises(NotImplementedError):
         Env(size=6)
-    with pytest.raises(NotImplementedError):
-        Env(encoded=True)
 
 
 def test_against_oracle_random_boards(gb, gm, oracle):
@@ -163,3 +161,31 @@ def test_against_oracle_random_boards(gb, gm, oracle):
             os_, or_ = oracle.latent_state_values(t, a)
             np.testing.assert_array_equal(s, os_)
             assert r == or_
+
+
+def test_encoded_and_normalized_variants(Env, golden):
+    """TwentyFortyEight(encoded=True / normalize=True) (twentyfortyeight.py:66-67, :80-81) against
+    fixtures from the reference's utils/binary.py and utils/normalize.py."""
+    import torch
+    from simulate_2048_b200 import ops
+    from simulate_2048_b200.twentyfortyeight.utils.binary import encode_flatten
+    from simulate_2048_b200.twentyfortyeight.utils.normalize import normalize_reward
+    from tests.helpers import pack_tiles
+    g = golden('encodings')
+    onehot = ops.observe_onehot(torch.from_numpy(pack_tiles(g['tiles']).view(np.int64)).cuda(), 31)
+    np.testing.assert_array_equal(onehot.reshape(len(g['tiles']), -1).cpu().numpy(), g['onehot'])
+    enc = encode_flatten(g['tiles'][3], encodage_size=31)
+    assert enc.dtype == np.int64 and enc.shape == (496,)
+    np.testing.assert_array_equal(enc, g['onehot'][3])
+    for r, want in zip(g['rewards'], g['normalized']):
+        assert normalize_reward(float(r)) == want
+    # test_environment.py:87-97: encoded observation length 4*4*31
+    env = Env(size=4, encoded=True)
+    assert env.reset().ndim == 1 and len(env.observation) == 4 * 4 * 31
+    # test_environment.py:99-115: normalised reward is log-compressed
+    env_n, env_r = Env(size=4, normalize=True), Env(size=4)
+    board = np.array([[2, 2, 0, 0], [0] * 4, [0] * 4, [0] * 4])
+    env_n._current_state, env_r._current_state = board.copy(), board.copy()
+    _, rn, _ = env_n.step(0)
+    _, rr, _ = env_r.step(0)
+    assert 0 < rn < rr and rn == 2 / 16

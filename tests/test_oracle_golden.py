@@ -355,3 +355,15 @@ def test_restatement_against_live_reference(oracle):
         b, rb = npe.next_state(t.copy(), 1, r2)
         np.testing.assert_array_equal(a, b)
         assert ra == rb
+
+
+# ---------------------------------------------------------------- presentation helpers (utils/)
+
+def test_oracle_encodings_match_reference(golden):
+    """utils/binary.py encode_flatten(., 31) and utils/normalize.py normalize_reward."""
+    g = golden('encodings')
+    for tiles, want in zip(g['tiles'], g['onehot']):
+        np.testing.assert_array_equal(npe.encode_flatten(tiles.astype(np.int64), 31), want)
+    for r, want in zip(g['rewards'], g['normalized']):
+        assert npe.normalize_reward(float(r)) == want
+    assert g['normalized'][0] == 0.0 and g['normalized'][1] == 2 / 16
