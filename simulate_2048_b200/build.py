@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libg2048.so')
 SOURCES = ['g2048_kernels.cu']
-HEADERS = ['g2048_device.cuh', os.path.join('..', '..', 'include', 'g2048.h')]
+HEADERS = ['g2048_device.cuh', 'g2048_fast.cuh', os.path.join('..', '..', 'include', 'g2048.h')]
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',

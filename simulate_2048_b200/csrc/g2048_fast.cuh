@@ -11,15 +11,18 @@
 //     and use adds where the operands have disjoint bits.
 //
 // Orientation.  Up / right / down become "left" through a transform F_a and back through
-// G_a = F_a^-1.  With  T = Bt.Nt  (Nt: swap nibbles 1<->4, 3<->6 inside each 32-bit half;
-// Bt: 2x2 byte-block transpose across the halves) and  R = Br.Nr  (Nr: swap the nibbles of
-// every byte; Br: swap the bytes of every halfword), Nr commutes with every byte permutation
-// and Nt with Bt, so
-//   F_a = P_a . Nr^[a&2] . Nt^[a&1]          G_a = Nt^[a&1] . Nr^[a&2] . Q_a
-// with ONE byte permutation each (a PRMT pair whose selector is per-thread data) and the nibble
-// stages made conditional by a mask that is zero when the stage is off.  The six per-action
-// words (two masks, four selectors) come from a 4-entry shared-memory table: two conflict-free
-// broadcast loads per env.
+// G_a = F_a^-1.  Lines are independent, so any line order serves, and each F_a factors into ONE
+// nibble-level involution S_a applied inside each 32-bit half and ONE byte permutation P_a:
+//   up    : transpose       S = swap nibbles 1<->4, 3<->6 (delta swap, distance 12 bits)
+//   right : mirror          S = swap the nibbles of every byte (distance 4)
+//   down  : anti-transpose  S = swap nibbles 0<->5, 2<->7 (distance 20) — columns taken right to
+//           left and read bottom-up, which keeps S an involution (a plain transpose followed by a
+//           mirror is a 4-cycle on the 2x2 nibble blocks and would need two stages)
+//   F_a = P_a . S_a          G_a = S_a . Q_a
+// The delta swap t = (x ^ x>>k) & m; x ^= t ^ t<<k takes its distance from two per-thread
+// multipliers (x>>k = mulhi(x, 2^(32-k)), t<<k = t * 2^k) and is a no-op when m = 0, so every
+// action runs the same 4 instructions per half; P_a / Q_a are one PRMT pair whose selector is
+// per-thread data.  The seven per-action words come from a 4-entry shared-memory table.
 //
 // Row-table entry (u32): bits 0..15 = (merge score of the row) >> 2, bits 16..31 = the row after
 // a left move.  With the score in the LOW half the four entries of a board simply add up:
@@ -136,40 +139,40 @@ G2048_HD u32 mulhi(u32 a, u32 b) {
 
 // ---- per-action orientation words -----------------------------------------------------------
 struct alignas(32) Orient {
-    u32 mt, mr;        // nibble-stage masks (0 = stage off)
+    u32 mask;          // delta-swap mask (0 = no nibble stage)
+    u32 mul_hi;        // 2^(32-k): x >> k as the high word of a product (IMAD.HI)
+    u32 mul_lo;        // 2^k:      t << k as a product (IMAD)
+    u32 pad0;
     u32 f_lo, f_hi;    // forward byte permutation (PRMT selectors)
     u32 b_lo, b_hi;    // backward byte permutation
-    u32 pad0, pad1;    // 32-byte entries
 };
 
-// action 0 left, 1 up, 2 right, 3 down
-#define G2048_ORIENT_TABLE                                                          \
-    {                                                                               \
-        {0x00000000u, 0x00000000u, 0x3210u, 0x7654u, 0x3210u, 0x7654u, 0u, 0u},     \
-        {0x0000F0F0u, 0x00000000u, 0x6240u, 0x7351u, 0x6240u, 0x7351u, 0u, 0u},     \
-        {0x00000000u, 0x0F0F0F0Fu, 0x2301u, 0x6745u, 0x2301u, 0x6745u, 0u, 0u},     \
-        {0x0000F0F0u, 0x0F0F0F0Fu, 0x2604u, 0x3715u, 0x7351u, 0x6240u, 0u, 0u},     \
+// action 0 left, 1 up, 2 right, 3 down.  Derivation of the selectors: tools/derive_orient.py.
+#define G2048_ORIENT_TABLE                                                                        \
+    {                                                                                             \
+        {0x00000000u, 0x00000000u, 0x00000000u, 0u, 0x3210u, 0x7654u, 0x3210u, 0x7654u},          \
+        {0x0000F0F0u, 0x00100000u, 0x00001000u, 0u, 0x6240u, 0x7351u, 0x6240u, 0x7351u},          \
+        {0x0F0F0F0Fu, 0x10000000u, 0x00000010u, 0u, 0x2301u, 0x6745u, 0x2301u, 0x6745u},          \
+        {0x00000F0Fu, 0x00001000u, 0x00100000u, 0u, 0x3715u, 0x2604u, 0x3715u, 0x2604u},          \
     }
 
-// conditional nibble stages on one half: swap the nibble pairs selected by the mask
-G2048_HD u32 stage_nt(u32 x, u32 mt) {
-    const u32 t = lop3<(kA ^ kB) & kC>(x, shr<12>(x), mt);
-    return lop3<kA ^ kB ^ kC>(x, t, t << 12);
-}
-G2048_HD u32 stage_nr(u32 x, u32 mr) {
-    const u32 t = lop3<(kA ^ kB) & kC>(x, shr<4>(x), mr);
-    return lop3<kA ^ kB ^ kC>(x, t, t << 4);
+// the one conditional nibble stage: delta swap of the nibble pairs selected by the mask, with the
+// shift distance k (12 / 4 / 20 bits) carried by two per-thread multipliers, so that both shifts
+// run on the FMA pipe and the stage is the same instruction sequence for every action
+G2048_HD u32 stage(u32 x, const Orient& o) {
+    const u32 t = lop3<(kA ^ kB) & kC>(x, mulhi(x, o.mul_hi), o.mask);
+    return lop3<kA ^ kB ^ kC>(x, t, t * o.mul_lo);
 }
 
 G2048_HD void orient_forward(u32& lo, u32& hi, const Orient& o) {
-    const u32 l = stage_nr(stage_nt(lo, o.mt), o.mr), h = stage_nr(stage_nt(hi, o.mt), o.mr);
+    const u32 l = stage(lo, o), h = stage(hi, o);
     lo = prmt(l, h, o.f_lo);
     hi = prmt(l, h, o.f_hi);
 }
 G2048_HD void orient_backward(u32& lo, u32& hi, const Orient& o) {
     const u32 l = prmt(lo, hi, o.b_lo), h = prmt(lo, hi, o.b_hi);
-    lo = stage_nt(stage_nr(l, o.mr), o.mt);
-    hi = stage_nt(stage_nr(h, o.mr), o.mt);
+    lo = stage(l, o);
+    hi = stage(h, o);
 }
 
 // bit 3 of every nibble = (nibble != 0); all other bits 0
@@ -193,9 +196,9 @@ G2048_HD u32 hash_row16(u32 row) { return (row ^ ((row >> 4) & 0x0FFFu)) & 0xFFF
 
 // true when some tile is >= 16384 (nibble >= 14): such boards leave the fast path, which keeps
 // every row inside the staged table window and rules out a 15+15 merge.
+G2048_HD u32 big_tile_half(u32 x) { return lop3<kA & kB & kC>(x, x << 1, x << 2); }  // dirty outside bit 3
 G2048_HD u32 big_tile_bits(u32 lo, u32 hi) {
-    const u32 a = lop3<kA & kB & kC>(lo, lo << 1, lo << 2), b = lop3<kA & kB & kC>(hi, hi << 1, hi << 2);
-    return lop3<(kA | kB) & kC>(a, b, 0x88888888u);
+    return lop3<(kA | kB) & kC>(big_tile_half(lo), big_tile_half(hi), 0x88888888u);
 }
 G2048_HD bool has_big_tile(u32 lo, u32 hi) { return big_tile_bits(lo, hi) != 0u; }
 
@@ -241,13 +244,15 @@ G2048_HD u32 move_fast(u32 lo, u32 hi, const Orient& o, const Lut& lut, u32 one,
     u32 xl = lo, xh = hi;
     orient_forward(xl, xh, o);
     const u32 yl = hash_rows(xl), yh = hash_rows(xh);
-    // byte offsets: the x4 is an IMAD.SHL (FMA pipe), one ALU op per lookup for the extraction
-    const u32 e0 = lut((yl << 2) & 0x3FFFCu), e1 = lut(prmt(yl, 0u, 0x4432u) << 2);
-    const u32 e2 = lut((yh << 2) & 0x3FFFCu), e3 = lut(prmt(yh, 0u, 0x4432u) << 2);
+    // byte offsets: one ALU op per lookup for the extraction, the x4 on the FMA pipe (IMAD.SHL;
+    // for the high row a run-time multiplier, or ptxas folds shift + base into an ALU-pipe LEA)
+    const u32 four = one << 2;
+    const u32 e0 = lut((yl << 2) & 0x3FFFCu), e1 = lut(prmt(yl, 0u, 0x4432u) * four);
+    const u32 e2 = lut((yh << 2) & 0x3FFFCu), e3 = lut(prmt(yh, 0u, 0x4432u) * four);
     al = prmt(e0, e1, 0x7632);
     ah = prmt(e2, e3, 0x7632);
     moved = (al != xl) | (ah != xh);
-    const u32 reward = (add(add(e0, e1, one), add(e2, e3, one), one) << 2) & 0x3FFFCu;
+    const u32 reward = shr<14>(add(add(e0, e1, one), add(e2, e3, one), one) << 16);  // (sum & 0xFFFF) * 4
     orient_backward(al, ah, o);
     return reward;
 }
@@ -257,8 +262,8 @@ G2048_HD u32 move_fast(u32 lo, u32 hi, const Orient& o, const Lut& lut, u32 one,
 // Inclusive prefix count of EMPTY cells at nibble k of a half = (k + 1) - prefix(tiles), so with
 // t = tile indicators at bit 0:  g = 0x87654321 + (7 - r)*0x11111111 - t*0x11111111  has bit 3
 // set exactly in the nibbles whose empty-count exceeds r (every nibble stays <= 15).
-G2048_HD u32 spawn_marker(u32 nlo, u32 nhi, u32 tiles_lo, u32 rank, bool& in_hi) {
-    const u32 clo = 8u - tiles_lo;
+G2048_HD u32 spawn_marker(u32 nlo, u32 nhi, u32 tiles_lo, u32 rank, u32 one, bool& in_hi) {
+    const u32 clo = mad(tiles_lo, 0u - one, 8u);   // 8 - tiles_lo as an IMAD
     in_hi = rank >= clo;
     const u32 nsel = in_hi ? nhi : nlo;
     const u32 r = in_hi ? rank - clo : rank;
@@ -279,17 +284,19 @@ G2048_HD FastOut transition_fast(u32 lo, u32 hi, const Orient& o, u32 rank, u32 
     if (kPhilox) rank = mulhi(w0, ne);
     const bool ok = rank < ne;
     bool in_hi;
-    const u32 bit3 = spawn_marker(nlo, nhi, tiles_lo, rank, in_hi);
+    const u32 bit3 = spawn_marker(nlo, nhi, tiles_lo, rank, one, in_hi);
     const u32 tile = shr<3>(bit3) * exp;         // exponent 1 or 2 at bit 0 of that nibble
+    // status bits besides the mask: 0x10 is cancelled below when some action is legal;
+    // not moved -> 0x10, moved without a valid spawn -> MOVED | BADSPAWN, moved and spawned -> MOVED
+    u32 status = moved ? 0xB0u : 0x10u;
     if (moved & ok) {
+        status = 0x30u;
         if (in_hi) { ah += tile; nhi += bit3; } else { al += tile; nlo += bit3; }
     }
 
-    // ---- flags of the new board ----
+    // ---- flags of the new board: mask | DONE (0x10) iff no action is legal | status ----
     const u32 m = legal_mask(al, ah, nlo, nhi, one);
-    u32 f = mad(nonzero01(m), 0xFFFFFFF0u, m) + 0x10u;   // + DONE (0x10) iff no action is legal
-    if (moved) f += 0x20u;                               // MOVED
-    if (moved & !ok) f += 0x80u;                         // BADSPAWN
+    const u32 f = add(mad(nonzero01(m), 0xFFFFFFF0u, m), status, one);
     return FastOut{al, ah, reward, f};
 }
 

@@ -335,8 +335,10 @@ __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 s
                                            int4& rw, u32& fl) {
     u32 big = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) big |= fast::big_tile_bits((u32)in.b[k], (u32)(in.b[k] >> 32));
-    const bool slow = (big != 0u) | (!kPhilox && (spawns & 0x80808080u) != 0u);
+    for (int k = 0; k < 4; ++k)  // one 3-input OR per env, the bit-3 mask once per tile
+        big = fast::lop3<fast::kA | fast::kB | fast::kC>(big, fast::big_tile_half((u32)in.b[k]),
+                                                         fast::big_tile_half((u32)(in.b[k] >> 32)));
+    const bool slow = ((big & 0x88888888u) != 0u) | (!kPhilox && (spawns & 0x80808080u) != 0u);
     int rws[4];
     fl = 0;
     if (slow) {
@@ -360,7 +362,7 @@ __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 s
         const unsigned char* op = reinterpret_cast<const unsigned char*>(s_orient) + fast::prmt(act4, 0u, 0x4440u + k);
         const uint4 o0 = *reinterpret_cast<const uint4*>(op), o1 = *reinterpret_cast<const uint4*>(op + 16);
         fast::Orient o;
-        o.mt = o0.x; o.mr = o0.y; o.f_lo = o0.z; o.f_hi = o0.w; o.b_lo = o1.x; o.b_hi = o1.y;
+        o.mask = o0.x; o.mul_hi = o0.y; o.mul_lo = o0.z; o.f_lo = o1.x; o.f_hi = o1.y; o.b_lo = o1.z; o.b_hi = o1.w;
         u32 rank = 0, exp, w0 = 0;
         if (kPhilox) {
             const Philox4 p = philox_env(a.keys, env0 + k, a.step_base, G2048_PHILOX_TAG_STEP);
@@ -965,7 +967,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(const ExpandA
                 u32 lo = rec.x, hi = rec.y;
                 if (cc > 1u) {  // cc == 1: full afterstate, the child is the state itself
                     bool in_hi;
-                    const u32 bit3 = fast::spawn_marker(rec.z, rec.w, __popc(rec.z), lane >> 1, in_hi);
+                    const u32 bit3 = fast::spawn_marker(rec.z, rec.w, __popc(rec.z), lane >> 1, 1u, in_hi);
                     const u32 tile = (bit3 >> 3) << (lane & 1u);
                     if (in_hi) hi |= tile; else lo |= tile;
                 }
@@ -1159,7 +1161,7 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const Rollout
         if (kFast && !fast::has_big_tile(lo, hi)) {
             const uint4 o0 = sm.orient[2u * action], o1 = sm.orient[2u * action + 1u];
             fast::Orient o;
-            o.mt = o0.x; o.mr = o0.y; o.f_lo = o0.z; o.f_hi = o0.w; o.b_lo = o1.x; o.b_hi = o1.y;
+            o.mask = o0.x; o.mul_hi = o0.y; o.mul_lo = o0.z; o.f_lo = o1.x; o.f_hi = o1.y; o.b_lo = o1.z; o.b_hi = o1.w;
             bool moved;
             reward = fast::move_fast(lo, hi, o, lut, one, al, ah, moved);
         } else {
@@ -1172,7 +1174,7 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const Rollout
         nhi = fast::nz8(ah, one);
         const u32 tiles_lo = fast::popc(nlo), ne = 16u - (tiles_lo + fast::popc(nhi));
         bool in_hi;
-        const u32 bit3 = fast::spawn_marker(nlo, nhi, tiles_lo, __umulhi(p.x, ne), in_hi);
+        const u32 bit3 = fast::spawn_marker(nlo, nhi, tiles_lo, __umulhi(p.x, ne), one, in_hi);
         const u32 exp = 2u - fast::nonzero01(__umulhi(p.y, 10u));  // word1 < 0x1999999A -> 4
         const u32 tile = fast::shr<3>(bit3) * exp;
         if (in_hi) { ah += tile; nhi += bit3; } else { al += tile; nlo += bit3; }
