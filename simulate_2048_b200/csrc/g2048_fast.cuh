@@ -18,11 +18,11 @@
 //   down  : anti-transpose  S = swap nibbles 0<->5, 2<->7 (distance 20) — columns taken right to
 //           left and read bottom-up, which keeps S an involution (a plain transpose followed by a
 //           mirror is a 4-cycle on the 2x2 nibble blocks and would need two stages)
-//   F_a = P_a . S_a          G_a = S_a . Q_a
+//   F_a = P_a . S_a          G_a = S_a . P_a      (every P_a is an involution)
 // The delta swap t = (x ^ x>>k) & m; x ^= t ^ t<<k takes its distance from two per-thread
 // multipliers (x>>k = mulhi(x, 2^(32-k)), t<<k = t * 2^k) and is a no-op when m = 0, so every
-// action runs the same 4 instructions per half; P_a / Q_a are one PRMT pair whose selector is
-// per-thread data.  The seven per-action words come from a 4-entry shared-memory table.
+// action runs the same 4 instructions per half; P_a is one PRMT pair whose selector is per-thread
+// data.  The five per-action words come from a 4-entry shared-memory table.
 //
 // Row-table entry (u32): bits 0..15 = (merge score of the row) >> 2, bits 16..31 = the row after
 // a left move.  With the score in the LOW half the four entries of a board simply add up:
@@ -111,6 +111,35 @@ G2048_HD u32 nonzero01(u32 x) {
 #endif
 }
 
+// acc + k if x != 0, as a predicated IMAD: a LOP3 that produces x can set the predicate itself
+// (LOP3.LUT P, ...), so no ALU-pipe instruction is spent on the test.  k = 0 stands for `one`
+// (a literal multiplier 1 would let ptxas fold the mad into an ALU-pipe add).
+template <u32 k>
+G2048_HD u32 add_if_nonzero(u32 acc, u32 x, u32 one) {
+#if defined(__CUDA_ARCH__)
+    if (k == 1u)
+        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p mad.lo.u32 %0, %2, %2, %0;\n\t}"
+            : "+r"(acc) : "r"(x), "r"(one));
+    else
+        asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p mad.lo.u32 %0, %2, %3, %0;\n\t}"
+            : "+r"(acc) : "r"(x), "r"(one), "n"(k));
+    return acc;
+#else
+    return x ? acc + k * one : acc;
+#endif
+}
+
+// x - 16 if x != ref (cancels the DONE bit once some mask bit was added), predicated IMAD
+G2048_HD u32 sub16_if_differ(u32 x, u32 ref, u32 one) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %0, %1;\n\t@p mad.lo.u32 %0, %2, 0xFFFFFFF0, %0;\n\t}"
+        : "+r"(x) : "r"(ref), "r"(one));
+    return x;
+#else
+    return x != ref ? x - 16u * one : x;
+#endif
+}
+
 // a * b + c on the FMA pipe (IMAD)
 G2048_HD u32 mad(u32 a, u32 b, u32 c) {
 #if defined(__CUDA_ARCH__)
@@ -139,21 +168,21 @@ G2048_HD u32 mulhi(u32 a, u32 b) {
 
 // ---- per-action orientation words -----------------------------------------------------------
 struct alignas(32) Orient {
-    u32 mask;          // delta-swap mask (0 = no nibble stage)
-    u32 mul_hi;        // 2^(32-k): x >> k as the high word of a product (IMAD.HI)
-    u32 mul_lo;        // 2^k:      t << k as a product (IMAD)
-    u32 pad0;
-    u32 f_lo, f_hi;    // forward byte permutation (PRMT selectors)
-    u32 b_lo, b_hi;    // backward byte permutation
+    u32 mask;            // delta-swap mask (0 = no nibble stage)
+    u32 mul_hi;          // 2^(32-k): x >> k as the high word of a product (IMAD.HI)
+    u32 mul_lo;          // 2^k:      t << k as a product (IMAD)
+    u32 sel_lo, sel_hi;  // byte permutation (PRMT selectors); every P_a is an involution, so the
+                         // same pair serves forwards and backwards
+    u32 pad0, pad1, pad2;
 };
 
 // action 0 left, 1 up, 2 right, 3 down.  Derivation of the selectors: tools/derive_orient.py.
-#define G2048_ORIENT_TABLE                                                                        \
-    {                                                                                             \
-        {0x00000000u, 0x00000000u, 0x00000000u, 0u, 0x3210u, 0x7654u, 0x3210u, 0x7654u},          \
-        {0x0000F0F0u, 0x00100000u, 0x00001000u, 0u, 0x6240u, 0x7351u, 0x6240u, 0x7351u},          \
-        {0x0F0F0F0Fu, 0x10000000u, 0x00000010u, 0u, 0x2301u, 0x6745u, 0x2301u, 0x6745u},          \
-        {0x00000F0Fu, 0x00001000u, 0x00100000u, 0u, 0x3715u, 0x2604u, 0x3715u, 0x2604u},          \
+#define G2048_ORIENT_TABLE                                                             \
+    {                                                                                  \
+        {0x00000000u, 0x00000000u, 0x00000000u, 0x3210u, 0x7654u, 0u, 0u, 0u},         \
+        {0x0000F0F0u, 0x00100000u, 0x00001000u, 0x6240u, 0x7351u, 0u, 0u, 0u},         \
+        {0x0F0F0F0Fu, 0x10000000u, 0x00000010u, 0x2301u, 0x6745u, 0u, 0u, 0u},         \
+        {0x00000F0Fu, 0x00001000u, 0x00100000u, 0x3715u, 0x2604u, 0u, 0u, 0u},         \
     }
 
 // the one conditional nibble stage: delta swap of the nibble pairs selected by the mask, with the
@@ -166,11 +195,11 @@ G2048_HD u32 stage(u32 x, const Orient& o) {
 
 G2048_HD void orient_forward(u32& lo, u32& hi, const Orient& o) {
     const u32 l = stage(lo, o), h = stage(hi, o);
-    lo = prmt(l, h, o.f_lo);
-    hi = prmt(l, h, o.f_hi);
+    lo = prmt(l, h, o.sel_lo);
+    hi = prmt(l, h, o.sel_hi);
 }
 G2048_HD void orient_backward(u32& lo, u32& hi, const Orient& o) {
-    const u32 l = prmt(lo, hi, o.b_lo), h = prmt(lo, hi, o.b_hi);
+    const u32 l = prmt(lo, hi, o.sel_lo), h = prmt(lo, hi, o.sel_hi);
     lo = stage(l, o);
     hi = stage(h, o);
 }
@@ -208,7 +237,9 @@ G2048_HD bool has_big_tile(u32 lo, u32 hi) { return big_tile_bits(lo, hi) != 0u;
 //   right / down: a tile equal to its neighbour, or an empty cell
 //                 whose neighbour is a tile                           (n & ~e) | (~n & s)
 // The shifted-in neighbour bits at column 0 / row 0 are garbage and masked out at the end.
-G2048_HD u32 legal_mask(u32 lo, u32 hi, u32 nlo, u32 nhi, u32 one) {
+// Returns base + mask (base = 0 for the plain mask; the step kernel passes its status bits so
+// that the first mask bit is a predicated add as well instead of a select).
+G2048_HD u32 legal_mask(u32 lo, u32 hi, u32 nlo, u32 nhi, u32 one, u32 base = 0u) {
     constexpr u32 kFwd = kA & ~(kB & kC) & 0xFF, kBwd = ((kA & ~kB) | (~kA & kC)) & 0xFF;
     // horizontal, valid at columns 1..3
     const u32 elo = differ8_dirty(lo, lo << 4, one), ehi = differ8_dirty(hi, hi << 4, one);  // differs from left neighbour
@@ -221,8 +252,13 @@ G2048_HD u32 legal_mask(u32 lo, u32 hi, u32 nlo, u32 nhi, u32 one) {
     const u32 tlo = nlo << 16;
     const u32 U = lop3<(kA & kB) | kC>(lop3<kFwd>(nlo, flo, tlo), 0xFFFF0000u, lop3<kFwd>(nhi, fhi, thi));
     const u32 D = lop3<(kA & kB) | kC>(lop3<kBwd>(nlo, flo, tlo), 0xFFFF0000u, lop3<kBwd>(nhi, fhi, thi));
-    // any bit set -> 0/1 (min.u32, full rate), then l + 2u + 4r + 8d on the FMA pipe
-    return mad(mad(nonzero01(D), 2u, nonzero01(R)), 4u, mad(nonzero01(U), 2u, nonzero01(L)));
+    // any bit set -> mask bit: four predicated IMADs, the predicates set by the LOP3s above
+    u32 m = base;
+    m = add_if_nonzero<1u>(m, L, one);
+    m = add_if_nonzero<2u>(m, U, one);
+    m = add_if_nonzero<4u>(m, R, one);
+    m = add_if_nonzero<8u>(m, D, one);
+    return m;
 }
 
 struct FastOut {
@@ -282,7 +318,8 @@ G2048_HD FastOut transition_fast(u32 lo, u32 hi, const Orient& o, u32 rank, u32 
     u32 nlo = nz8(al, one), nhi = nz8(ah, one);
     const u32 tiles_lo = popc(nlo), ne = 16u - (tiles_lo + popc(nhi));
     if (kPhilox) rank = mulhi(w0, ne);
-    const bool ok = rank < ne;
+    // a Philox rank is < ne by construction (and a move always leaves an empty cell)
+    const bool ok = kPhilox ? true : rank < ne;
     bool in_hi;
     const u32 bit3 = spawn_marker(nlo, nhi, tiles_lo, rank, one, in_hi);
     const u32 tile = shr<3>(bit3) * exp;         // exponent 1 or 2 at bit 0 of that nibble
@@ -295,9 +332,8 @@ G2048_HD FastOut transition_fast(u32 lo, u32 hi, const Orient& o, u32 rank, u32 
     }
 
     // ---- flags of the new board: mask | DONE (0x10) iff no action is legal | status ----
-    const u32 m = legal_mask(al, ah, nlo, nhi, one);
-    const u32 f = add(mad(nonzero01(m), 0xFFFFFFF0u, m), status, one);
-    return FastOut{al, ah, reward, f};
+    const u32 f = legal_mask(al, ah, nlo, nhi, one, status);
+    return FastOut{al, ah, reward, sub16_if_differ(f, status, one)};
 }
 
 }  // namespace fast

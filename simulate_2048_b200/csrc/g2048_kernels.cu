@@ -290,12 +290,26 @@ struct TileIn {
     u32 actions, spawns;
 };
 
+// per-thread stream cursors: advanced once per loop trip, every access a compile-time offset away
+struct StepCursor {
+    const u64* boards_in;
+    const uint8_t* actions;
+    const uint8_t* spawns;
+    u64* boards_out;
+    int32_t* rewards;
+    uint8_t* flags;
+    u64 env;  // global env id of the thread's first env (Philox counter)
+    __device__ __forceinline__ void advance(size_t d) {
+        boards_in += d; actions += d; spawns += d; boards_out += d; rewards += d; flags += d; env += d;
+    }
+};
+
 template <bool kPhilox>
-__device__ __forceinline__ TileIn load_tile(const StepArgs& a, size_t env0) {
+__device__ __forceinline__ TileIn load_tile(const StepCursor& c, size_t off) {
     TileIn t;
-    t.boards = ld_boards4(a.boards_in + env0);
-    t.actions = ld_u32_stream(a.actions + env0);
-    t.spawns = kPhilox ? 0u : ld_u32_stream(a.spawns + env0);
+    t.boards = ld_boards4(c.boards_in + off);
+    t.actions = ld_u32_stream(c.actions + off);
+    t.spawns = kPhilox ? 0u : ld_u32_stream(c.spawns + off);
     return t;
 }
 
@@ -317,6 +331,7 @@ __device__ __noinline__ uint4 transition_slow(u64 board, u32 action, u32 spawn, 
 // known to ptxas, so a lookup is `LDS R, [R + UR]` with the base in a uniform register.
 extern __shared__ __align__(128) u32 smem_words[];
 
+
 struct SmemLut {
     // staged (hashed) row table at the start of dynamic shared memory, indexed by BYTE offset
     __device__ __forceinline__ u32 operator()(u32 byte_off) const {
@@ -333,12 +348,23 @@ __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 s
                                            const StepArgs& a, u64 env0, const SmemLut& lut,
                                            const uint4* __restrict__ s_orient, Boards4& ob,
                                            int4& rw, u32& fl) {
-    u32 big = 0;
+    // Range test in two levels.  Cheap filter (one LOP3 per word): bit 3 of acc is set where some
+    // nibble has bits 3 and 2 set, i.e. a tile >= 4096.  Only then the exact test (nibble >= 14)
+    // runs — never on the benchmark set or in random play, rarely with a strong player.
+    u32 acc = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)  // one 3-input OR per env, the bit-3 mask once per tile
-        big = fast::lop3<fast::kA | fast::kB | fast::kC>(big, fast::big_tile_half((u32)in.b[k]),
-                                                         fast::big_tile_half((u32)(in.b[k] >> 32)));
-    const bool slow = ((big & 0x88888888u) != 0u) | (!kPhilox && (spawns & 0x80808080u) != 0u);
+    for (int k = 0; k < 4; ++k) {
+        const u32 lo = (u32)in.b[k], hi = (u32)(in.b[k] >> 32);
+        acc = fast::lop3<fast::kA | (fast::kB & fast::kC)>(acc, lo, lo << 1);
+        acc = fast::lop3<fast::kA | (fast::kB & fast::kC)>(acc, hi, hi << 1);
+    }
+    bool slow = !kPhilox && (spawns & 0x80808080u) != 0u;
+    if ((acc & 0x88888888u) != 0u) {
+        u32 big = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) big |= fast::big_tile_bits((u32)in.b[k], (u32)(in.b[k] >> 32));
+        slow |= big != 0u;
+    }
     int rws[4];
     fl = 0;
     if (slow) {
@@ -360,9 +386,10 @@ __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 s
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const unsigned char* op = reinterpret_cast<const unsigned char*>(s_orient) + fast::prmt(act4, 0u, 0x4440u + k);
-        const uint4 o0 = *reinterpret_cast<const uint4*>(op), o1 = *reinterpret_cast<const uint4*>(op + 16);
+        const uint4 o0 = *reinterpret_cast<const uint4*>(op);
         fast::Orient o;
-        o.mask = o0.x; o.mul_hi = o0.y; o.mul_lo = o0.z; o.f_lo = o1.x; o.f_hi = o1.y; o.b_lo = o1.z; o.b_hi = o1.w;
+        o.mask = o0.x; o.mul_hi = o0.y; o.mul_lo = o0.z; o.sel_lo = o0.w;
+        o.sel_hi = *reinterpret_cast<const u32*>(op + 16);
         u32 rank = 0, exp, w0 = 0;
         if (kPhilox) {
             const Philox4 p = philox_env(a.keys, env0 + k, a.step_base, G2048_PHILOX_TAG_STEP);
@@ -392,27 +419,27 @@ struct TileBuf {
 };
 
 template <bool kPhilox, int kGroups>
-__device__ __forceinline__ void load_tiles(TileBuf<kPhilox, kGroups>& t, const StepArgs& a, size_t env0) {
+__device__ __forceinline__ void load_tiles(TileBuf<kPhilox, kGroups>& t, const StepCursor& c, size_t off) {
 #pragma unroll
-    for (int j = 0; j < kGroups; ++j) t.g[j] = load_tile<kPhilox>(a, env0 + 4 * j);
+    for (int j = 0; j < kGroups; ++j) t.g[j] = load_tile<kPhilox>(c, off + 4 * j);
 }
 
 template <bool kPhilox, int kGroups>
 __device__ __forceinline__ void compute_store_tiles(const TileBuf<kPhilox, kGroups>& t, const StepArgs& a,
-                                                    size_t env0, const SmemLut& lut,
+                                                    const StepCursor& c, size_t off, const SmemLut& lut,
                                                     const uint4* __restrict__ s_orient) {
     Boards4 ob[kGroups];
     int4 rw[kGroups];
     u32 fl[kGroups];
 #pragma unroll
     for (int j = 0; j < kGroups; ++j)
-        step_tile4<kPhilox>(t.g[j].boards, t.g[j].actions, t.g[j].spawns, a, a.env_offset + env0 + 4 * j,
+        step_tile4<kPhilox>(t.g[j].boards, t.g[j].actions, t.g[j].spawns, a, c.env + off + 4 * j,
                             lut, s_orient, ob[j], rw[j], fl[j]);
 #pragma unroll
     for (int j = 0; j < kGroups; ++j) {
-        st_boards4(a.boards_out + env0 + 4 * j, ob[j]);
-        st_int4_stream(a.rewards + env0 + 4 * j, rw[j]);
-        st_u32_stream(a.flags + env0 + 4 * j, fl[j]);
+        st_boards4(c.boards_out + off + 4 * j, ob[j]);
+        st_int4_stream(c.rewards + off + 4 * j, rw[j]);
+        st_u32_stream(c.flags + off + 4 * j, fl[j]);
     }
 }
 
@@ -434,23 +461,27 @@ __global__ void __launch_bounds__(kThreads, 1) step_lut_kernel(const StepArgs a)
     const size_t full_tiles = a.n / kTile;
     const size_t t_begin = full_tiles * blockIdx.x / gridDim.x;
     const size_t t_end = full_tiles * (blockIdx.x + 1) / gridDim.x;
-    size_t env0 = t_begin * kTile + threadIdx.x * kPerThread;
-    const size_t env_end = t_end * kTile;
+    const size_t tiles = t_end - t_begin;
+    StepCursor c{a.boards_in, a.actions, a.spawns, a.boards_out, a.rewards, a.flags, a.env_offset};
+    c.advance(t_begin * kTile + threadIdx.x * kPerThread);
 
     TileBuf<kPhilox, kGroups> bufA, bufB;
-    if (env0 < env_end) load_tiles(bufA, a, env0);
+    if (tiles != 0) load_tiles(bufA, c, 0);
 
     table_stage_wait(bar);  // __syncthreads inside also publishes s_orient
     const SmemLut lut{};
 
-    while (env0 < env_end) {
-        const bool hasB = env0 + kTile < env_end;
-        if (hasB) load_tiles(bufB, a, env0 + kTile);          // tile B loads while tile A computes
-        compute_store_tiles(bufA, a, env0, lut, s_orient);
+    // bounds are pointer compares: a 32-bit trip counter makes ptxas build a jump table (BRX) for the
+    // three tests below, which costs 12 % of the throughput
+    const u64* const end = c.boards_in + tiles * kTile;
+    while (c.boards_in < end) {
+        const bool hasB = c.boards_in + kTile < end;
+        if (hasB) load_tiles(bufB, c, kTile);
+        compute_store_tiles(bufA, a, c, 0, lut, s_orient);
         if (!hasB) break;
-        if (env0 + 2 * kTile < env_end) load_tiles(bufA, a, env0 + 2 * kTile);
-        compute_store_tiles(bufB, a, env0 + kTile, lut, s_orient);
-        env0 += 2 * kTile;
+        if (c.boards_in + 2 * kTile < end) load_tiles(bufA, c, 2 * kTile);
+        compute_store_tiles(bufB, a, c, kTile, lut, s_orient);
+        c.advance(2 * kTile);
     }
 
     // ragged tail (< one tile): spread over the CTAs, one env per thread through the exact path
@@ -1159,9 +1190,10 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const Rollout
         const u32 action = sm.pick[mask * 4u + __umulhi(p.z, (u32)__popc(mask))];
         u32 al, ah, reward;
         if (kFast && !fast::has_big_tile(lo, hi)) {
-            const uint4 o0 = sm.orient[2u * action], o1 = sm.orient[2u * action + 1u];
+            const uint4 o0 = sm.orient[2u * action];
             fast::Orient o;
-            o.mask = o0.x; o.mul_hi = o0.y; o.mul_lo = o0.z; o.f_lo = o1.x; o.f_hi = o1.y; o.b_lo = o1.z; o.b_hi = o1.w;
+            o.mask = o0.x; o.mul_hi = o0.y; o.mul_lo = o0.z; o.sel_lo = o0.w;
+            o.sel_hi = sm.orient[2u * action + 1u].x;
             bool moved;
             reward = fast::move_fast(lo, hi, o, lut, one, al, ah, moved);
         } else {
