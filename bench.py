@@ -457,8 +457,23 @@ def run_ours(args):
             ex_d = ops.expand(eb, children='dense', zero_fill=False)
             n_children = int(ex_c.children.numel())
             reps = 40 if n_e == 65536 else 10
-            _, t_c, _ = timed(lambda: ops.expand(eb, children='compact', out=ex_c), reps, 3)
-            _, t_d, _ = timed(lambda: ops.expand(eb, children='dense', out=ex_d), reps, 3)
+
+            def graph_time(fn, calls):
+                # device time per call: `calls` back-to-back calls replayed from one CUDA graph
+                # (a Python/ctypes call costs ~10 us, more than the kernels of a 65536-board call)
+                fn()
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                side_e = torch.cuda.Stream()
+                with torch.cuda.stream(side_e):
+                    with torch.cuda.graph(g, stream=side_e):
+                        for _ in range(calls):
+                            fn()
+                torch.cuda.synchronize()
+                _, mean_s, _ = timed(g.replay, 5, 3)
+                return mean_s / calls
+            t_c = graph_time(lambda: ops.expand(eb, children='compact', out=ex_c), reps)
+            t_d = graph_time(lambda: ops.expand(eb, children='dense', out=ex_d), reps)
             bytes_c = n_e * (8 + 8 + 1 + 32 + 16 + 4 + 4) + 8 * n_children
             exp_out[str(n_e)] = {
                 'children_per_board': n_children / n_e,
@@ -467,7 +482,8 @@ def run_ours(args):
                 'dense': {'us_per_launch': t_d * 1e6, 'boards_per_sec': n_e / t_d},
             }
             del ex_c, ex_d
-        exp_out['note'] = ('g2048_expand into preallocated outputs; compact = children packed at child_offsets '
+        exp_out['note'] = ('g2048_expand into preallocated outputs (two kernels: moves, children), device time per call '
+                           'from a CUDA graph of back-to-back calls; compact = children packed at child_offsets '
                            '(offsets from a count pass + cumsum, not timed), dense = [N,4,16,2] slots')
         extra['expand'] = exp_out
         # config 4: fused rollouts to termination

@@ -916,6 +916,8 @@ struct ExpandArgs {
     int layout;
     size_t n;
     const u32* table;
+    const u32* table_hashed;
+    u32 one;  // run-time 1 (see StepArgs)
 };
 
 __device__ __forceinline__ u32 empty_cells16(Board b) {
@@ -930,31 +932,51 @@ __device__ __forceinline__ u32 empty_cells16(Board b) {
     return m;
 }
 
-// Two phases per warp-tile of 32 boards.
-//   1. lane = board: the four afterstates (the transposed board is shared by up and down),
-//      rewards, counts, mask; the fixed-size outputs are written with 128-bit stores and a
-//      16-byte record {after.lo, after.hi, n_lo, n_hi} per (board, action) goes to shared memory.
-//   2. lane = child: for every legal (board, action) the warp writes the child segment
-//      coalesced; lane j builds child j (empty cell j/2 in row-major order, tile 2 then 4:
-//      gameboard.py:154,162) with the branch-free rank select of g2048_fast.cuh.
-constexpr int kExpandWarps = 8;
+// Expansion in two kernels.
+//   expand_moves_*_kernel   lane = board: the four afterstates through the fast move of
+//       g2048_fast.cuh with compile-time orientation words, rewards, empty counts, child counts
+//       and the legal mask; all fixed-size outputs are one wide store per lane.  Large batches
+//       run it persistent with the hashed row table staged in shared memory (TMA bulk copy, as
+//       the step kernel); small ones gather the same table from L2.  A board holding a tile
+//       >= 16384 takes the exact first-generation path.
+//   expand_children_kernel   warp = board, lane = empty cell of one of the legal afterstates:
+//       the (action, rank) of lane j follows from the four counts, the lane builds BOTH children
+//       of its cell (tile 2 then 4: gameboard.py:154,162) with the branch-free rank select and
+//       writes them with one 128-bit store.  In the compact layout the children of a board are
+//       contiguous, so the warp writes one coalesced run of up to 512 bytes per pass.
+// A legal move always leaves an empty cell, so child counts are even and compact offsets keep
+// the 16-byte alignment; an odd caller-supplied offset falls back to two 64-bit stores.
+struct GlobalLut {
+    const u32* tab;  // hashed row table in global memory (L2 resident)
+    __device__ __forceinline__ u32 operator()(u32 byte_off) const {
+        return __ldg(reinterpret_cast<const u32*>(reinterpret_cast<const unsigned char*>(tab) + byte_off));
+    }
+};
 
-__global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(const ExpandArgs a) {
-    __shared__ uint4 s_rec[kExpandWarps][128];
-    __shared__ long long s_off[kExpandWarps][128];
-    __shared__ uint8_t s_cc[kExpandWarps][128];
-    const GlobalTable T{a.table};
-    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const size_t warp_stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t wb = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) - lane; wb < a.n; wb += warp_stride) {
-        const size_t i = wb + lane;
-        const bool live = i < a.n;
-        const Board b = live ? split(a.boards[i]) : Board{0u, 0u};
-        const Board bt = transpose(b);  // shared by up and down
-        u32 m = 0, ovf = 0, ne4 = 0, cc4 = 0;
-        long long off = (live && a.layout == G2048_CHILDREN_COMPACT) ? a.child_offsets[i] : 0;
-        uint2 after4[4];
-        int rew4[4];
+template <class Lut>
+__device__ __forceinline__ void expand_moves_board(const ExpandArgs& a, size_t i, const Lut& lut) {
+    constexpr fast::Orient kOrient[4] = G2048_ORIENT_TABLE;
+    const u64 packed = a.boards[i];
+    const u32 lo = (u32)packed, hi = (u32)(packed >> 32);
+    u32 m = 0, ovf = 0, ne4 = 0, cc4 = 0;
+    uint2 after4[4];
+    int rew4[4];
+    if (!fast::has_big_tile(lo, hi)) {
+#pragma unroll
+        for (u32 act = 0; act < 4; ++act) {
+            u32 al, ah;
+            bool moved;
+            rew4[act] = (int)fast::move_fast(lo, hi, kOrient[act], lut, a.one, al, ah, moved);
+            const u32 ne = 16u - __popc(fast::nz8(al, a.one)) - __popc(fast::nz8(ah, a.one));
+            m |= moved ? (1u << act) : 0u;
+            after4[act] = make_uint2(al, ah);
+            ne4 |= ne << (8 * act);
+            cc4 |= (moved ? 2u * ne : 0u) << (8 * act);  // a move always leaves an empty cell
+        }
+    } else {
+        const GlobalTable T{a.table};
+        const Board b{lo, hi};
+        const Board bt = transpose(b);
 #pragma unroll
         for (u32 act = 0; act < 4; ++act) {
             Board x = (act & 1u) ? bt : b;
@@ -962,52 +984,133 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(const ExpandA
             MoveResult r = move_left(x, T);
             if (act & 2u) r.after = reverse_rows(r.after);
             if (act & 1u) r.after = transpose(r.after);
-            const bool moved = live & ((r.after.lo != b.lo) | (r.after.hi != b.hi));
+            const bool moved = (r.after.lo != b.lo) | (r.after.hi != b.hi);
             m |= moved ? (1u << act) : 0u;
             ovf |= r.overflow ? 1u : 0u;
-            const u32 nlo = nz8(r.after.lo), nhi = nz8(r.after.hi);
-            const u32 ne = 16u - __popc(nlo) - __popc(nhi);
-            const u32 cc = moved ? (ne ? 2u * ne : 1u) : 0u;
+            const u32 ne = 16u - __popc(nz8(r.after.lo)) - __popc(nz8(r.after.hi));
             after4[act] = make_uint2(r.after.lo, r.after.hi);
             rew4[act] = (int)r.score;
             ne4 |= ne << (8 * act);
-            cc4 |= cc << (8 * act);
-            s_rec[w][lane * 4 + act] = make_uint4(r.after.lo, r.after.hi, nlo, nhi);
-            s_cc[w][lane * 4 + act] = (uint8_t)cc;
-            s_off[w][lane * 4 + act] = (a.layout == G2048_CHILDREN_DENSE) ? (long long)((i * 4 + act) * 32) : off;
-            off += cc;
+            cc4 |= (moved ? (ne ? 2u * ne : 1u) : 0u) << (8 * act);
         }
-        if (live) {
-            if (a.after) {
-                uint4* o = reinterpret_cast<uint4*>(a.after + i * 4);
-                o[0] = make_uint4(after4[0].x, after4[0].y, after4[1].x, after4[1].y);
-                o[1] = make_uint4(after4[2].x, after4[2].y, after4[3].x, after4[3].y);
-            }
-            if (a.rewards) *reinterpret_cast<int4*>(a.rewards + i * 4) = make_int4(rew4[0], rew4[1], rew4[2], rew4[3]);
-            if (a.num_empty) *reinterpret_cast<u32*>(a.num_empty + i * 4) = ne4;
-            if (a.child_count) *reinterpret_cast<u32*>(a.child_count + i * 4) = cc4;
-            if (a.mask) a.mask[i] = (uint8_t)(board_flags(m) | (ovf ? G2048_FLAG_OVERFLOW : 0u));
+    }
+    uint4* o = reinterpret_cast<uint4*>(a.after + i * 4);
+    o[0] = make_uint4(after4[0].x, after4[0].y, after4[1].x, after4[1].y);
+    o[1] = make_uint4(after4[2].x, after4[2].y, after4[3].x, after4[3].y);
+    if (a.rewards) *reinterpret_cast<int4*>(a.rewards + i * 4) = make_int4(rew4[0], rew4[1], rew4[2], rew4[3]);
+    if (a.num_empty) *reinterpret_cast<u32*>(a.num_empty + i * 4) = ne4;
+    *reinterpret_cast<u32*>(a.child_count + i * 4) = cc4;
+    if (a.mask) a.mask[i] = (uint8_t)(board_flags(m) | (ovf ? G2048_FLAG_OVERFLOW : 0u));
+}
+
+// persistent, hashed table staged in shared memory
+__global__ void __launch_bounds__(1024, 1) expand_moves_smem_kernel(const ExpandArgs a) {
+    u32* smem_tab = smem_words;
+    u64* bar = reinterpret_cast<u64*>(smem_words + kSmemRows);
+    table_stage_begin(smem_tab, bar, a.table_hashed);
+    table_stage_wait(bar);
+    const SmemLut lut{};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x)
+        expand_moves_board(a, i, lut);
+}
+
+// small batches: the same table gathered from L2
+__global__ void __launch_bounds__(256) expand_moves_gather_kernel(const ExpandArgs a) {
+    const GlobalLut lut{a.table_hashed};
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x)
+        expand_moves_board(a, i, lut);
+}
+
+constexpr int kChildWarps = 8;
+
+template <int kLayout>
+__global__ void __launch_bounds__(kChildWarps * 32) expand_children_kernel(const ExpandArgs a) {
+    // per warp: the records of a tile of 32 boards, loaded coalesced once (lane = board), then
+    // read back by the whole warp board after board.  In that second phase a lane serves a FIXED
+    // (action, rank) pair — action = lane / 8, rank = lane % 8 (+ 8 in the second pass) — so no
+    // per-child search for the segment is needed and the record is read once per board.
+    __shared__ uint4 s_rec[kChildWarps][32][4];  // {after.lo, after.hi, n_lo, n_hi} per action
+    __shared__ uint4 s_meta[kChildWarps][32];    // {counts, first pair of each action, offset lo, hi}
+    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const u32 act = lane >> 3, r0 = lane & 7u, byte_sel = 0x4440u + act;
+    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t tile = warp * 32; tile < a.n; tile += n_warps * 32) {
+        const size_t mine = tile + lane;
+        uint4 meta = make_uint4(0u, 0u, 0u, 0u);
+        if (mine < a.n) {
+            const u32 cc4 = *reinterpret_cast<const u32*>(a.child_count + mine * 4);
+            const uint4* src = reinterpret_cast<const uint4*>(a.after + mine * 4);
+            const uint4 s01 = src[0], s23 = src[1];
+            s_rec[w][lane][0] = make_uint4(s01.x, s01.y, fast::nz8(s01.x, 1u), fast::nz8(s01.y, 1u));
+            s_rec[w][lane][1] = make_uint4(s01.z, s01.w, fast::nz8(s01.z, 1u), fast::nz8(s01.w, 1u));
+            s_rec[w][lane][2] = make_uint4(s23.x, s23.y, fast::nz8(s23.x, 1u), fast::nz8(s23.y, 1u));
+            s_rec[w][lane][3] = make_uint4(s23.z, s23.w, fast::nz8(s23.z, 1u), fast::nz8(s23.w, 1u));
+            const unsigned long long off = (kLayout == G2048_CHILDREN_COMPACT)
+                                               ? (unsigned long long)a.child_offsets[mine]
+                                               : (unsigned long long)mine * 128ull;
+            // pairs (= empty cells) in front of each action's segment, one byte per action
+            const u32 h = (cc4 >> 1) & 0x7F7F7F7Fu;
+            const u32 first4 = (h << 8) + (h << 16) + (h << 24);
+            meta = make_uint4(cc4, first4, (u32)off, (u32)(off >> 32));
         }
-        if (a.layout == G2048_CHILDREN_NONE) continue;
+        s_meta[w][lane] = meta;
         __syncwarp();
-        for (u32 seg = 0; seg < 128u; ++seg) {
-            const u32 cc = s_cc[w][seg];  // warp-uniform
-            if (cc == 0u) continue;
-            const uint4 rec = s_rec[w][seg];
-            if (lane < cc) {
-                u32 lo = rec.x, hi = rec.y;
-                if (cc > 1u) {  // cc == 1: full afterstate, the child is the state itself
-                    bool in_hi;
-                    const u32 bit3 = fast::spawn_marker(rec.z, rec.w, __popc(rec.z), lane >> 1, 1u, in_hi);
-                    const u32 tile = (bit3 >> 3) << (lane & 1u);
-                    if (in_hi) hi |= tile; else lo |= tile;
+        const u32 n_here = (u32)min((size_t)32, a.n - tile);
+        for (u32 k = 0; k < n_here; ++k) {
+            const uint4 mt = s_meta[w][k];  // warp-uniform
+            const u32 cc4 = mt.x;
+            if (cc4 == 0u) continue;
+            u64* const board_dst = a.children + (((unsigned long long)mt.w << 32) | mt.z);
+            if (((cc4 & 0x01010101u) | (kLayout == G2048_CHILDREN_COMPACT ? (mt.z & 1u) : 0u)) == 0u) {
+                // even counts, 16-byte aligned destination: the common case
+                const uint4 rec = s_rec[w][k][act];
+                const u32 q = fast::prmt(cc4, 0u, byte_sel) >> 1;  // empty cells of my action
+                const u32 slot0 = (kLayout == G2048_CHILDREN_COMPACT) ? 2u * fast::prmt(mt.y, 0u, byte_sel) : 32u * act;
+                const u32 tiles_lo = __popc(rec.z);
+                const bool second = ((cc4 + 0x6F6F6F6Fu) & 0x80808080u) != 0u;  // some count > 16
+#pragma unroll
+                for (u32 pass = 0; pass < 2u; ++pass) {
+                    if (pass == 1u && !second) break;  // warp-uniform
+                    const u32 rank = r0 + 8u * pass;
+                    if (rank < q) {
+                        bool in_hi;
+                        const u32 bit3 = fast::spawn_marker(rec.z, rec.w, tiles_lo, rank, 1u, in_hi);
+                        const u32 t = bit3 >> 3;             // exponent 1 (tile 2) in the target nibble
+                        const u32 tl = in_hi ? 0u : t, th = in_hi ? t : 0u;
+                        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(
+                                         board_dst + slot0 + 2u * rank),
+                                     "r"(rec.x + tl), "r"(rec.y + th), "r"(rec.x + 2u * tl), "r"(rec.y + 2u * th)
+                                     : "memory");
+                    }
                 }
-                a.children[s_off[w][seg] + lane] = ((u64)hi << 32) | lo;
+            } else if (lane < 4u) {
+                // Odd counts or an odd caller-supplied offset: one lane per action, serially.  A
+                // count of 1 (an afterstate without an empty cell) cannot follow a move; the exact
+                // path keeps the reference's convention (gameboard.py:158-159) for completeness.
+                const u32 cc = (cc4 >> (8u * lane)) & 0xFFu;
+                u32 before = 0;
+                for (u32 q = 0; q < lane; ++q) before += (cc4 >> (8u * q)) & 0xFFu;
+                u64* dst = board_dst + ((kLayout == G2048_CHILDREN_COMPACT) ? before : 32u * lane);
+                const uint4 rec = s_rec[w][k][lane];
+                const u64 st = ((u64)rec.y << 32) | rec.x;
+                if (cc == 1u) {
+                    *dst = st;
+                } else {
+                    u32 q = 0;
+                    for (u32 cell = 0; cell < 16u && q < cc; ++cell) {
+                        if ((st >> (4u * cell)) & 0xFull) continue;
+                        dst[q++] = st | (1ull << (4u * cell));
+                        dst[q++] = st | (2ull << (4u * cell));
+                    }
+                }
             }
         }
         __syncwarp();
     }
 }
+
+constexpr size_t kExpandSmemMinBoards = (size_t)1 << 17;
 
 extern "C" int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* rewards,
                             uint8_t* mask, uint8_t* num_empty, uint8_t* child_count,
@@ -1024,11 +1127,44 @@ extern "C" int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* re
     DeviceState* s;
     int rc = current_state(&s);
     if (rc) return rc;
-    ExpandArgs a{reinterpret_cast<const u64*>(boards), reinterpret_cast<u64*>(after), rewards, mask,
-                 num_empty, child_count, reinterpret_cast<u64*>(children), child_offsets,
-                 child_layout, n, s->table};
-    expand_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(a);
+    cudaStream_t st = (cudaStream_t)stream;
+    // the children kernel reads the afterstates and counts back: stream-ordered scratch when the
+    // caller does not want them
+    void* scratch = nullptr;
+    u64* after_buf = reinterpret_cast<u64*>(after);
+    uint8_t* count_buf = child_count;
+    if (!after_buf || !count_buf) {
+        CU(cudaMallocAsync(&scratch, n * 36, st));
+        if (!after_buf) after_buf = reinterpret_cast<u64*>(scratch);
+        if (!count_buf) count_buf = reinterpret_cast<uint8_t*>(scratch) + n * 32;
+    }
+    ExpandArgs a{reinterpret_cast<const u64*>(boards), after_buf, rewards, mask,
+                 num_empty, count_buf, reinterpret_cast<u64*>(children), child_offsets,
+                 child_layout, n, s->table, s->table_hashed, 1u};
+    if (n >= kExpandSmemMinBoards) {
+        CU(cudaFuncSetAttribute(expand_moves_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(kSmemTableBytes + 64u)));
+        expand_moves_smem_kernel<<<s->sms, 1024, kSmemTableBytes + 64u, st>>>(a);
+    } else {
+        expand_moves_gather_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, st>>>(a);
+    }
     CU(cudaGetLastError());
+    if (child_layout != G2048_CHILDREN_NONE) {
+        // one wave: as many blocks as are resident at once (a partial second wave costs ~14 %)
+        static int occ = 0;
+        if (occ == 0) {
+            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &occ, expand_children_kernel<G2048_CHILDREN_COMPACT>, kChildWarps * 32, 0));
+            if (occ < 1) occ = 1;
+        }
+        const int grid = grid_for(n, kChildWarps * 32, s->sms, occ);
+        if (child_layout == G2048_CHILDREN_COMPACT)
+            expand_children_kernel<G2048_CHILDREN_COMPACT><<<grid, kChildWarps * 32, 0, st>>>(a);
+        else
+            expand_children_kernel<G2048_CHILDREN_DENSE><<<grid, kChildWarps * 32, 0, st>>>(a);
+        CU(cudaGetLastError());
+    }
+    if (scratch) CU(cudaFreeAsync(scratch, st));
     return G2048_OK;
 }
 
