@@ -49,7 +49,7 @@ def test_expand_reproduces_reference(T, ops, golden):
     assert int(ex.child_count.sum().item()) == 249022
 
 
-@pytest.mark.parametrize('n', [1, 31, 33, 65536, 65536 + 7])
+@pytest.mark.parametrize('n', [1, 31, 33, 65536, 65536 + 7, (1 << 17) + 37])
 def test_expand_vs_oracle(T, ops, oracle, n):
     boards = synthetic_packed(n, seed=n + 1, max_exp=6 if n % 2 else 11)
     for layout, code in (('none', 0), ('dense', 1), ('compact', 2)):
@@ -88,6 +88,35 @@ def test_expand_edge_cases(T, ops, oracle):
     # the single-empty board has 2 children per legal action with P = 0.9 / 0.1
     cc = ex.child_count.cpu().numpy()
     assert set(cc[4][cc[4] > 0]) == {2}
+
+
+def test_expand_large_batch_with_big_tiles(T, ops, oracle):
+    """n >= 2^17 runs the persistent moves kernel with the staged table; boards holding a tile
+    >= 16384 (also 32768 pairs that overflow) take its exact path inside the same launch."""
+    n = (1 << 17) + 5
+    boards = synthetic_packed(n, seed=99, max_exp=11)
+    boards[::97] = synthetic_packed(len(boards[::97]), seed=5, max_exp=15)
+    ex = ops.expand(dev(T, boards), children='compact')
+    want = oracle.expand(boards, child_layout=2)
+    np.testing.assert_array_equal(host(ex.after), want['after'])
+    np.testing.assert_array_equal(ex.rewards.cpu().numpy(), want['rewards'])
+    np.testing.assert_array_equal(ex.mask.cpu().numpy(), want['mask'])
+    np.testing.assert_array_equal(ex.child_count.cpu().numpy(), want['child_count'])
+    np.testing.assert_array_equal(host(ex.children), want['children'])
+    assert (ex.mask.cpu().numpy() & FLAG_OVERFLOW).any()
+
+
+def test_expand_odd_child_offsets(T, ops):
+    """Caller-supplied compact offsets that break the 16-byte alignment of the child pairs take
+    the 64-bit store path: same children, shifted by one slot."""
+    boards = dev(T, synthetic_packed(5000, seed=17))
+    ex = ops.expand(boards, children='compact')
+    total = ex.children.numel()
+    shifted = ex._replace(children=T.full((total + 1,), -1, dtype=T.int64, device='cuda'),
+                          child_offsets=ex.child_offsets + 1)
+    ops.expand(boards, children='compact', out=shifted)
+    assert int(shifted.children[0].item()) == -1
+    np.testing.assert_array_equal(host(shifted.children[1:]), host(ex.children))
 
 
 def test_after_state_vs_oracle(T, ops, oracle):
