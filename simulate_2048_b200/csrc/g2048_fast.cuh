@@ -269,7 +269,8 @@ struct FastOut {
 //   lut(off) returns the u32 entry of the staged (hashed) row table at BYTE offset `off`.
 //   Preconditions (checked by the caller): !has_big_tile(lo, hi).
 //   rank = spawn rank among the empties (injected) — ignored when kPhilox (then w0 draws it);
-//   exp  = spawned exponent (1 or 2);  one = the run-time constant 1 (see add()).
+//   exp_mul = spawned exponent (1 or 2) << 29: the tile is the high word of marker * exp_mul;
+//   one = the run-time constant 1 (see add()).
 // ---- building blocks (also used by the fused rollout kernel) ---------------------------------
 
 // Afterstate of (lo,hi) under the action whose orientation words are `o`.  Returns the merge
@@ -308,7 +309,7 @@ G2048_HD u32 spawn_marker(u32 nlo, u32 nhi, u32 tiles_lo, u32 rank, u32 one, boo
 }
 
 template <bool kPhilox, class Lut>
-G2048_HD FastOut transition_fast(u32 lo, u32 hi, const Orient& o, u32 rank, u32 exp, u32 w0,
+G2048_HD FastOut transition_fast(u32 lo, u32 hi, const Orient& o, u32 rank, u32 exp_mul, u32 w0,
                                  const Lut& lut, u32 one) {
     u32 al, ah;
     bool moved;
@@ -322,7 +323,7 @@ G2048_HD FastOut transition_fast(u32 lo, u32 hi, const Orient& o, u32 rank, u32 
     const bool ok = kPhilox ? true : rank < ne;
     bool in_hi;
     const u32 bit3 = spawn_marker(nlo, nhi, tiles_lo, rank, one, in_hi);
-    const u32 tile = shr<3>(bit3) * exp;         // exponent 1 or 2 at bit 0 of that nibble
+    const u32 tile = mulhi(bit3, exp_mul);       // exponent 1 or 2 at bit 0 of that nibble (one IMAD.HI)
     // status bits besides the mask: 0x10 is cancelled below when some action is legal;
     // not moved -> 0x10, moved without a valid spawn -> MOVED | BADSPAWN, moved and spawned -> MOVED
     u32 status = moved ? 0xB0u : 0x10u;

@@ -382,7 +382,7 @@ __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 s
     }
     const u32 act4 = (actions << 5) & 0x60606060u;     // byte k = 32 * action_k (byte offset)
     const u32 rank4 = spawns & 0x0F0F0F0Fu;            // byte k = spawn rank
-    const u32 exp4 = fast::shr<4>(spawns & 0x10101010u) + 0x01010101u;  // byte k = exponent (1 or 2)
+    const u32 exp4 = ((spawns & 0x10101010u) << 1) + 0x20202020u;       // byte k = exponent (1 or 2) << 5
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const unsigned char* op = reinterpret_cast<const unsigned char*>(s_orient) + fast::prmt(act4, 0u, 0x4440u + k);
@@ -390,18 +390,18 @@ __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 s
         fast::Orient o;
         o.mask = o0.x; o.mul_hi = o0.y; o.mul_lo = o0.z; o.sel_lo = o0.w;
         o.sel_hi = *reinterpret_cast<const u32*>(op + 16);
-        u32 rank = 0, exp, w0 = 0;
+        u32 rank = 0, exp_mul, w0 = 0;  // exp_mul = exponent << 29
         if (kPhilox) {
             const Philox4 p = philox_env(a.keys, env0 + k, a.step_base, G2048_PHILOX_TAG_STEP);
             w0 = p.x;
             // word1 < 0x1999999A  <=>  mulhi(word1, 10) == 0   (0x1999999A * 10 = 2^32 + 4)
-            exp = 2u - fast::nonzero01(__umulhi(p.y, 10u));
+            exp_mul = fast::mad(fast::nonzero01(__umulhi(p.y, 10u)), 0xE0000000u, 0x40000000u);
         } else {
             rank = fast::prmt(rank4, 0u, 0x4440u + k);
-            exp = fast::prmt(exp4, 0u, 0x4440u + k);
+            exp_mul = fast::prmt(exp4, 0u, 0x0444u + (k << 12));  // byte k of exp4 into byte 3
         }
         const fast::FastOut r = fast::transition_fast<kPhilox>((u32)in.b[k], (u32)(in.b[k] >> 32), o,
-                                                               rank, exp, w0, lut, a.one);
+                                                               rank, exp_mul, w0, lut, a.one);
         ob.b[k] = ((u64)r.hi << 32) | r.lo;
         rws[k] = (int)r.reward;
         fl = fast::add(r.flags << (8 * k), fl, a.one);

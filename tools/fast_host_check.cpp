@@ -54,7 +54,7 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < n; ++i) {
         const u32 lo = (u32)boards[i], hi = (u32)(boards[i] >> 32);
         if (has_big_tile(lo, hi)) { ++skipped; continue; }
-        FastOut f = transition_fast<false>(lo, hi, orient[act[i] & 3], spn[i] & 0xFu, 1u + ((spn[i] >> 4) & 1u), 0, lut, 1u);
+        FastOut f = transition_fast<false>(lo, hi, orient[act[i] & 3], spn[i] & 0xFu, (1u + ((spn[i] >> 4) & 1u)) << 29, 0, lut, 1u);
         const uint64_t got = ((uint64_t)f.hi << 32) | f.lo;
         if (got != out[i] || (int32_t)f.reward != rw[i] || (uint8_t)f.flags != fl[i]) {
             if (bad < 10)
@@ -73,7 +73,7 @@ int main(int argc, char** argv) {
         const uint64_t env = off + i;
         uint32_t ctr[4] = {(uint32_t)env, (uint32_t)(env >> 32), 7, 0}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, w[4];
         orc_philox4x32_10(ctr, key, w);
-        FastOut f = transition_fast<true>(lo, hi, orient[act[i] & 3], 0, 2u - nonzero01(mulhi(w[1], 10u)), w[0], lut, 1u);
+        FastOut f = transition_fast<true>(lo, hi, orient[act[i] & 3], 0, (2u - nonzero01(mulhi(w[1], 10u))) << 29, w[0], lut, 1u);
         const uint64_t got = ((uint64_t)f.hi << 32) | f.lo;
         if (got != out[i] || (int32_t)f.reward != rw[i] || (uint8_t)f.flags != fl[i]) {
             if (bad < 20)
