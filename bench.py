@@ -523,6 +523,13 @@ def run_ours(args):
         extra['selfplay_4096_fused'] = {'us_per_iteration': dt / 200 * 1e6, 'env_steps_per_sec': 4096 * 200 / dt,
                                         'note': 'BatchedEnv: next observation, legal mask, reward, done from ONE '
                                                 'graph-replayed launch per iteration'}
+        # row (f4): n-step TD(lambda) targets over device trajectory buffers [T=200, N=4096]
+        tr = torch.rand((200, 4096), device=dev) * 64
+        tv = torch.rand((200, 4096), device=dev) * 500
+        tout = torch.empty_like(tr)
+        _, t_ns, _ = timed(lambda: ops.nstep_returns(tr, tv, 0.999, 10, 0.5, out=tout), 20, 3)
+        extra['nstep_returns_200x4096'] = {'us_per_call': t_ns * 1e6, 'targets_per_sec': 200 * 4096 / t_ns,
+                                           'note': 'g2048_nstep_returns, n_steps 10, f64 arithmetic'}
         line['secondary'] = extra
 
     if rank == 0 and world == 1 and not args.no_cpu:

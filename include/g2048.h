@@ -179,6 +179,18 @@ int g2048_observe(const uint64_t* boards, float* obs, uint8_t* max_exp, size_t n
  * 16 <= width <= 64.  out is u8[n*16*width]. */
 int g2048_observe_onehot(const uint64_t* boards, uint8_t* out, int width, size_t n, void* stream);
 
+/* n-step TD(lambda) returns over device trajectory buffers (reinforce/training/self_play.py:524
+ * compute_n_step_returns, same weighting and normalisation), time-major layout [T][N]:
+ *   G_n(t) = sum_{i<n} discount^i r[t+i] + discount^n v[t+n]   (the bootstrap term only if t+n < len)
+ *   out[t] = sum_n w_n G_n(t) / sum_n w_n,  n = 1..min(n_steps, len - t),
+ *   w_n = (1-lambda) lambda^(n-1) for n < n_steps, lambda^(n-1) for n = n_steps;
+ *   out[t] = v[t] when the weights sum to 0.
+ * lengths i32[N] gives the trajectory length of each env (NULL: T for all); steps t >= length are
+ * written as 0.  Arithmetic is f64, inputs and output f32. */
+int g2048_nstep_returns(const float* rewards, const float* values, const int32_t* lengths,
+                        double discount, int n_steps, double td_lambda, float* out, size_t T,
+                        size_t n, void* stream);
+
 /*
  * Fused random-policy rollout to termination, board in registers:
  *   policy = uniform over legal actions (Philox word2), spawns from Philox words 0/1.

@@ -157,6 +157,26 @@ def normalize_reward(reward: float, max_tile: int = 2 ** 16) -> float:
     return 0.0 if reward == 0 else float(np.log2(reward) / np.log2(max_tile))
 
 
+def n_step_returns(rewards: np.ndarray, values: np.ndarray, discount: float, n_steps: int,
+                   td_lambda: float = 0.5) -> np.ndarray:
+    """reinforce/training/self_play.py:524-579 — TD(lambda)-weighted n-step returns of ONE
+    trajectory (float64): G_n = sum_{i<n} g^i r[t+i] (+ g^n v[t+n] if t+n < T), weights
+    (1-l) l^(n-1) for n < n_steps and l^(n-1) for n = n_steps, normalised by their sum."""
+    T = len(rewards)
+    out = np.zeros(T)
+    for t in range(T):
+        total = weight_sum = 0.0
+        for n in range(1, min(n_steps, T - t) + 1):
+            g_n = float(sum(discount ** i * rewards[t + i] for i in range(n)))
+            if t + n < T:
+                g_n += discount ** n * values[t + n]
+            w = (1 - td_lambda) * td_lambda ** (n - 1) if n < n_steps else td_lambda ** (n - 1)
+            total += w * g_n
+            weight_sum += w
+        out[t] = total / weight_sum if weight_sum > 0 else values[t]
+    return out
+
+
 class Game:
     """twentyfortyeight.py:10-140 (size 4, raw observation, raw reward)."""
 

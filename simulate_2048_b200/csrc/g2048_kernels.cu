@@ -1204,6 +1204,55 @@ extern "C" int g2048_after_state(const uint64_t* boards, uint64_t* children, uin
 }
 
 // ---------------------------------------------------------------------------------------------
+// n-step TD(lambda) returns (self_play.py:524): one thread per (t, env), time-major buffers so
+// that a warp reads consecutive envs of one time step; the n loop carries the discounted reward
+// sum, the discount power and the lambda power.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nstep_returns_kernel(const float* __restrict__ rewards,
+                                                            const float* __restrict__ values,
+                                                            const int32_t* __restrict__ lengths, double discount,
+                                                            int n_steps, double lam, float* __restrict__ out,
+                                                            size_t T, size_t n) {
+    const size_t total = T * n;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t t = idx / n, e = idx - t * n;
+        const size_t len = lengths ? (size_t)max(lengths[e], 0) : T;
+        if (t >= len) {
+            out[idx] = 0.0f;
+            continue;
+        }
+        const size_t n_max = min((size_t)max(n_steps, 0), len - t);
+        double ret = 0.0, wsum = 0.0, rsum = 0.0, g = 1.0, lp = 1.0;  // g = discount^(k-1), lp = lambda^(k-1)
+        for (size_t k = 1; k <= n_max; ++k) {
+            rsum += g * (double)rewards[(t + k - 1) * n + e];
+            g *= discount;
+            double gk = rsum;
+            if (t + k < len) gk += g * (double)values[(t + k) * n + e];
+            const double w = (k < (size_t)n_steps) ? (1.0 - lam) * lp : lp;
+            ret += w * gk;
+            wsum += w;
+            lp *= lam;
+        }
+        out[idx] = (float)(wsum > 0.0 ? ret / wsum : (double)values[idx]);
+    }
+}
+
+extern "C" int g2048_nstep_returns(const float* rewards, const float* values, const int32_t* lengths,
+                                   double discount, int n_steps, double td_lambda, float* out, size_t T,
+                                   size_t n, void* stream) {
+    if (T == 0 || n == 0) return G2048_OK;
+    if (!rewards || !values || !out || n_steps < 0) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    nstep_returns_kernel<<<grid_for(T * n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        rewards, values, lengths, discount, n_steps, td_lambda, out, T, n);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // fused random rollout: board, score, step counter live in registers until the game ends
 // ---------------------------------------------------------------------------------------------
 struct RolloutArgs {

@@ -19,7 +19,7 @@ from ._cabi import check, lib
 
 __all__ = [
     'StepOut', 'ExpandOut', 'RolloutOut', 'step', 'env_step', 'legal_flags', 'expand', 'reset',
-    'observe', 'observe_onehot', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'step_host', 'row_table', 'set_impl', 'set_tuning', 'init',
+    'observe', 'observe_onehot', 'nstep_returns', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'step_host', 'row_table', 'set_impl', 'set_tuning', 'init',
     'pinned_empty',
 ]
 
@@ -259,6 +259,28 @@ def observe_onehot(boards: torch.Tensor, width: int = 31) -> torch.Tensor:
     out = torch.empty((n, 16, width), dtype=torch.uint8, device=boards.device)
     with torch.cuda.device(boards.device):
         check(lib().g2048_observe_onehot(_ptr(boards), _ptr(out), int(width), n, _stream()))
+    return out
+
+
+def nstep_returns(rewards: torch.Tensor, values: torch.Tensor, discount: float, n_steps: int,
+                  td_lambda: float = 0.5, lengths: Optional[torch.Tensor] = None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """n-step TD(lambda) returns over time-major trajectory buffers, float32[T,N]
+    (g2048_nstep_returns; self_play.py:524 compute_n_step_returns per env).  ``lengths`` int32[N]
+    limits each env's trajectory; steps beyond it come back as 0."""
+    if rewards.dim() != 2 or rewards.shape != values.shape:
+        raise ValueError('rewards and values must both be [T, N]')
+    for name, t in (('rewards', rewards), ('values', values)):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError(f'{name}: contiguous float32 CUDA tensor required')
+    T, n = rewards.shape
+    _opt(lengths, torch.int32, 'lengths', n)
+    if out is None:
+        out = torch.empty_like(rewards)
+    _opt(out, torch.float32, 'out', T * n)
+    with torch.cuda.device(rewards.device):
+        check(lib().g2048_nstep_returns(_ptr(rewards), _ptr(values), _ptr(lengths), float(discount),
+                                        int(n_steps), float(td_lambda), _ptr(out), T, n, _stream()))
     return out
 
 

@@ -106,3 +106,70 @@ class BatchedEnv:
             self._graph = g
         self._graph.replay()
         return self._result()
+
+
+class TrajectoryBuffer:
+    """Device-side trajectory storage for N parallel games, time-major (the layout
+    ``ops.nstep_returns`` reads): replaces the per-step ``np.array(...)`` host copies and the O(N)
+    Python bookkeeping of ``self_play.py:346-368``.  Step t holds the observation and legal mask
+    the policy saw, the action it chose, the reward of that action and whether the game was
+    already over (such steps carry reward 0 and do not count towards ``lengths``)."""
+
+    def __init__(self, capacity: int, n: int, device=None):
+        dev = torch.device('cuda' if device is None else device)
+        self.capacity, self.n, self.t = capacity, n, 0
+        self.obs = torch.zeros((capacity, n, 16), dtype=torch.float32, device=dev)
+        self.legal = torch.zeros((capacity, n, 4), dtype=torch.bool, device=dev)
+        self.actions = torch.zeros((capacity, n), dtype=torch.uint8, device=dev)
+        self.rewards = torch.zeros((capacity, n), dtype=torch.float32, device=dev)
+        self.active = torch.zeros((capacity, n), dtype=torch.bool, device=dev)
+        self.lengths = torch.zeros(n, dtype=torch.int32, device=dev)
+
+    def clear(self) -> None:
+        self.t = 0
+        self.lengths.zero_()
+
+    def returns(self, values: torch.Tensor, discount: float, n_steps: int, td_lambda: float = 0.5) -> torch.Tensor:
+        """n-step TD(lambda) targets float32[t,N] for the recorded steps (self_play.py:524);
+        ``values`` float32[t,N] are the caller's value estimates (search root values)."""
+        return ops.nstep_returns(self.rewards[:self.t], values.contiguous(), discount, n_steps, td_lambda,
+                                 lengths=self.lengths)
+
+
+def play_recorded(env: BatchedEnv, policy, buf: TrajectoryBuffer, max_steps: Optional[int] = None) -> int:
+    """Self-play loop without a host copy per step: ``policy(StepResult) -> uint8[N] actions`` runs
+    on the device, every step is appended to ``buf``.  The only host sync is one ``all done``
+    check every 16 steps.  Returns the number of recorded steps."""
+    res = env._result()
+    limit = buf.capacity if max_steps is None else min(max_steps, buf.capacity)
+    buf.clear()
+    while buf.t < limit:
+        t = buf.t
+        alive = ~res.done
+        buf.obs[t].copy_(res.observation)
+        buf.legal[t].copy_(res.legal_mask)
+        buf.active[t].copy_(alive)
+        buf.lengths.add_(alive.to(torch.int32))
+        actions = policy(res)
+        buf.actions[t].copy_(actions.reshape(-1))
+        res = env.step(actions)
+        buf.rewards[t].copy_(res.reward)
+        buf.t = t + 1
+        if buf.t % 16 == 0 and bool(res.done.all().item()):
+            break
+    return buf.t
+
+
+def uniform_legal_policy(seed: int = 0):
+    """Random policy over the legal actions, on the device (the reference's evaluation baseline)."""
+    gen: list = []
+
+    def policy(res: StepResult) -> torch.Tensor:
+        if not gen:
+            g = torch.Generator(device=res.legal_mask.device)
+            g.manual_seed(seed)
+            gen.append(g)
+        w = res.legal_mask.to(torch.float32)
+        w[:, 0] += (w.sum(dim=1) == 0).to(torch.float32)  # finished games: any action (a no-op)
+        return torch.multinomial(w, 1, generator=gen[0]).reshape(-1).to(torch.uint8)
+    return policy

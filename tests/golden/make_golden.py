@@ -18,6 +18,7 @@ Fixtures
                   every (board, action, next board, reward, done)
   fill_cells.npz  fill_cells draws on a fixed board, seeds 0..63, and reset(seed) boards
   encodings.npz   utils/binary.py encode_flatten(., 31) of 64 boards; utils/normalize.py values
+  nstep.npz       reinforce/training/self_play.py compute_n_step_returns on 7 random trajectories
 """
 
 from __future__ import annotations
@@ -217,7 +218,33 @@ def make_encodings() -> None:
     print('encodings', onehot.shape, norm[:4])
 
 
+def make_nstep() -> None:
+    """compute_n_step_returns lives in a module that imports jax (absent here): the function is
+    plain NumPy, so its definition alone is compiled from the reference source and executed."""
+    import ast
+    path = '/root/reference/reinforce/training/self_play.py'
+    tree = ast.parse(open(path).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == 'compute_n_step_returns'][0]
+    ns = {'np': np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, 'exec'), ns)
+    ref = ns['compute_n_step_returns']
+    rng = np.random.default_rng(524)
+    cases = []
+    for T, n_steps, disc, lam in ((1, 10, 0.999, 0.5), (7, 10, 0.999, 0.5), (40, 10, 0.999, 0.5),
+                                  (40, 5, 0.97, 0.8), (33, 1, 0.9, 0.5), (25, 4, 1.0, 0.0), (25, 4, 0.95, 1.0)):
+        r = (rng.integers(0, 64, T) * 4).astype(np.float32)
+        v = rng.normal(200.0, 80.0, T).astype(np.float32)
+        cases.append((r, v, disc, n_steps, lam, ref(r.astype(np.float64), v.astype(np.float64), disc, n_steps, lam)))
+    np.savez_compressed(
+        os.path.join(HERE, 'nstep.npz'),
+        **{f'r{i}': c[0] for i, c in enumerate(cases)}, **{f'v{i}': c[1] for i, c in enumerate(cases)},
+        **{f'out{i}': c[5] for i, c in enumerate(cases)},
+        params=np.array([[c[2], c[3], c[4]] for c in cases], dtype=np.float64))
+    print('nstep', len(cases), cases[2][5][:3])
+
+
 if __name__ == '__main__':
+    make_nstep()
     make_encodings()
     make_rows()
     make_synthetic()

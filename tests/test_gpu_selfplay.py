@@ -46,3 +46,43 @@ def test_batched_env_matches_oracle(oracle, graph, injected):
             np.testing.assert_array_equal(res.max_tile.cpu().numpy(), mt)
             np.testing.assert_array_equal(res.legal_mask.cpu().numpy(), ((fl[:, None] >> np.arange(4)) & 1).astype(bool))
     assert st[2].sum() > 0
+
+
+def test_recorded_self_play_replays_through_oracle(oracle):
+    """play_recorded keeps the whole trajectory on the device; replaying the recorded actions
+    through the oracle (same Philox key) must reproduce every recorded observation, legal mask and
+    reward, lengths must equal the oracle's step counts, and the n-step targets computed from the
+    buffers must match the reference formula per env."""
+    import torch
+    from oracle import np_engine as npe
+    from simulate_2048_b200.selfplay import BatchedEnv, TrajectoryBuffer, play_recorded, uniform_legal_policy
+    n, cap = 512, 400
+    env = BatchedEnv(n, seed=3, graph=True)
+    env.reset()
+    buf = TrajectoryBuffer(cap, n)
+    steps = play_recorded(env, uniform_legal_policy(seed=1), buf)
+    assert 100 < steps <= cap and bool(env.state.done.all().item())
+    key = env._key
+    st = (oracle.reset(n, seed=key), np.zeros(n, np.int32), np.zeros(n, np.uint8), np.zeros(n, np.float32))
+    obs_rec, legal_rec = buf.obs[:steps].cpu().numpy(), buf.legal[:steps].cpu().numpy()
+    act_rec, rew_rec = buf.actions[:steps].cpu().numpy(), buf.rewards[:steps].cpu().numpy()
+    active_rec = buf.active[:steps].cpu().numpy()
+    for t in range(steps):
+        o_obs, _ = oracle.observe(st[0])
+        np.testing.assert_array_equal(obs_rec[t], o_obs)
+        np.testing.assert_array_equal(legal_rec[t], ((oracle.mask(st[0])[:, None] >> np.arange(4)) & 1).astype(bool))
+        np.testing.assert_array_equal(active_rec[t], ~st[2].astype(bool))
+        # the policy only picks legal actions while the game is alive
+        alive = ~st[2].astype(bool)
+        assert legal_rec[t][alive, act_rec[t][alive]].all()
+        st, rew, _, _, _ = oracle.env_step(*st, act_rec[t], None, seed=key)
+        np.testing.assert_array_equal(rew_rec[t], rew)
+    lengths = buf.lengths.cpu().numpy()
+    np.testing.assert_array_equal(lengths, st[1])
+    assert lengths.min() > 20 and abs(lengths.mean() - 118) < 15  # random play: ~118 moves per game
+    values = torch.from_numpy(np.random.default_rng(0).normal(300, 50, (steps, n)).astype(np.float32)).cuda()
+    targets = buf.returns(values, 0.999, 10, 0.5).cpu().numpy()
+    for e in (0, 7, n - 1):
+        L = int(lengths[e])
+        want = npe.n_step_returns(rew_rec[:L, e].astype(np.float64), values[:L, e].cpu().numpy().astype(np.float64), 0.999, 10, 0.5)
+        np.testing.assert_allclose(targets[:L, e], want, rtol=4e-7, atol=1e-5)

@@ -367,3 +367,14 @@ def test_oracle_encodings_match_reference(golden):
     for r, want in zip(g['rewards'], g['normalized']):
         assert npe.normalize_reward(float(r)) == want
     assert g['normalized'][0] == 0.0 and g['normalized'][1] == 2 / 16
+
+
+# ---------------------------------------------------------------- n-step returns (self_play.py:524)
+
+def test_oracle_nstep_returns_match_reference(golden):
+    """compute_n_step_returns of the real reference on 7 trajectories (T = 1 .. 40; lambda 0, 1;
+    n_steps 1; discount 1).  Same arithmetic order, so the restatement agrees to rounding."""
+    g = golden('nstep')
+    for i, (disc, n_steps, lam) in enumerate(g['params']):
+        got = npe.n_step_returns(g[f'r{i}'].astype(np.float64), g[f'v{i}'].astype(np.float64), disc, int(n_steps), lam)
+        np.testing.assert_allclose(got, g[f'out{i}'], rtol=1e-13, atol=0)
