@@ -321,13 +321,16 @@ def run_ours(args):
                       torch.empty(B, dtype=torch.uint8, device=dev))
     env_offset = rank * B
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, collective=True):
         """CUDA events on the launching (current) stream around every step; barrier + sync on
-        both sides; returns (total seconds = max over ranks, mean launch seconds)."""
+        both sides; returns (total seconds = max over ranks, mean launch seconds).  The
+        rank-local secondary measurements pass collective=False: they run on rank 0 only, so a
+        barrier there would pair with the other ranks' final barrier and hang the job."""
+        sync = barrier if collective else torch.cuda.synchronize
         for _ in range(warmup):
             fn()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        barrier()
+        sync()
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
@@ -336,8 +339,10 @@ def run_ours(args):
             fn()
             b.record()
         t1.record()
-        barrier()
-        total = max_over_ranks(t0.elapsed_time(t1) / 1e3)
+        sync()
+        total = t0.elapsed_time(t1) / 1e3
+        if collective:
+            total = max_over_ranks(total)
         per = [a.elapsed_time(b) / 1e3 for a, b in ev]
         return total, sum(per) / len(per), min(per)
 
@@ -435,7 +440,7 @@ def run_ours(args):
                 for _ in range(len(views)):
                     one_m()
         torch.cuda.synchronize()
-        _, g_mean, g_min = timed(graph.replay, 20, 3)
+        _, g_mean, g_min = timed(graph.replay, 20, 3, collective=False)
         lat_mean, lat_min = g_mean / len(views), g_min / len(views)
         extra['latency_1m'] = {'boards': m1, 'us_per_launch_mean': lat_mean * 1e6,
                                'us_per_launch_min': lat_min * 1e6, 'env_steps_per_sec': m1 / lat_mean,
@@ -444,7 +449,7 @@ def run_ours(args):
                                        'slices replayed back to back from one CUDA graph'}
         # LUT-in-shared-memory vs pure register arithmetic (north star: "the choice evidenced by ncu")
         ops.set_impl(2)
-        r_total, r_mean, _ = timed(step_inj, 10, 3)
+        r_total, r_mean, _ = timed(step_inj, 10, 3, collective=False)
         ops.set_impl(0)
         extra['register_arithmetic_variant'] = {'env_steps_per_sec': B / r_mean,
                                                 'achieved_gbs': BYTES_INJECTED * B / r_mean / 1e9,
@@ -470,7 +475,7 @@ def run_ours(args):
                         for _ in range(calls):
                             fn()
                 torch.cuda.synchronize()
-                _, mean_s, _ = timed(g.replay, 5, 3)
+                _, mean_s, _ = timed(g.replay, 5, 3, collective=False)
                 return mean_s / calls
             t_c = graph_time(lambda: ops.expand(eb, children='compact', out=ex_c), reps)
             t_d = graph_time(lambda: ops.expand(eb, children='dense', out=ex_d), reps)
@@ -491,7 +496,7 @@ def run_ours(args):
         ro = ops.rollout(n_roll, seed=1, per_env=False)
         torch.cuda.synchronize()
         r_steps = int(ro.stats[1].item())
-        _, ro_mean, _ = timed(lambda: ops.rollout(n_roll, seed=1, per_env=False), 3, 1)
+        _, ro_mean, _ = timed(lambda: ops.rollout(n_roll, seed=1, per_env=False), 3, 1, collective=False)
         extra['rollout'] = {'envs': n_roll, 'env_steps_per_sec': r_steps / ro_mean,
                             'mean_length': r_steps / n_roll, 'ms': ro_mean * 1e3}
         # config 5: self-play stepping loop, N = 4096, 200 steps, three API calls per iteration
@@ -527,7 +532,7 @@ def run_ours(args):
         tr = torch.rand((200, 4096), device=dev) * 64
         tv = torch.rand((200, 4096), device=dev) * 500
         tout = torch.empty_like(tr)
-        _, t_ns, _ = timed(lambda: ops.nstep_returns(tr, tv, 0.999, 10, 0.5, out=tout), 20, 3)
+        _, t_ns, _ = timed(lambda: ops.nstep_returns(tr, tv, 0.999, 10, 0.5, out=tout), 20, 3, collective=False)
         extra['nstep_returns_200x4096'] = {'us_per_call': t_ns * 1e6, 'targets_per_sec': 200 * 4096 / t_ns,
                                            'note': 'g2048_nstep_returns, n_steps 10, f64 arithmetic'}
         line['secondary'] = extra

@@ -34,3 +34,17 @@ def test_is_packed_detection():
     assert not core.is_packed(torch.zeros((4, 4), dtype=torch.int32))
     with pytest.raises(TypeError):
         core.pack_boards(torch.zeros(3, dtype=torch.int32))
+
+
+def test_bench_rank_local_block_has_no_collective():
+    """bench.py's secondary measurements run on rank 0 only: a barrier / all-reduce inside that
+    block pairs with the other ranks' final barrier and hangs the torchrun job (seen at N=2)."""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'bench.py')).read()
+    a = src.index('# ---- secondary measurements (rank-local, short) ----')
+    b = src.index("line['secondary'] = extra")
+    block = src[a:b]
+    assert 'barrier(' not in block and 'max_over_ranks(' not in block and 'dist.' not in block
+    calls = re.findall(r'timed\(.*', block)
+    assert calls and all('collective=False' in c for c in calls), calls
