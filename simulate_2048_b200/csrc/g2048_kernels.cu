@@ -16,6 +16,7 @@
 // No Triton, no CPU fallback: every entry point either launches these kernels or fails.
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <mutex>
 
 #include "g2048_device.cuh"
@@ -1536,7 +1537,7 @@ extern "C" int g2048_row_table_host(uint16_t* result, uint32_t* reward, uint8_t*
 namespace {
 struct HostPipe {
     static constexpr int kSlots = 4;
-    static constexpr size_t kChunk = (size_t)1 << 20;  // 1 Mi envs / chunk: 10 MB in, 13 MB out
+    static constexpr size_t kChunk = (size_t)1 << 21;  // capacity of a slot (envs); the stage size is chosen at run time
     bool ready = false;
     cudaStream_t stream[kSlots];
     uint64_t *d_in[kSlots], *d_out[kSlots];
@@ -1578,10 +1579,16 @@ extern "C" int g2048_step_host(const uint64_t* boards_in, const uint8_t* actions
     HostPipe* p;
     rc = pipe_get(&p);
     if (rc) return rc;
+    static size_t chunk = 0;  // envs per pipeline stage (<= kChunk); env G2048_HOST_CHUNK_LOG2 overrides
+    if (chunk == 0) {
+        const char* e = getenv("G2048_HOST_CHUNK_LOG2");
+        const int lg = e ? atoi(e) : 21;
+        chunk = (lg >= 12 && lg <= 21) ? ((size_t)1 << lg) : HostPipe::kChunk;
+    }
     size_t done = 0;
     int slot = 0;
     while (done < n) {
-        const size_t m = (n - done < HostPipe::kChunk) ? n - done : HostPipe::kChunk;
+        const size_t m = (n - done < chunk) ? n - done : chunk;
         cudaStream_t st = p->stream[slot];
         // stream order makes reuse of this slot's buffers safe (previous chunk's D2H precedes)
         CU(cudaMemcpyAsync(p->d_in[slot], boards_in + done, m * 8, cudaMemcpyHostToDevice, st));
