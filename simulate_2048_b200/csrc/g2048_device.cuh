@@ -104,25 +104,15 @@ __host__ __device__ inline u32 make_entry(u32 row) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Row-table accessors.  `SmemTable` reads the staged copy (one LDS per row); `GlobalTable`
-// gathers from the full table through L1/L2.
+// Row-table accessors of the exact (first-generation) path: `GlobalTable` gathers from the full
+// table through L1/L2, `RegisterTable` computes the row.  The staged shared-memory copy is read
+// through `SmemLut` (g2048_kernels.cu) by the fast transition of g2048_fast.cuh.
 // ---------------------------------------------------------------------------------------------
 struct GlobalTable {
     const u32* __restrict__ tab;
     __device__ __forceinline__ u32 operator()(u32 row) const { return __ldg(tab + row); }
     // every row is in range
     __device__ __forceinline__ bool covers(Board) const { return true; }
-};
-
-struct SmemTable {
-    const u32* smem;              // kSmemRows entries
-    const u32* __restrict__ tab;  // full table (slow path)
-    __device__ __forceinline__ u32 operator()(u32 row) const { return smem[row]; }
-    // true when all four rows index inside the staged window
-    __device__ __forceinline__ bool covers(Board b) const {
-        return (b.lo < 0xE0000000u) & (b.hi < 0xE0000000u) & ((b.lo << 16) < 0xE0000000u) &
-               ((b.hi << 16) < 0xE0000000u);
-    }
 };
 
 struct MoveResult {
