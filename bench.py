@@ -499,6 +499,17 @@ def run_ours(args):
         _, ro_mean, _ = timed(lambda: ops.rollout(n_roll, seed=1, per_env=False), 3, 1, collective=False)
         extra['rollout'] = {'envs': n_roll, 'env_steps_per_sec': r_steps / ro_mean,
                             'mean_length': r_steps / n_roll, 'ms': ro_mean * 1e3}
+        # a larger batch amortises the tail (lanes whose last game ends early idle until the longest ends)
+        n_big = 1 << 24
+        ops.rollout(n_big, seed=1, per_env=False)
+        _, rb_mean, _ = timed(lambda: ops.rollout(n_big, seed=1, per_env=False), 2, 0, collective=False)
+        extra['rollout_16m'] = {'envs': n_big, 'env_steps_per_sec': r_steps / n_roll * n_big / rb_mean,
+                                'ms': rb_mean * 1e3, 'note': 'steps estimated from the mean length of the 1M run'}
+        try:  # integer-pipe utilisation of the rollout kernel from `ncu --set full` (profiles/)
+            with open(os.path.join(ROOT, 'profiles', 'r01_rollout_pipes.json')) as f:
+                extra['rollout']['integer_pipe_utilisation'] = json.load(f)
+        except Exception:
+            pass
         # config 5: self-play stepping loop, N = 4096, 200 steps, three API calls per iteration
         from simulate_2048_b200 import game
         st = game.batched_reset(7, 4096, device=dev)
