@@ -80,7 +80,8 @@ extern "C" {
 
 /* children layout for g2048_expand */
 #define G2048_CHILDREN_NONE 0
-#define G2048_CHILDREN_DENSE 1   /* children[((i*4 + a)*16 + k)*2 + v], k-th empty, v: 0 -> 2, 1 -> 4 */
+#define G2048_CHILDREN_DENSE 1   /* children[((i*4 + a)*16 + k)*2 + v], k-th empty, v: 0 -> 2, 1 -> 4;
+                                    every slot is written: slots beyond child_count hold 0 */
 #define G2048_CHILDREN_COMPACT 2 /* children[child_offsets[i] + ...], action-major, cell-major, value-minor */
 
 /* which row-move implementation the step kernel uses (for the ncu comparison) */

@@ -1036,32 +1036,53 @@ __global__ void __launch_bounds__(kChildWarps * 32) expand_children_kernel(const
     const u32 act = lane >> 3, r0 = lane & 7u, byte_sel = 0x4440u + act;
     const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
     const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    for (size_t tile = warp * 32; tile < a.n; tile += n_warps * 32) {
-        const size_t mine = tile + lane;
-        uint4 meta = make_uint4(0u, 0u, 0u, 0u);
+    // the records of the NEXT tile are fetched into registers while the current one is expanded
+    struct TileRegs {
+        uint4 s01, s23;
+        u32 cc4;
+        unsigned long long off;
+    };
+    auto fetch = [&](size_t tile_base) {
+        TileRegs r;
+        r.s01 = r.s23 = make_uint4(0u, 0u, 0u, 0u);
+        r.cc4 = 0u;
+        r.off = 0ull;
+        const size_t mine = tile_base + lane;
         if (mine < a.n) {
-            const u32 cc4 = *reinterpret_cast<const u32*>(a.child_count + mine * 4);
+            r.cc4 = *reinterpret_cast<const u32*>(a.child_count + mine * 4);
             const uint4* src = reinterpret_cast<const uint4*>(a.after + mine * 4);
-            const uint4 s01 = src[0], s23 = src[1];
+            r.s01 = src[0];
+            r.s23 = src[1];
+            r.off = (kLayout == G2048_CHILDREN_COMPACT) ? (unsigned long long)a.child_offsets[mine]
+                                                        : (unsigned long long)mine * 128ull;
+        }
+        return r;
+    };
+    TileRegs cur = fetch(warp * 32);
+    for (size_t tile = warp * 32; tile < a.n; tile += n_warps * 32) {
+        uint4 meta = make_uint4(0u, 0u, 0u, 0u);
+        {
+            const uint4 s01 = cur.s01, s23 = cur.s23;
+            const u32 cc4 = cur.cc4;
             s_rec[w][lane][0] = make_uint4(s01.x, s01.y, fast::nz8(s01.x, 1u), fast::nz8(s01.y, 1u));
             s_rec[w][lane][1] = make_uint4(s01.z, s01.w, fast::nz8(s01.z, 1u), fast::nz8(s01.w, 1u));
             s_rec[w][lane][2] = make_uint4(s23.x, s23.y, fast::nz8(s23.x, 1u), fast::nz8(s23.y, 1u));
             s_rec[w][lane][3] = make_uint4(s23.z, s23.w, fast::nz8(s23.z, 1u), fast::nz8(s23.w, 1u));
-            const unsigned long long off = (kLayout == G2048_CHILDREN_COMPACT)
-                                               ? (unsigned long long)a.child_offsets[mine]
-                                               : (unsigned long long)mine * 128ull;
             // pairs (= empty cells) in front of each action's segment, one byte per action
             const u32 h = (cc4 >> 1) & 0x7F7F7F7Fu;
             const u32 first4 = (h << 8) + (h << 16) + (h << 24);
-            meta = make_uint4(cc4, first4, (u32)off, (u32)(off >> 32));
+            meta = make_uint4(cc4, first4, (u32)cur.off, (u32)(cur.off >> 32));
         }
+        cur = fetch(tile + n_warps * 32);  // in flight during the expansion below
         s_meta[w][lane] = meta;
         __syncwarp();
         const u32 n_here = (u32)min((size_t)32, a.n - tile);
         for (u32 k = 0; k < n_here; ++k) {
             const uint4 mt = s_meta[w][k];  // warp-uniform
             const u32 cc4 = mt.x;
-            if (cc4 == 0u) continue;
+            // dense layout: every one of the board's 128 slots is written (children, then zeros), so
+            // the output needs no memset and DRAM sees full lines instead of partial 256-byte slots
+            if (kLayout == G2048_CHILDREN_COMPACT && cc4 == 0u) continue;
             u64* const board_dst = a.children + (((unsigned long long)mt.w << 32) | mt.z);
             if (((cc4 & 0x01010101u) | (kLayout == G2048_CHILDREN_COMPACT ? (mt.z & 1u) : 0u)) == 0u) {
                 // even counts, 16-byte aligned destination: the common case
@@ -1072,9 +1093,13 @@ __global__ void __launch_bounds__(kChildWarps * 32) expand_children_kernel(const
                 const bool second = ((cc4 + 0x6F6F6F6Fu) & 0x80808080u) != 0u;  // some count > 16
 #pragma unroll
                 for (u32 pass = 0; pass < 2u; ++pass) {
-                    if (pass == 1u && !second) break;  // warp-uniform
+                    if (kLayout == G2048_CHILDREN_COMPACT && pass == 1u && !second) break;  // warp-uniform
                     const u32 rank = r0 + 8u * pass;
-                    if (rank < q) {
+                    if (kLayout == G2048_CHILDREN_DENSE && rank >= q) {
+                        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(
+                                         board_dst + slot0 + 2u * rank), "r"(0u)
+                                     : "memory");
+                    } else if (rank < q) {
                         bool in_hi;
                         const u32 bit3 = fast::spawn_marker(rec.z, rec.w, tiles_lo, rank, 1u, in_hi);
                         const u32 t = bit3 >> 3;             // exponent 1 (tile 2) in the target nibble
@@ -1085,7 +1110,13 @@ __global__ void __launch_bounds__(kChildWarps * 32) expand_children_kernel(const
                                      : "memory");
                     }
                 }
-            } else if (lane < 4u) {
+            } else {
+              if (kLayout == G2048_CHILDREN_DENSE) {  // zero the board's slots first
+                  asm volatile("st.global.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(board_dst + 2u * lane), "r"(0u) : "memory");
+                  asm volatile("st.global.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(board_dst + 64u + 2u * lane), "r"(0u) : "memory");
+                  __syncwarp();
+              }
+              if (lane < 4u) {
                 // Odd counts or an odd caller-supplied offset: one lane per action, serially.  A
                 // count of 1 (an afterstate without an empty cell) cannot follow a move; the exact
                 // path keeps the reference's convention (gameboard.py:158-159) for completeness.
@@ -1105,6 +1136,7 @@ __global__ void __launch_bounds__(kChildWarps * 32) expand_children_kernel(const
                         dst[q++] = st | (2ull << (4u * cell));
                     }
                 }
+              }
             }
         }
         __syncwarp();

@@ -155,8 +155,9 @@ def expand(boards: torch.Tensor, children: str = 'none', zero_fill: bool = True,
            out: Optional[ExpandOut] = None) -> ExpandOut:
     """MCTS leaf expansion (g2048_expand): mask, the four afterstates + rewards and every chance
     child of each legal afterstate (gameboard.py:132 after_state order: cell-major, 2 then 4;
-    probability of a child = {0.9, 0.1} / num_empty).  Dense slots beyond ``child_count`` are
-    zero when ``zero_fill`` (a 64 MB memset per 65536 boards) and unspecified otherwise."""
+    probability of a child = {0.9, 0.1} / num_empty).  The dense layout writes every slot (the
+    slots beyond ``child_count`` hold 0), so no memset is needed; ``zero_fill`` is kept for
+    callers of the earlier signature and ignored."""
     _req(boards, torch.int64, 'boards')
     n = boards.numel()
     dev = boards.device
@@ -187,7 +188,7 @@ def expand(boards: torch.Tensor, children: str = 'none', zero_fill: bool = True,
             total = int(incl[-1].item()) if n else 0
             ch = torch.empty(total, dtype=torch.int64, device=dev)
         elif layout == _cabi.CHILDREN_DENSE:
-            ch = (torch.zeros if zero_fill else torch.empty)((n, 4, 16, 2), dtype=torch.int64, device=dev)
+            ch = torch.empty((n, 4, 16, 2), dtype=torch.int64, device=dev)
         check(lib().g2048_expand(_ptr(boards), _ptr(after), _ptr(rewards), _ptr(mask),
                                  _ptr(num_empty), _ptr(child_count), _ptr(ch), _ptr(off), layout, n,
                                  _stream()))

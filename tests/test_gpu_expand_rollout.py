@@ -119,6 +119,19 @@ def test_expand_odd_child_offsets(T, ops):
     np.testing.assert_array_equal(host(shifted.children[1:]), host(ex.children))
 
 
+def test_expand_dense_writes_every_slot(T, ops, oracle):
+    """The dense layout needs no memset: slots beyond child_count are written as 0 by the kernel,
+    also for done boards, illegal actions and boards on the exact (big tile) path."""
+    boards = synthetic_packed(3000, seed=23, max_exp=11)
+    boards[::50] = synthetic_packed(len(boards[::50]), seed=6, max_exp=15)
+    boards[:2] = pack_tiles(np.array([[[0] * 4] * 4, [[2, 4, 2, 4], [4, 2, 4, 2], [2, 4, 2, 4], [4, 2, 4, 2]]]))
+    d = dev(T, boards)
+    ex = ops.expand(d, children='dense')
+    ex.children.fill_(-1)
+    ops.expand(d, children='dense', out=ex)
+    np.testing.assert_array_equal(host(ex.children), oracle.expand(boards, child_layout=1)['children'])
+
+
 def test_after_state_vs_oracle(T, ops, oracle):
     boards = synthetic_packed(20000, seed=3)
     boards[:3] = pack_tiles(np.array([[[0] * 4] * 4, [[2] * 4] * 4, [[2, 4, 8, 16], [32, 64, 128, 0], [2, 4, 8, 16], [32, 64, 128, 256]]]))
