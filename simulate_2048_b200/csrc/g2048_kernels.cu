@@ -1174,15 +1174,17 @@ extern "C" int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* re
     ExpandArgs a{reinterpret_cast<const u64*>(boards), after_buf, rewards, mask,
                  num_empty, count_buf, reinterpret_cast<u64*>(children), child_offsets,
                  child_layout, n, s->table, s->table_hashed, 1u};
-    if (n >= kExpandSmemMinBoards) {
-        CU(cudaFuncSetAttribute(expand_moves_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)(kSmemTableBytes + 64u)));
-        expand_moves_smem_kernel<<<s->sms, 1024, kSmemTableBytes + 64u, st>>>(a);
-    } else {
-        expand_moves_gather_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, st>>>(a);
-    }
-    CU(cudaGetLastError());
-    if (child_layout != G2048_CHILDREN_NONE) {
+    // the launches in a helper so that the scratch buffer is released on every path
+    auto launch = [&]() -> int {
+        if (n >= kExpandSmemMinBoards) {
+            CU(cudaFuncSetAttribute(expand_moves_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(kSmemTableBytes + 64u)));
+            expand_moves_smem_kernel<<<s->sms, 1024, kSmemTableBytes + 64u, st>>>(a);
+        } else {
+            expand_moves_gather_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, st>>>(a);
+        }
+        CU(cudaGetLastError());
+        if (child_layout == G2048_CHILDREN_NONE) return G2048_OK;
         // one wave: as many blocks as are resident at once (a partial second wave costs ~14 %)
         static int occ = 0;
         if (occ == 0) {
@@ -1196,9 +1198,14 @@ extern "C" int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* re
         else
             expand_children_kernel<G2048_CHILDREN_DENSE><<<grid, kChildWarps * 32, 0, st>>>(a);
         CU(cudaGetLastError());
+        return G2048_OK;
+    };
+    rc = launch();
+    if (scratch) {
+        const cudaError_t fe = cudaFreeAsync(scratch, st);
+        if (rc == G2048_OK && fe != cudaSuccess) return cuda_fail(fe, "cudaFreeAsync(scratch)");
     }
-    if (scratch) CU(cudaFreeAsync(scratch, st));
-    return G2048_OK;
+    return rc;
 }
 
 __global__ void __launch_bounds__(256) after_state_kernel(const u64* __restrict__ boards,
@@ -1504,19 +1511,24 @@ extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint3
                   trace_stride, s->table, s->table_hashed, 1u, philox_key_schedule(seed)};
     unsigned long long* next = nullptr;
     CU(cudaMallocAsync(&next, sizeof(unsigned long long), st));
-    CU(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
-    const bool smem = n >= (size_t)s->sms * 512 && s->smem_optin >= kSmemTableBytes + 64;
-    if (smem) {
-        const int bytes = (int)kSmemTableBytes + 64;
-        CU(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-        rollout_kernel<true><<<s->sms, 1024, bytes, st>>>(a, next);
-    } else {
-        int grid = grid_for(n, 512, s->sms, 1);
-        rollout_kernel<false><<<grid, 512, 0, st>>>(a, next);
-    }
-    CU(cudaGetLastError());
-    CU(cudaFreeAsync(next, st));
-    return G2048_OK;
+    auto launch = [&]() -> int {  // in a helper so that the counter is released on every path
+        CU(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
+        const bool smem = n >= (size_t)s->sms * 512 && s->smem_optin >= kSmemTableBytes + 64;
+        if (smem) {
+            const int bytes = (int)kSmemTableBytes + 64;
+            CU(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+            rollout_kernel<true><<<s->sms, 1024, bytes, st>>>(a, next);
+        } else {
+            int grid = grid_for(n, 512, s->sms, 1);
+            rollout_kernel<false><<<grid, 512, 0, st>>>(a, next);
+        }
+        CU(cudaGetLastError());
+        return G2048_OK;
+    };
+    rc = launch();
+    const cudaError_t fe = cudaFreeAsync(next, st);
+    if (rc == G2048_OK && fe != cudaSuccess) return cuda_fail(fe, "cudaFreeAsync(next)");
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
