@@ -312,3 +312,19 @@ def jx_encode_observation(board: np.ndarray) -> np.ndarray:
     b = board.astype(np.float32)
     logs = np.where(board > 0, np.log2(np.where(board > 0, b, 1.0)), 0.0).astype(np.float32)
     return (logs / np.float32(16.0)).reshape(-1)
+
+
+def jx_action_distribution(temperature: float, policy: np.ndarray, legal: np.ndarray) -> np.ndarray:
+    """core.py:401-421 — the distribution sample_action draws from (float32 arithmetic)."""
+    pol = np.where(legal, policy.astype(np.float32), np.float32(0.0))
+    total = pol.sum(dtype=np.float32)
+    n_legal = np.float32(legal.sum())
+    uniform = legal.astype(np.float32) / max(n_legal, np.float32(1.0))
+    pol = uniform if total < 1e-8 else pol / total
+    if temperature < 0.01:
+        out = np.zeros(4, dtype=np.float32)
+        out[int(np.argmax(pol))] = 1.0
+        return out
+    z = np.log(pol + np.float32(1e-8)) / np.float32(temperature)
+    z = np.exp(z - z.max())
+    return (z / z.sum()).astype(np.float32)

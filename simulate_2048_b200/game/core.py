@@ -184,6 +184,35 @@ def encode_observation(board: Array) -> Array:
     return obs.reshape(*_lead(board), 16)
 
 
+# -- core.py:381 sample_action ------------------------------------------------------------------
+
+def action_distribution(temperature: float, policy: Array, legal_mask: Array) -> Array:
+    """The distribution core.py:401-421 samples from: illegal actions masked, renormalised (uniform
+    over the legal actions when the mass is below 1e-8), then softmax(log(p + 1e-8) / temperature),
+    or a one-hot of the argmax when temperature < 0.01.  float32[..., 4]."""
+    legal = legal_mask.to(torch.bool)
+    pol = policy.to(torch.float32)
+    masked = torch.where(legal, pol, torch.zeros_like(pol))
+    total = masked.sum(dim=-1, keepdim=True)
+    legal_f = legal.to(torch.float32)
+    uniform = legal_f / legal_f.sum(dim=-1, keepdim=True).clamp(min=1.0)
+    masked = torch.where(total < 1e-8, uniform, masked / total)
+    if temperature < 0.01:
+        return torch.nn.functional.one_hot(masked.argmax(dim=-1), NUM_ACTIONS).to(torch.float32)
+    return torch.softmax(torch.log(masked + 1e-8) / temperature, dim=-1)
+
+
+def sample_action(key: Key, temperature: float, policy: Array, legal_mask: Array) -> Array:
+    """core.py:381 — an action drawn from ``action_distribution`` (int64[...]; a scalar tensor for a
+    single policy).  The JAX key becomes the seed of a device generator: the threefry draw itself
+    cannot be reproduced, the distribution is the reference's."""
+    dist = action_distribution(temperature, policy, legal_mask)
+    gen = torch.Generator(device=dist.device)
+    gen.manual_seed(key_to_seed(key) & (2 ** 63 - 1))
+    picks = torch.multinomial(dist.reshape(-1, NUM_ACTIONS), 1, generator=gen)
+    return picks.reshape(dist.shape[:-1])
+
+
 def max_tile(board: Array) -> Array:
     """core.py:427 — the largest tile VALUE (int32), 0 for an empty board."""
     packed = pack_boards(board).reshape(-1)
@@ -202,6 +231,6 @@ def count_empty(board: Array) -> Array:
 __all__ = [
     'BOARD_SIZE', 'NUM_ACTIONS', 'merge_row', 'slide_and_merge', 'latent_state', 'fill_cells',
     'next_state', 'legal_actions_mask', 'is_done', 'create_initial_board', 'encode_observation',
-    'max_tile', 'count_empty', 'pack_boards', 'unpack_boards', 'is_packed', 'key_to_seed',
+    'max_tile', 'count_empty', 'sample_action', 'action_distribution', 'pack_boards', 'unpack_boards', 'is_packed', 'key_to_seed',
     'FLAG_LEGAL_MASK',
 ]

@@ -172,3 +172,41 @@ class TestBatchedEnvAgainstRestatement:
             np.testing.assert_array_equal(info['max_tile'].cpu().numpy(), [s[0].max() for s in ref])
             del obs
         assert states.done.any()
+
+
+class TestSampleAction:
+    """core.py:381 sample_action: the distribution is checked against the NumPy restatement
+    (float32, tolerance 1e-6), the draw against that distribution."""
+
+    CASES = [
+        ([0.1, 0.2, 0.3, 0.4], [True, True, True, True]),
+        ([0.1, 0.2, 0.3, 0.4], [True, False, True, False]),
+        ([0.0, 0.0, 0.0, 1.0], [True, True, True, False]),   # all legal mass zero -> uniform over legal
+        ([0.25, 0.25, 0.25, 0.25], [False, False, False, True]),
+        ([0.7, 0.1, 0.1, 0.1], [False, False, False, False]),  # no legal action (finished game)
+    ]
+
+    @pytest.mark.parametrize('temperature', [1.0, 0.5, 0.25, 0.0])
+    def test_distribution_matches_restatement(self, T, G, temperature):
+        from oracle import np_engine as npe
+        pol = T.tensor([c[0] for c in self.CASES], dtype=T.float32, device='cuda')
+        legal = T.tensor([c[1] for c in self.CASES], device='cuda')
+        got = G.core.action_distribution(temperature, pol, legal).cpu().numpy()
+        for i, (p, m) in enumerate(self.CASES):
+            want = npe.jx_action_distribution(temperature, np.array(p, np.float32), np.array(m))
+            np.testing.assert_allclose(got[i], want, rtol=1e-5, atol=1e-6)
+
+    def test_greedy_and_legal_only(self, T, G):
+        pol = T.tensor([0.1, 0.6, 0.2, 0.1], device='cuda')
+        legal = T.tensor([True, False, True, True], device='cuda')
+        assert int(G.core.sample_action(0, 0.0, pol, legal)) == 2  # argmax among the legal actions
+        draws = T.stack([G.core.sample_action(k, 1.0, pol, legal) for k in range(200)]).cpu().numpy()
+        assert set(draws.tolist()) <= {0, 2, 3} and len(set(draws.tolist())) == 3
+
+    def test_batched_draw_follows_distribution(self, T, G):
+        n = 40000
+        pol = T.tensor([0.1, 0.2, 0.3, 0.4], device='cuda').repeat(n, 1)
+        legal = T.ones((n, 4), dtype=T.bool, device='cuda')
+        picks = G.core.sample_action(7, 1.0, pol, legal).cpu().numpy()
+        freq = np.bincount(picks, minlength=4) / n
+        np.testing.assert_allclose(freq, [0.1, 0.2, 0.3, 0.4], atol=0.01)
