@@ -170,6 +170,31 @@ def numpy_port_rate(packed: np.ndarray, actions: np.ndarray, per_worker: int, wo
     return total / dt, dt
 
 
+def _np_expand_worker(tiles):
+    """Config 3 on the NumPy port: mask, four afterstates + rewards, every chance child."""
+    from oracle import np_engine
+    children = 0
+    for b in tiles:
+        mask = np_engine.legal_actions_mask(b)
+        for a in range(4):
+            after, _ = np_engine.latent_state(b, a)
+            if mask[a]:
+                children += len(np_engine.after_state(np.array(after)))
+    return children
+
+
+def numpy_expand_rate(packed: np.ndarray, per_worker: int, workers: int, pool):
+    from oracle import c_oracle
+    total = per_worker * workers
+    tiles = c_oracle.unpack(packed[:total]).astype(np.int64).reshape(total, 4, 4)
+    t0 = time.perf_counter()
+    kids = sum(pool.map(_np_expand_worker, [tiles[w * per_worker:(w + 1) * per_worker] for w in range(workers)]))
+    dt = time.perf_counter() - t0
+    return {'boards_per_sec': total / dt, 'children_per_sec': kids / dt, 'cores': workers,
+            'sample': f'{total} boards of the config-2 set: legal_actions_mask + latent_state x4 + after_state '
+                      f'of every legal afterstate through oracle/np_engine.py, {dt:.1f} s'}
+
+
 def _games_worker(args):
     first, count = args
     from oracle import np_engine
@@ -198,9 +223,11 @@ def cpu_baseline_block(packed, actions, cores):
     import multiprocessing as mp
     from oracle import c_oracle
     c_oracle.build()
-    per_worker = 1 << 13
     with mp.get_context('fork').Pool(cores) as pool:
+        probe, _ = numpy_port_rate(packed, actions, 1 << 11, cores, pool)   # untimed sizing probe
+        per_worker = int(max(1 << 12, min(1 << 18, probe / cores * 30.0)))   # ~10 s of work per core (the probe includes pool start-up)
         rate, dt = numpy_port_rate(packed, actions, per_worker, cores, pool)
+        cfg3 = numpy_expand_rate(packed, 2048, cores, pool)
     rate1, _ = numpy_port_rate(packed, actions, 1 << 12, 1)
     n_c = min(packed.size, 1 << 22)
     t0 = time.perf_counter()
@@ -216,6 +243,9 @@ def cpu_baseline_block(packed, actions, cores):
         'sample': f'NumPy port of the reference engine (oracle/np_engine.py next_state, one Python call '
                   f'per env), {per_worker} boards x {cores} processes of the config-2 set, {dt:.1f} s',
         'single_core_value': rate1,
+        'config3_numpy_expand': cfg3,
+        'jax_on_cpu': 'unavailable in this image (jax / jaxlib are not installed and there is no network); '
+                      'the JAX engine is covered by a NumPy restatement of its semantics, not timed as "JAX"',
         'c_oracle': {'value': c_rate, 'single_core_value': c_rate1, 'cores': cores, 'unit': UNIT,
                      'sample': f'oracle/g2048_oracle.c orc_step, {n_c} boards, pthreads'},
     }
@@ -381,6 +411,7 @@ def run_ours(args):
         },
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                     'frac_of_spec_8000gbs': achieved / 8000.0,
                      'kernel': 'step_lut_kernel<false, 512>', 'mean_launch_ms': mean_launch * 1e3,
                      'best_launch_ms': best_launch * 1e3,
                      'algorithmic_bytes_per_launch': BYTES_INJECTED * B},
