@@ -180,6 +180,18 @@ int g2048_observe(const uint64_t* boards, float* obs, uint8_t* max_exp, size_t n
  * 16 <= width <= 64.  out is u8[n*16*width]. */
 int g2048_observe_onehot(const uint64_t* boards, uint8_t* out, int width, size_t n, void* stream);
 
+/* Expectation over the chance children of every (board, action) — the value backup of an
+ * expectimax / MCTS leaf expansion.  Inputs are the compact-layout outputs of
+ * g2048_expand plus one value per child (e.g. a network's estimate, in child order):
+ *   q[i*4 + a] = rewards[i*4 + a] + discount * sum_k (0.9 * v[2k] + 0.1 * v[2k+1]) / num_empty
+ * with the probabilities of gameboard.py:13,132-171 (after_state: P(2) = 0.9, P(4) = 0.1, uniform
+ * over the empty cells); an illegal action (child_count 0) gets `illegal_value`.  A count of 1 (an
+ * afterstate without an empty cell, probability 1: gameboard.py:158-159) is honoured.
+ * rewards may be NULL (treated as 0).  f32 arithmetic. */
+int g2048_expect(const float* child_values, const uint8_t* child_count, const int64_t* child_offsets,
+                 const int32_t* rewards, float discount, float illegal_value, float* q_out, size_t n,
+                 void* stream);
+
 /* n-step TD(lambda) returns over device trajectory buffers (reinforce/training/self_play.py:524
  * compute_n_step_returns, same weighting and normalisation), time-major layout [T][N]:
  *   G_n(t) = sum_{i<n} discount^i r[t+i] + discount^n v[t+n]   (the bootstrap term only if t+n < len)

@@ -157,6 +157,20 @@ def normalize_reward(reward: float, max_tile: int = 2 ** 16) -> float:
     return 0.0 if reward == 0 else float(np.log2(reward) / np.log2(max_tile))
 
 
+def expectimax_q(board: np.ndarray, value_fn, discount: float = 1.0) -> np.ndarray:
+    """Depth-1 expectimax action values with the reference's own building blocks
+    (gameboard.py:105 latent_state, :132 after_state incl. its probabilities, gamemove.py:45):
+    q[a] = reward + discount * sum_i p_i * value_fn(child_i); -inf for an illegal action."""
+    q = np.full(4, -np.inf)
+    legal = legal_actions_mask(board)
+    for a in range(4):
+        if not legal[a]:
+            continue
+        after, reward = latent_state(board, a)
+        q[a] = reward + discount * sum(p * value_fn(child) for child, p in after_state(np.array(after)))
+    return q
+
+
 def n_step_returns(rewards: np.ndarray, values: np.ndarray, discount: float, n_steps: int,
                    td_lambda: float = 0.5) -> np.ndarray:
     """reinforce/training/self_play.py:524-579 — TD(lambda)-weighted n-step returns of ONE

@@ -1244,6 +1244,54 @@ extern "C" int g2048_after_state(const uint64_t* boards, uint64_t* children, uin
 }
 
 // ---------------------------------------------------------------------------------------------
+// expectation over chance children (row f2): 8 lanes per (board, action), lane k of a group sums
+// the cells k, k+8 of its segment, a 3-step shuffle reduction finishes the group.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) expect_kernel(const float* __restrict__ v, const uint8_t* __restrict__ child_count,
+                                                     const int64_t* __restrict__ child_offsets,
+                                                     const int32_t* __restrict__ rewards, float discount,
+                                                     float illegal_value, float* __restrict__ q, size_t n) {
+    const u32 lane = threadIdx.x & 31u, act = lane >> 3, r0 = lane & 7u;
+    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t i = warp; i < n; i += n_warps) {
+        const u32 cc4 = *reinterpret_cast<const u32*>(child_count + i * 4);
+        const u32 cc = (cc4 >> (8u * act)) & 0xFFu;
+        u32 before = 0;
+        for (u32 k = 0; k < act; ++k) before += (cc4 >> (8u * k)) & 0xFFu;
+        const float* seg = v + child_offsets[i] + before;
+        float acc = 0.0f;
+        if (cc == 1u) {
+            if (r0 == 0u) acc = seg[0];  // the afterstate itself, probability 1
+        } else {
+            for (u32 cell = r0; 2u * cell < cc; cell += 8u) acc += 0.9f * seg[2u * cell] + 0.1f * seg[2u * cell + 1u];
+        }
+        acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 4);
+        acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 2);
+        acc += __shfl_xor_sync(0xFFFFFFFFu, acc, 1);
+        if (r0 == 0u) {
+            const float ne = cc == 1u ? 1.0f : (float)(cc >> 1);
+            const float r = rewards ? (float)rewards[i * 4 + act] : 0.0f;
+            q[i * 4 + act] = cc ? r + discount * (acc / ne) : illegal_value;
+        }
+    }
+}
+
+extern "C" int g2048_expect(const float* child_values, const uint8_t* child_count, const int64_t* child_offsets,
+                            const int32_t* rewards, float discount, float illegal_value, float* q_out, size_t n,
+                            void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!child_values || !child_count || !child_offsets || !q_out || !aligned(child_count, 4)) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    expect_kernel<<<grid_for(n * 32, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        child_values, child_count, child_offsets, rewards, discount, illegal_value, q_out, n);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // n-step TD(lambda) returns (self_play.py:524): one thread per (t, env), time-major buffers so
 // that a warp reads consecutive envs of one time step; the n loop carries the discounted reward
 // sum, the discount power and the lambda power.

@@ -19,7 +19,7 @@ from ._cabi import check, lib
 
 __all__ = [
     'StepOut', 'ExpandOut', 'RolloutOut', 'step', 'env_step', 'legal_flags', 'expand', 'reset',
-    'observe', 'observe_onehot', 'nstep_returns', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'step_host', 'row_table', 'set_impl', 'set_tuning', 'init',
+    'observe', 'observe_onehot', 'nstep_returns', 'expect', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'step_host', 'row_table', 'set_impl', 'set_tuning', 'init',
     'pinned_empty',
 ]
 
@@ -261,6 +261,23 @@ def observe_onehot(boards: torch.Tensor, width: int = 31) -> torch.Tensor:
     with torch.cuda.device(boards.device):
         check(lib().g2048_observe_onehot(_ptr(boards), _ptr(out), int(width), n, _stream()))
     return out
+
+
+def expect(child_values: torch.Tensor, ex: 'ExpandOut', discount: float = 1.0,
+           illegal_value: float = float('-inf'), use_rewards: bool = True) -> torch.Tensor:
+    """float32[N,4] action values of a depth-1 expectimax backup (g2048_expect): reward + discount *
+    E[value of the chance child], with the after_state probabilities of gameboard.py:132-171.
+    ``ex`` is a compact ``expand`` result, ``child_values`` float32[total] one value per child."""
+    if ex.children is None or ex.child_offsets is None:
+        raise ValueError('expect needs the compact children layout of expand()')
+    n = ex.after.shape[0]
+    _opt(child_values, torch.float32, 'child_values', ex.children.numel())
+    q = torch.empty((n, 4), dtype=torch.float32, device=ex.after.device)
+    with torch.cuda.device(ex.after.device):
+        check(lib().g2048_expect(_ptr(child_values), _ptr(ex.child_count), _ptr(ex.child_offsets),
+                                 _ptr(ex.rewards) if use_rewards else None, float(discount),
+                                 float(illegal_value), _ptr(q), n, _stream()))
+    return q
 
 
 def nstep_returns(rewards: torch.Tensor, values: torch.Tensor, discount: float, n_steps: int,

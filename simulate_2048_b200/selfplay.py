@@ -173,3 +173,15 @@ def uniform_legal_policy(seed: int = 0):
         w[:, 0] += (w.sum(dim=1) == 0).to(torch.float32)  # finished games: any action (a no-op)
         return torch.multinomial(w, 1, generator=gen[0]).reshape(-1).to(torch.uint8)
     return policy
+
+
+def expectimax_depth1(boards: torch.Tensor, value_fn, discount: float = 1.0):
+    """Batched depth-1 expectimax on real boards: one ``expand`` (mask, four
+    afterstates, every chance child), ``value_fn(children int64[total]) -> float32[total]`` on all
+    children at once (e.g. a value network), then the probability-weighted backup of
+    ``g2048_expect``.  Returns (q float32[N,4] with -inf for illegal actions, best action int64[N],
+    the ``ExpandOut``)."""
+    ex = ops.expand(boards, children='compact')
+    values = value_fn(ex.children).to(torch.float32).contiguous()
+    q = ops.expect(values, ex, discount=discount)
+    return q, q.argmax(dim=1), ex

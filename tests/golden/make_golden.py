@@ -19,6 +19,7 @@ Fixtures
   fill_cells.npz  fill_cells draws on a fixed board, seeds 0..63, and reset(seed) boards
   encodings.npz   utils/binary.py encode_flatten(., 31) of 64 boards; utils/normalize.py values
   nstep.npz       reinforce/training/self_play.py compute_n_step_returns on 7 random trajectories
+  expectimax.npz  depth-1 expectimax values of 256 boards: latent_state + after_state probabilities
 """
 
 from __future__ import annotations
@@ -218,6 +219,29 @@ def make_encodings() -> None:
     print('encodings', onehot.shape, norm[:4])
 
 
+def leaf_value(tiles) -> float:
+    """Deterministic stand-in for a value network: empty cells + log2(max tile) / 4 (exact in f32)."""
+    t = np.asarray(tiles)
+    mx = int(t.max())
+    return float((t == 0).sum()) + 0.25 * (mx.bit_length() - 1 if mx else 0)
+
+
+def make_expectimax(n: int = 256) -> None:
+    """Depth-1 expectimax values from the real reference: latent_state + after_state (with its
+    probabilities) + legal_actions_mask, leaf values from `leaf_value`."""
+    boards = synthetic_boards(n, seed=77)
+    q = np.full((n, 4), -np.inf)
+    for i, b in enumerate(boards):
+        legal = legal_actions_mask(b)
+        for a in range(4):
+            if legal[a]:
+                s_after, r = latent_state(b, a)
+                q[i, a] = r + 0.99 * sum(p * leaf_value(child) for child, p in after_state(np.array(s_after)))
+    np.savez_compressed(os.path.join(HERE, 'expectimax.npz'), tiles=boards.astype(np.int32),
+                        packed=np.array([pack(b) for b in boards], dtype=np.uint64), q=q, discount=np.array(0.99))
+    print('expectimax', n, q[:2])
+
+
 def make_nstep() -> None:
     """compute_n_step_returns lives in a module that imports jax (absent here): the function is
     plain NumPy, so its definition alone is compiled from the reference source and executed."""
@@ -244,6 +268,7 @@ def make_nstep() -> None:
 
 
 if __name__ == '__main__':
+    make_expectimax()
     make_nstep()
     make_encodings()
     make_rows()

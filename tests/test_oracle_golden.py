@@ -378,3 +378,19 @@ def test_oracle_nstep_returns_match_reference(golden):
     for i, (disc, n_steps, lam) in enumerate(g['params']):
         got = npe.n_step_returns(g[f'r{i}'].astype(np.float64), g[f'v{i}'].astype(np.float64), disc, int(n_steps), lam)
         np.testing.assert_allclose(got, g[f'out{i}'], rtol=1e-13, atol=0)
+
+
+# ---------------------------------------------------------------- expectimax backup (row f2)
+
+def test_oracle_expectimax_matches_reference(golden):
+    """Depth-1 expectimax values computed with the real reference's latent_state / after_state."""
+    g = golden('expectimax')
+
+    def leaf(tiles):
+        t = np.asarray(tiles)
+        mx = int(t.max())
+        return float((t == 0).sum()) + 0.25 * (mx.bit_length() - 1 if mx else 0)
+    for tiles, want in zip(g['tiles'][:96], g['q'][:96]):
+        got = npe.expectimax_q(tiles.astype(np.int64), leaf, float(g['discount']))
+        assert np.array_equal(np.isinf(got), np.isinf(want))
+        np.testing.assert_allclose(got[np.isfinite(want)], want[np.isfinite(want)], rtol=1e-12)
