@@ -2,17 +2,19 @@
 //
 // Hot path (BASELINE.json north_star): one batched 2048 transition per env
 //   board(u64) , action(u8) [, spawn(u8)]  ->  board(u64), reward(i32), flags(u8)
-// HBM-bound: 22 B/env (Philox) or 23 B/env (injected spawns).  Design:
-//   * persistent grid, one 1024-thread CTA per SM, 4 consecutive envs per thread so every
-//     stream is one wide access per thread: 256-bit board load/store (LDG.E.256 / STG.E.256),
-//     128-bit reward store, 32-bit action / spawn / flags;
-//   * the 57344-entry row table (224 KiB) is staged into shared memory once per CTA by a TMA
-//     bulk copy (cp.async.bulk, UBLKCP) that completes on an mbarrier while the first boards
-//     are already in flight; a move is then 4 LDS + 2 PRMT;
-//   * up / right / down are reduced to "left" by a nibble transpose (8 LOP/SHF + 2 PRMT) and a
-//     row mirror, reward rides in the table entry, the legal mask / done of the NEW board and
-//     the tile spawn are nibble-parallel register arithmetic in the same pass;
+// HBM-bound by design: 22 B/env (Philox) or 23 B/env (injected spawns).  Design:
+//   * persistent grid, one 512-thread CTA per SM over a contiguous range of tiles, 4 consecutive
+//     envs per thread so every stream is one wide access per thread: 256-bit board load/store
+//     (LDG.E.256 / STG.E.256), 128-bit reward store, 32-bit action / spawn / flags;
+//   * the 57344-entry row table (224 KiB, hashed against bank conflicts) is staged into shared
+//     memory once per CTA by TMA bulk copies (cp.async.bulk, UBLKCP) that complete on an mbarrier
+//     while the first boards are already in flight; a move is then 4 LDS + 2 PRMT;
+//   * up / right / down are reduced to "left" by ONE per-action nibble delta swap and one byte
+//     permutation each way (g2048_fast.cuh), reward rides in the table entry, the legal mask /
+//     done of the NEW board and the tile spawn are nibble-parallel register arithmetic in the
+//     same pass, without a data-dependent branch;
 //   * inputs of tile t+1 are loaded before tile t is computed (register double buffering).
+// The other entry points (expand, rollout, env_step, observe, n-step returns, ...) follow below.
 // No Triton, no CPU fallback: every entry point either launches these kernels or fails.
 #include <cstdio>
 #include <cstring>

@@ -1,5 +1,5 @@
 #!/bin/bash
-# tools/profile_other.sh <tag> — ncu --set full of rollout_kernel and expand_kernel (run under gpurun)
+# tools/profile_other.sh <tag> — ncu --set full of the rollout and expand kernels (run under gpurun)
 set -u
 TAG=${1:-r01}
 OUT=gpurun_out
