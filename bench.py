@@ -412,7 +412,9 @@ def run_ours(args):
         'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                      'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                      'frac_of_spec_8000gbs': achieved / 8000.0,
-                     'kernel': 'step_lut_kernel<false, 512>', 'mean_launch_ms': mean_launch * 1e3,
+                     'kernel': 'step_lut_kernel<false, %s, %s>' % (os.environ.get('G2048_STEP_THREADS', '640'),
+                                                                    int(os.environ.get('G2048_STEP_ENVS', '4')) // 4),
+                     'mean_launch_ms': mean_launch * 1e3,
                      'best_launch_ms': best_launch * 1e3,
                      'algorithmic_bytes_per_launch': BYTES_INJECTED * B},
         'clocks': clocks.summary(),

@@ -98,8 +98,9 @@ const char* g2048_last_cuda_error(void); /* thread-local text of the last CUDA f
 int g2048_init(int device);
 /* Select the row-move implementation used by g2048_step/g2048_env_step (process-wide). */
 int g2048_set_impl(int impl);
-/* Tuning knobs of the smem-table step kernel: threads per CTA (512, 768 or 1024; one CTA per
- * SM) and consecutive envs per thread (4 or 8). */
+/* Tuning knobs of the smem-table step kernel: threads per CTA (0 = automatic — 640 with injected
+ * spawns, 512 with Philox — or 512, 640, 768, 1024; one CTA per SM) and consecutive envs per
+ * thread (4, or 8 with 512 / 768 / 1024 threads). */
 int g2048_set_tuning(int step_threads, int envs_per_thread);
 
 /*

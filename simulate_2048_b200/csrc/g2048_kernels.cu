@@ -80,7 +80,7 @@ struct DeviceState {
 };
 static DeviceState g_dev[64];
 static int g_impl = G2048_IMPL_AUTO;
-static int g_step_threads = 512;
+static int g_step_threads = 0;  // 0 = automatic: 640 with injected spawns (5 warps per scheduler at 96 registers: +1 %), 512 with Philox
 static int g_step_groups = 1;   // groups of 4 envs per thread (1 or 2)  // tuning knob (g2048_set_tuning)
 
 static int current_state(DeviceState** out) {
@@ -123,8 +123,10 @@ extern "C" int g2048_init(int device) {
 }
 
 extern "C" int g2048_set_tuning(int step_threads, int envs_per_thread) {
-    if (step_threads != 512 && step_threads != 768 && step_threads != 1024) return G2048_EINVAL;
+    if (step_threads != 0 && step_threads != 512 && step_threads != 640 && step_threads != 768 && step_threads != 1024)
+        return G2048_EINVAL;
     if (envs_per_thread != 4 && envs_per_thread != 8) return G2048_EINVAL;
+    if (step_threads == 640 && envs_per_thread == 8) return G2048_EINVAL;  // not instantiated
     g_step_threads = step_threads;
     g_step_groups = envs_per_thread / 4;
     return G2048_OK;
@@ -571,7 +573,7 @@ extern "C" int g2048_step(const uint64_t* boards_in, const uint8_t* actions, con
 
     if (use_lut) {
         const int smem = (int)kStepSmemBytes;
-        const int threads = g_step_threads, groups = g_step_groups;
+        const int threads = g_step_threads ? g_step_threads : (spawns ? 640 : 512), groups = g_step_groups;
         const size_t tiles = n / ((size_t)threads * 4 * groups);
         const int grid = (int)(tiles < (size_t)s->sms ? (tiles ? tiles : 1) : (size_t)s->sms);
 #define G2048_LAUNCH_STEP(PH, TH, GR)                                                                     \
@@ -588,6 +590,7 @@ extern "C" int g2048_step(const uint64_t* boards_in, const uint8_t* actions, con
             else G2048_LAUNCH_STEP(PH, 1024, 2);                         \
         } else {                                                         \
             if (threads == 512) G2048_LAUNCH_STEP(PH, 512, 1);           \
+            else if (threads == 640) G2048_LAUNCH_STEP(PH, 640, 1);      \
             else if (threads == 768) G2048_LAUNCH_STEP(PH, 768, 1);      \
             else G2048_LAUNCH_STEP(PH, 1024, 1);                         \
         }                                                                \

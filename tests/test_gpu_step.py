@@ -131,6 +131,28 @@ def test_step_philox_vs_oracle(T, ops, oracle, n, impl):
     np.testing.assert_array_equal(fl, o_fl)
 
 
+@pytest.mark.parametrize('threads,envs', [(512, 4), (640, 4), (768, 4), (1024, 4), (512, 8), (1024, 8)])
+def test_step_launch_geometries_vs_oracle(T, ops, oracle, threads, envs):
+    """Every instantiated CTA size / envs-per-thread of the smem-table kernel, both spawn modes,
+    at a size that leaves a ragged tail for each tile size."""
+    n = (1 << 19) + 4099
+    boards = synthetic_packed(n, seed=threads + envs)
+    actions = np.random.default_rng(threads).integers(0, 4, n).astype(np.uint8)
+    spawns = valid_spawn_bytes(afterstates(oracle, boards, actions), seed=envs)
+    ops.set_tuning(threads, envs)
+    try:
+        got_inj = run_step(T, ops, boards, actions, spawns)
+        got_phx = run_step(T, ops, boards, actions, None, seed=99, step_base=3)
+    finally:
+        ops.set_tuning(0, 4)
+    for got, want in ((got_inj, oracle.step(boards, actions, spawns)),
+                      (got_phx, oracle.step(boards, actions, None, seed=99, step_base=3))):
+        for g, w in zip(got, want):
+            np.testing.assert_array_equal(g, w)
+    with pytest.raises(Exception):
+        ops.set_tuning(640, 8)
+
+
 def test_step_optional_inputs_vs_oracle(T, ops, oracle):
     n = 10007
     boards = synthetic_packed(n, seed=8)
