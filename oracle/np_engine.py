@@ -157,17 +157,26 @@ def normalize_reward(reward: float, max_tile: int = 2 ** 16) -> float:
     return 0.0 if reward == 0 else float(np.log2(reward) / np.log2(max_tile))
 
 
-def expectimax_q(board: np.ndarray, value_fn, discount: float = 1.0) -> np.ndarray:
-    """Depth-1 expectimax action values with the reference's own building blocks
+def expectimax_q(board: np.ndarray, value_fn, discount: float = 1.0, depth: int = 1,
+                 terminal_value: float = 0.0) -> np.ndarray:
+    """Depth-`depth` expectimax action values with the reference's own building blocks
     (gameboard.py:105 latent_state, :132 after_state incl. its probabilities, gamemove.py:45):
-    q[a] = reward + discount * sum_i p_i * value_fn(child_i); -inf for an illegal action."""
+    q[a] = reward + discount * sum_i p_i * V(child_i), V = value_fn at the leaves and the max over
+    legal actions (terminal_value when there is none) above; -inf for an illegal action."""
+    def child_value(child):
+        if depth == 1:
+            return value_fn(child)
+        q_c = expectimax_q(np.asarray(child), value_fn, discount, depth - 1, terminal_value)
+        best = q_c.max()
+        return terminal_value if np.isinf(best) else best
+
     q = np.full(4, -np.inf)
     legal = legal_actions_mask(board)
     for a in range(4):
         if not legal[a]:
             continue
         after, reward = latent_state(board, a)
-        q[a] = reward + discount * sum(p * value_fn(child) for child, p in after_state(np.array(after)))
+        q[a] = reward + discount * sum(p * child_value(child) for child, p in after_state(np.array(after)))
     return q
 
 

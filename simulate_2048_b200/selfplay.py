@@ -175,13 +175,28 @@ def uniform_legal_policy(seed: int = 0):
     return policy
 
 
-def expectimax_depth1(boards: torch.Tensor, value_fn, discount: float = 1.0):
-    """Batched depth-1 expectimax on real boards: one ``expand`` (mask, four
-    afterstates, every chance child), ``value_fn(children int64[total]) -> float32[total]`` on all
-    children at once (e.g. a value network), then the probability-weighted backup of
-    ``g2048_expect``.  Returns (q float32[N,4] with -inf for illegal actions, best action int64[N],
-    the ``ExpandOut``)."""
+def expectimax(boards: torch.Tensor, value_fn, depth: int = 1, discount: float = 1.0,
+               terminal_value: float = 0.0):
+    """Batched depth-``depth`` expectimax on real boards:
+        Q_d(b, a) = r(b, a) + discount * sum_children p * V_{d-1}(child)     (g2048_expect)
+        V_d(b)    = max over the legal actions of Q_d(b, a), ``terminal_value`` if there is none
+        V_0(b)    = value_fn(b)
+    One ``expand`` per level (mask, four afterstates, every chance child), ``value_fn(int64[M]) ->
+    float32[M]`` once on all leaves (e.g. a value network).  The number of boards grows ~60x per
+    level.  Returns (q float32[N,4] with -inf for illegal actions, best action int64[N], ExpandOut)."""
+    if depth < 1:
+        raise ValueError('depth must be >= 1')
     ex = ops.expand(boards, children='compact')
-    values = value_fn(ex.children).to(torch.float32).contiguous()
+    if depth == 1:
+        values = value_fn(ex.children).to(torch.float32).contiguous()
+    else:
+        q_child, _, _ = expectimax(ex.children, value_fn, depth - 1, discount, terminal_value)
+        best = q_child.max(dim=1).values
+        values = torch.where(torch.isinf(best), torch.full_like(best, terminal_value), best).contiguous()
     q = ops.expect(values, ex, discount=discount)
     return q, q.argmax(dim=1), ex
+
+
+def expectimax_depth1(boards: torch.Tensor, value_fn, discount: float = 1.0):
+    """``expectimax`` with one level: reward + discount * E[value_fn(chance child)]."""
+    return expectimax(boards, value_fn, 1, discount)

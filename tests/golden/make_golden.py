@@ -237,8 +237,32 @@ def make_expectimax(n: int = 256) -> None:
             if legal[a]:
                 s_after, r = latent_state(b, a)
                 q[i, a] = r + 0.99 * sum(p * leaf_value(child) for child, p in after_state(np.array(s_after)))
+    # depth 2 on a few crowded boards (few empty cells keep the tree small): the children's value is
+    # the max over their legal actions of the depth-1 value, 0 for a dead child
+    def q_depth1(b):
+        out = np.full(4, -np.inf)
+        legal = legal_actions_mask(b)
+        for a in range(4):
+            if legal[a]:
+                s_after, r = latent_state(b, a)
+                out[a] = r + 0.99 * sum(p * leaf_value(child) for child, p in after_state(np.array(s_after)))
+        return out
+    deep = [b for b in synthetic_boards(400, seed=78) if (b == 0).sum() <= 5][:12]
+    q2 = np.full((len(deep), 4), -np.inf)
+    for i, b in enumerate(deep):
+        legal = legal_actions_mask(b)
+        for a in range(4):
+            if legal[a]:
+                s_after, r = latent_state(b, a)
+                total = 0.0
+                for child, p in after_state(np.array(s_after)):
+                    best = q_depth1(np.asarray(child)).max()
+                    total += p * (0.0 if np.isinf(best) else best)
+                q2[i, a] = r + 0.99 * total
     np.savez_compressed(os.path.join(HERE, 'expectimax.npz'), tiles=boards.astype(np.int32),
-                        packed=np.array([pack(b) for b in boards], dtype=np.uint64), q=q, discount=np.array(0.99))
+                        packed=np.array([pack(b) for b in boards], dtype=np.uint64), q=q, discount=np.array(0.99),
+                        deep_tiles=np.array(deep, dtype=np.int32),
+                        deep_packed=np.array([pack(b) for b in deep], dtype=np.uint64), deep_q=q2)
     print('expectimax', n, q[:2])
 
 

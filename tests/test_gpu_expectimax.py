@@ -68,3 +68,17 @@ def test_expect_argument_checks():
     compact = ops.expand(boards, children='compact')
     with pytest.raises(ValueError):
         ops.expect(torch.zeros(3, device='cuda'), compact)
+
+
+def test_expectimax_depth2_reproduces_reference(golden):
+    """Two levels: V(child) = max over its legal actions of the depth-1 value (0 for a dead child),
+    computed by the fixture with the real reference's functions."""
+    import torch
+    from simulate_2048_b200.selfplay import expectimax
+    g = golden('expectimax')
+    boards = torch.from_numpy(g['deep_packed'].view(np.int64)).cuda()
+    q, _, _ = expectimax(boards, leaf_value_gpu, depth=2, discount=float(g['discount']))
+    got, want = q.cpu().numpy().astype(np.float64), g['deep_q']
+    assert np.array_equal(np.isinf(got), np.isinf(want))
+    fin = np.isfinite(want)
+    np.testing.assert_allclose(got[fin], want[fin], rtol=5e-6, atol=1e-3)

@@ -394,3 +394,16 @@ def test_oracle_expectimax_matches_reference(golden):
         got = npe.expectimax_q(tiles.astype(np.int64), leaf, float(g['discount']))
         assert np.array_equal(np.isinf(got), np.isinf(want))
         np.testing.assert_allclose(got[np.isfinite(want)], want[np.isfinite(want)], rtol=1e-12)
+
+
+def test_oracle_expectimax_depth2_matches_reference(golden):
+    g = golden('expectimax')
+
+    def leaf(tiles):
+        t = np.asarray(tiles)
+        mx = int(t.max())
+        return float((t == 0).sum()) + 0.25 * (mx.bit_length() - 1 if mx else 0)
+    for tiles, want in zip(g['deep_tiles'][:4], g['deep_q'][:4]):
+        got = npe.expectimax_q(tiles.astype(np.int64), leaf, float(g['discount']), depth=2)
+        assert np.array_equal(np.isinf(got), np.isinf(want))
+        np.testing.assert_allclose(got[np.isfinite(want)], want[np.isfinite(want)], rtol=1e-12)
