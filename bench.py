@@ -572,6 +572,22 @@ def run_ours(args):
         extra['selfplay_4096_fused'] = {'us_per_iteration': dt / 200 * 1e6, 'env_steps_per_sec': 4096 * 200 / dt,
                                         'note': 'BatchedEnv: next observation, legal mask, reward, done from ONE '
                                                 'graph-replayed launch per iteration'}
+        # row (f2): batched expectimax (expand + value function on every leaf + probability-weighted backup)
+        from simulate_2048_b200 import selfplay
+
+        def leaf_value(children):  # stand-in for a value network: empty cells + max exponent / 4
+            o, mx = ops.observe(children)
+            return (o == 0).sum(dim=1).to(torch.float32) + 0.25 * mx.to(torch.float32)
+        xm = {}
+        for depth, n_x in ((1, 65536), (2, 4096)):
+            xb = boards[:n_x].contiguous()
+            _, _, ex_x = selfplay.expectimax(xb, leaf_value, depth=depth)
+            _, t_x, _ = timed(lambda: selfplay.expectimax(xb, leaf_value, depth=depth), 5, 2, collective=False)
+            xm[f'depth{depth}_{n_x}'] = {'ms': t_x * 1e3, 'root_boards_per_sec': n_x / t_x,
+                                        'first_level_children': int(ex_x.children.numel())}
+            del ex_x
+        xm['note'] = 'selfplay.expectimax: one g2048_expand per level, leaf values from a torch function, g2048_expect backup'
+        extra['expectimax'] = xm
         # row (f4): n-step TD(lambda) targets over device trajectory buffers [T=200, N=4096]
         tr = torch.rand((200, 4096), device=dev) * 64
         tv = torch.rand((200, 4096), device=dev) * 500
