@@ -105,21 +105,29 @@ class ClockSampler:
             log('clock sampling unavailable:', e)
             self.nv = None
 
-    def _loop(self):
+    def sample(self):
+        """One reading of SM clock, throttle reasons and power (an NVML query takes milliseconds
+        while the GPU is busy, so it must stay off the launching thread: sampling from inside the
+        timed loop drained the launch queue and cost 40 % of the measured throughput)."""
         nv = self.nv
-        while not self._stop.is_set():
+        if nv is None:
+            return
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                try:
-                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for b, name in REASONS.items():
-                    if bits & b and name != 'gpu_idle':
-                        self.reasons.add(name)
-                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
-                pass
+                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for b, name in REASONS.items():
+                if bits & b and name != 'gpu_idle':
+                    self.reasons.add(name)
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+        except Exception:
+            pass
+
+    def _loop(self):
+        while not self._stop.is_set():
+            self.sample()
             self._stop.wait(self.period)
 
     def __enter__(self):
@@ -379,8 +387,11 @@ def run_ours(args):
     # ---- primary: injected spawns (the mode that is bit-exact against the reference) ----
     step_inj = lambda: ops.step(boards, actions, spawns, env_offset=env_offset, out=out)  # noqa: E731
     step_phx = lambda: ops.step(boards, actions, None, seed=2048, env_offset=env_offset, out=out)  # noqa: E731
-    with ClockSampler(local) as clocks:
-        total, mean_launch, best_launch = timed(step_inj, args.steps, args.warmup)
+    # the sampler runs through both timed regions of the step kernel (injected, then Philox): an NVML
+    # query takes ~10 ms under load, so a short run yields only a few samples per region
+    clocks = ClockSampler(local)
+    clocks.__enter__()
+    total, mean_launch, best_launch = timed(step_inj, args.steps, args.warmup)
     value = world * B * args.steps / total
     peak, peak_src = measured_peak()
     achieved = BYTES_INJECTED * B / mean_launch / 1e9
@@ -393,6 +404,7 @@ def run_ours(args):
             traffic = None
 
     p_total, p_mean, _ = timed(step_phx, max(args.steps // 2, 5), 3)
+    clocks.__exit__(None, None, None)
     philox = {'value': world * B * max(args.steps // 2, 5) / p_total, 'unit': UNIT,
               'achieved_gbs': BYTES_PHILOX * B / p_mean / 1e9,
               'frac': BYTES_PHILOX * B / p_mean / 1e9 / peak}
