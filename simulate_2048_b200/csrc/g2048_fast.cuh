@@ -140,6 +140,17 @@ G2048_HD u32 sub16_if_differ(u32 x, u32 ref, u32 one) {
 #endif
 }
 
+// x - y if c (predicated IADD instead of SEL + IADD)
+G2048_HD u32 sub_if(u32 x, u32 y, bool c) {
+#if defined(__CUDA_ARCH__)
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p sub.u32 %0, %0, %1;\n\t}"
+        : "+r"(x) : "r"(y), "r"((u32)c));
+    return x;
+#else
+    return c ? x - y : x;
+#endif
+}
+
 // a * b + c on the FMA pipe (IMAD)
 G2048_HD u32 mad(u32 a, u32 b, u32 c) {
 #if defined(__CUDA_ARCH__)
@@ -299,13 +310,67 @@ G2048_HD u32 move_fast(u32 lo, u32 hi, const Orient& o, const Lut& lut, u32 one,
 // Inclusive prefix count of EMPTY cells at nibble k of a half = (k + 1) - prefix(tiles), so with
 // t = tile indicators at bit 0:  g = 0x87654321 + (7 - r)*0x11111111 - t*0x11111111  has bit 3
 // set exactly in the nibbles whose empty-count exceeds r (every nibble stays <= 15).
-G2048_HD u32 spawn_marker(u32 nlo, u32 nhi, u32 tiles_lo, u32 rank, u32 one, bool& in_hi) {
+G2048_HD u32 spawn_prefix(u32 nlo, u32 nhi, u32 tiles_lo, u32 rank, u32 one, bool& in_hi) {
     const u32 clo = mad(tiles_lo, 0u - one, 8u);   // 8 - tiles_lo as an IMAD
     in_hi = rank >= clo;
     const u32 nsel = in_hi ? nhi : nlo;
     const u32 r = in_hi ? rank - clo : rank;
-    const u32 g = mad(shr<3>(nsel), 0xEEEEEEEFu, mad(r, 0xEEEEEEEFu, 0xFEDCBA98u)) & 0x88888888u;
-    return g & (0u - g);
+    return mad(shr<3>(nsel), 0xEEEEEEEFu, mad(r, 0xEEEEEEEFu, 0xFEDCBA98u));
+}
+// The empty-count is non-decreasing along the nibbles, so bit 3 of g is 0..0 1..1 from the target
+// upwards: the lowest set indicator is the one whose lower neighbour is clear (one LOP3 with the
+// shift on the FMA pipe, instead of mask, negate, and).
+constexpr u32 kLowestIndicator = kA & ~kB & kC & 0xFF;
+G2048_HD u32 spawn_marker(u32 nlo, u32 nhi, u32 tiles_lo, u32 rank, u32 one, bool& in_hi) {
+    const u32 g = spawn_prefix(nlo, nhi, tiles_lo, rank, one, in_hi);
+    return lop3<kLowestIndicator>(g, g << 4, 0x88888888u);
+}
+
+// The spawn commit of transition_fast, branch-free (a divergent branch here costs BSSY / BRA /
+// BSYNC and a reconvergence per env).  g = spawn_prefix(...); the marker is taken from it only when
+// the move is legal and the spawn valid (rank < ne; a Philox rank always is) and is 0 otherwise,
+// so the predicated adds are no-ops then.  tile = exponent (1 or 2) at bit 0 of the marked nibble
+// (one IMAD.HI: exp_mul = exponent << 29), added to the half `in_hi` selects together with its
+// non-empty indicator.  status = the flag bits besides the mask (0x10 is cancelled by the caller
+// when some action is legal): not moved -> 0x10, moved without a valid spawn -> MOVED | BADSPAWN,
+// moved and spawned -> MOVED.
+template <bool kCheckRank>
+G2048_HD void spawn_commit(u32& al, u32& ah, u32& nlo, u32& nhi, u32& status, u32 g, u32 exp_mul,
+                           bool moved, u32 rank, u32 ne, bool in_hi, u32 one) {
+#if defined(__CUDA_ARCH__)
+#define G2048_COMMIT_BODY                                    \
+        "setp.ne.u32 ph, %9, 0;\n\t"                          \
+        "selp.u32 %4, 0xB0, 0x10, pm;\n\t"                    \
+        "@pd mov.u32 %4, 0x30;\n\t"                           \
+        "shl.b32 g4, %5, 4;\n\t"                              \
+        "lop3.b32 b, %5, g4, 0x88888888, 0x20;\n\t"           \
+        "selp.u32 b, b, 0, pd;\n\t"                           \
+        "mul.hi.u32 t, b, %6;\n\t"                            \
+        "@ph mad.lo.u32 %1, t, %11, %1;\n\t"                  \
+        "@ph mad.lo.u32 %3, b, %11, %3;\n\t"                  \
+        "@!ph mad.lo.u32 %0, t, %11, %0;\n\t"                 \
+        "@!ph mad.lo.u32 %2, b, %11, %2;\n\t"                 \
+        "}"
+    if (kCheckRank)
+        asm("{\n\t.reg .pred pm, pd, ph;\n\t.reg .u32 b, t, g4;\n\t"
+            "setp.ne.u32 pm, %7, 0;\n\t"
+            "setp.lt.and.u32 pd, %8, %10, pm;\n\t" G2048_COMMIT_BODY
+            : "+r"(al), "+r"(ah), "+r"(nlo), "+r"(nhi), "=r"(status)
+            : "r"(g), "r"(exp_mul), "r"((u32)moved), "r"(rank), "r"((u32)in_hi), "r"(ne), "r"(one));
+    else
+        asm("{\n\t.reg .pred pm, pd, ph;\n\t.reg .u32 b, t, g4;\n\t"
+            "setp.ne.u32 pm, %7, 0;\n\t"
+            "setp.ne.u32 pd, %7, 0;\n\t" G2048_COMMIT_BODY
+            : "+r"(al), "+r"(ah), "+r"(nlo), "+r"(nhi), "=r"(status)
+            : "r"(g), "r"(exp_mul), "r"((u32)moved), "r"(rank), "r"((u32)in_hi), "r"(0u), "r"(one));
+#undef G2048_COMMIT_BODY
+#else
+    const bool ok = !kCheckRank || rank < ne;
+    status = moved ? (ok ? 0x30u : 0xB0u) : 0x10u;
+    const u32 b = (moved && ok) ? lop3<kLowestIndicator>(g, g << 4, 0x88888888u) : 0u;
+    const u32 t = mulhi(b, exp_mul);
+    if (in_hi) { ah += t; nhi += b; } else { al += t; nlo += b; }
+#endif
 }
 
 template <bool kPhilox, class Lut>
@@ -319,18 +384,11 @@ G2048_HD FastOut transition_fast(u32 lo, u32 hi, const Orient& o, u32 rank, u32 
     u32 nlo = nz8(al, one), nhi = nz8(ah, one);
     const u32 tiles_lo = popc(nlo), ne = 16u - (tiles_lo + popc(nhi));
     if (kPhilox) rank = mulhi(w0, ne);
-    // a Philox rank is < ne by construction (and a move always leaves an empty cell)
-    const bool ok = kPhilox ? true : rank < ne;
     bool in_hi;
-    const u32 bit3 = spawn_marker(nlo, nhi, tiles_lo, rank, one, in_hi);
-    const u32 tile = mulhi(bit3, exp_mul);       // exponent 1 or 2 at bit 0 of that nibble (one IMAD.HI)
-    // status bits besides the mask: 0x10 is cancelled below when some action is legal;
-    // not moved -> 0x10, moved without a valid spawn -> MOVED | BADSPAWN, moved and spawned -> MOVED
-    u32 status = moved ? 0xB0u : 0x10u;
-    if (moved & ok) {
-        status = 0x30u;
-        if (in_hi) { ah += tile; nhi += bit3; } else { al += tile; nlo += bit3; }
-    }
+    const u32 g = spawn_prefix(nlo, nhi, tiles_lo, rank, one, in_hi);
+    // a Philox rank is < ne by construction (and a move always leaves an empty cell)
+    u32 status;
+    spawn_commit<!kPhilox>(al, ah, nlo, nhi, status, g, exp_mul, moved, rank, ne, in_hi, one);
 
     // ---- flags of the new board: mask | DONE (0x10) iff no action is legal | status ----
     const u32 f = legal_mask(al, ah, nlo, nhi, one, status);

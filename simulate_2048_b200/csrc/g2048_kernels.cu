@@ -351,8 +351,8 @@ struct SmemLut {
 template <bool kPhilox>
 __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 spawns,
                                            const StepArgs& a, u64 env0, const SmemLut& lut,
-                                           const uint4* __restrict__ s_orient, Boards4& ob,
-                                           int4& rw, u32& fl) {
+                                           const uint4* __restrict__ s_orient, u64* out_boards,
+                                           int32_t* out_rewards, uint8_t* out_flags) {
     // Range test in two levels.  Cheap filter (one LOP3 per word): bit 3 of acc is set where some
     // nibble has bits 3 and 2 set, i.e. a tile >= 4096.  Only then the exact test (nibble >= 14)
     // runs — never on the benchmark set or in random play, rarely with a strong player.
@@ -363,16 +363,21 @@ __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 s
         acc = fast::lop3<fast::kA | (fast::kB & fast::kC)>(acc, lo, lo << 1);
         acc = fast::lop3<fast::kA | (fast::kB & fast::kC)>(acc, hi, hi << 1);
     }
-    bool slow = !kPhilox && (spawns & 0x80808080u) != 0u;
-    if ((acc & 0x88888888u) != 0u) {
-        u32 big = 0;
+    // One test on the common path: some tile >= 4096 or some absolute-cell spawn byte (bit 7)
+    const u32 abs4 = kPhilox ? 0u : spawns & 0x80808080u;
+    bool slow = false;
+    if (((acc & 0x88888888u) | abs4) != 0u) {
+        u32 big = abs4;
 #pragma unroll
         for (int k = 0; k < 4; ++k) big |= fast::big_tile_bits((u32)in.b[k], (u32)(in.b[k] >> 32));
-        slow |= big != 0u;
+        slow = big != 0u;
     }
-    int rws[4];
-    fl = 0;
+    // Each branch ends in its own stores: merging the results of the out-of-line calls with the
+    // fast path's into one set of registers costs ~10 moves per tile in front of the 256-bit store.
     if (slow) {
+        Boards4 ob;
+        int rws[4];
+        u32 fl = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {  // unrolled: static indices keep the arrays in registers
             const uint4 r = transition_slow<kPhilox>(in.b[k], (actions >> (8 * k)) & 0xFFu,
@@ -382,9 +387,14 @@ __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 s
             rws[k] = (int)r.z;
             fl |= r.w << (8 * k);
         }
-        rw = make_int4(rws[0], rws[1], rws[2], rws[3]);
+        st_boards4(out_boards, ob);
+        st_int4_stream(out_rewards, make_int4(rws[0], rws[1], rws[2], rws[3]));
+        st_u32_stream(out_flags, fl);
         return;
     }
+    Boards4 ob;
+    int rws[4];
+    u32 fl = 0;
     const u32 act4 = (actions << 5) & 0x60606060u;     // byte k = 32 * action_k (byte offset)
     const u32 rank4 = spawns & 0x0F0F0F0Fu;            // byte k = spawn rank
     const u32 exp4 = ((spawns & 0x10101010u) << 1) + 0x20202020u;       // byte k = exponent (1 or 2) << 5
@@ -409,9 +419,11 @@ __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 s
                                                                rank, exp_mul, w0, lut, a.one);
         ob.b[k] = ((u64)r.hi << 32) | r.lo;
         rws[k] = (int)r.reward;
-        fl = fast::add(r.flags << (8 * k), fl, a.one);
+        fl = fast::mad(r.flags, 1u << (8 * k), fl);   // one IMAD: shift and accumulate
     }
-    rw = make_int4(rws[0], rws[1], rws[2], rws[3]);
+    st_boards4(out_boards, ob);
+    st_int4_stream(out_rewards, make_int4(rws[0], rws[1], rws[2], rws[3]));
+    st_u32_stream(out_flags, fl);
 }
 
 constexpr u32 kStepSmemBytes = kSmemTableBytes + 64u + 4u * (u32)sizeof(fast::Orient);
@@ -433,19 +445,11 @@ template <bool kPhilox, int kGroups>
 __device__ __forceinline__ void compute_store_tiles(const TileBuf<kPhilox, kGroups>& t, const StepArgs& a,
                                                     const StepCursor& c, size_t off, const SmemLut& lut,
                                                     const uint4* __restrict__ s_orient) {
-    Boards4 ob[kGroups];
-    int4 rw[kGroups];
-    u32 fl[kGroups];
 #pragma unroll
     for (int j = 0; j < kGroups; ++j)
         step_tile4<kPhilox>(t.g[j].boards, t.g[j].actions, t.g[j].spawns, a, c.env + off + 4 * j,
-                            lut, s_orient, ob[j], rw[j], fl[j]);
-#pragma unroll
-    for (int j = 0; j < kGroups; ++j) {
-        st_boards4(c.boards_out + off + 4 * j, ob[j]);
-        st_int4_stream(c.rewards + off + 4 * j, rw[j]);
-        st_u32_stream(c.flags + off + 4 * j, fl[j]);
-    }
+                            lut, s_orient, c.boards_out + off + 4 * j, c.rewards + off + 4 * j,
+                            c.flags + off + 4 * j);
 }
 
 // Persistent CTA (one per SM).  Each CTA owns a CONTIGUOUS range of tiles so that the next tile
