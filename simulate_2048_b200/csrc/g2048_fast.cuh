@@ -140,17 +140,6 @@ G2048_HD u32 sub16_if_differ(u32 x, u32 ref, u32 one) {
 #endif
 }
 
-// x - y if c (predicated IADD instead of SEL + IADD)
-G2048_HD u32 sub_if(u32 x, u32 y, bool c) {
-#if defined(__CUDA_ARCH__)
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p sub.u32 %0, %0, %1;\n\t}"
-        : "+r"(x) : "r"(y), "r"((u32)c));
-    return x;
-#else
-    return c ? x - y : x;
-#endif
-}
-
 // a * b + c on the FMA pipe (IMAD)
 G2048_HD u32 mad(u32 a, u32 b, u32 c) {
 #if defined(__CUDA_ARCH__)
@@ -314,7 +303,7 @@ G2048_HD u32 spawn_prefix(u32 nlo, u32 nhi, u32 tiles_lo, u32 rank, u32 one, boo
     const u32 clo = mad(tiles_lo, 0u - one, 8u);   // 8 - tiles_lo as an IMAD
     in_hi = rank >= clo;
     const u32 nsel = in_hi ? nhi : nlo;
-    const u32 r = in_hi ? rank - clo : rank;
+    const u32 r = in_hi ? rank - clo : rank;   // (ptxas turns a predicated subtract into SEL + IADD as well)
     return mad(shr<3>(nsel), 0xEEEEEEEFu, mad(r, 0xEEEEEEEFu, 0xFEDCBA98u));
 }
 // The empty-count is non-decreasing along the nibbles, so bit 3 of g is 0..0 1..1 from the target

@@ -480,18 +480,24 @@ __global__ void __launch_bounds__(kThreads, 1) step_lut_kernel(const StepArgs a)
     table_stage_wait(bar);  // __syncthreads inside also publishes s_orient
     const SmemLut lut{};
 
-    // bounds are pointer compares: a 32-bit trip counter makes ptxas build a jump table (BRX) for the
-    // three tests below, which costs 12 % of the throughput
-    const u64* const end = c.boards_in + tiles * kTile;
-    while (c.boards_in < end) {
-        const bool hasB = c.boards_in + kTile < end;
+    // Bounds are compares of the LOW WORD of the board cursor against precomputed ends (one ISETP
+    // each; a 64-bit pointer compare is four instructions, and a 32-bit trip counter makes ptxas
+    // build a jump table (BRX) for the three tests, which costs 12 %).  A CTA's range is far below
+    // 4 GiB and the cursor only moves in whole tiles, so equality of the low words is exact.
+    constexpr u32 kTileBytes = (u32)(kTile * sizeof(u64));
+    const u32 end0 = (u32)reinterpret_cast<uintptr_t>(c.boards_in + tiles * kTile);
+    const u32 end1 = end0 - kTileBytes, end2 = end0 - 2u * kTileBytes;
+#define G2048_CUR() ((u32) reinterpret_cast<uintptr_t>(c.boards_in))
+    while (G2048_CUR() != end0) {
+        const bool hasB = G2048_CUR() != end1;
         if (hasB) load_tiles(bufB, c, kTile);
         compute_store_tiles(bufA, a, c, 0, lut, s_orient);
         if (!hasB) break;
-        if (c.boards_in + 2 * kTile < end) load_tiles(bufA, c, 2 * kTile);
+        if (G2048_CUR() != end2) load_tiles(bufA, c, 2 * kTile);
         compute_store_tiles(bufB, a, c, kTile, lut, s_orient);
         c.advance(2 * kTile);
     }
+#undef G2048_CUR
 
     // ragged tail (< one tile): spread over the CTAs, one env per thread through the exact path
     for (size_t i = full_tiles * kTile + blockIdx.x * (size_t)kThreads + threadIdx.x; i < a.n;
