@@ -153,6 +153,14 @@ int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* rewards, uint
                  uint8_t* num_empty, uint8_t* child_count, uint64_t* children,
                  const int64_t* child_offsets, int child_layout, size_t n, void* stream);
 
+/* The chance children alone, from the afterstates and child counts an earlier g2048_expand call
+ * wrote (after[n*4], child_count[n*4]): gameboard.py:132 after_state of every legal afterstate.
+ * A caller that sizes the compact children buffer from child_count (count, prefix sum, allocate)
+ * thus pays for the four moves once.  child_layout is DENSE or COMPACT; child_offsets as above. */
+int g2048_expand_children(const uint64_t* after, const uint8_t* child_count,
+                          const int64_t* child_offsets, uint64_t* children, int child_layout,
+                          size_t n, void* stream);
+
 /* Chance children of given boards (gameboard.py:132 after_state, :174 after_state_lazy):
  * children[n*32] dense (slot 2k + v = k-th empty cell in row-major order, v: 0 -> tile 2,
  * 1 -> tile 4; a full board yields children[0] = the board itself), num_empty[n], and

@@ -37,6 +37,7 @@ PROTOTYPES = {
     'g2048_env_step': (C.c_int, [_P, _P, _P, _P, _P, _P, _U64, _U64, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     'g2048_mask': (C.c_int, [_P, _P, _SZ, _P]),
     'g2048_expand': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _SZ, _P]),
+    'g2048_expand_children': (C.c_int, [_P, _P, _P, _P, C.c_int, _SZ, _P]),
     'g2048_after_state': (C.c_int, [_P, _P, _P, _P, _SZ, _P]),
     'g2048_reset': (C.c_int, [_U64, _U64, _P, _P, _P, _SZ, _P]),
     'g2048_spawn': (C.c_int, [_P, _P, _U64, _U64, _P, _U32, _U32, _P, _SZ, _P]),

@@ -1158,6 +1158,24 @@ __global__ void __launch_bounds__(kChildWarps * 32) expand_children_kernel(const
     }
 }
 
+// the second kernel of the expansion: one wave, as many blocks as are resident at once (a partial
+// second wave costs ~14 %)
+static int launch_expand_children(const ExpandArgs& a, const DeviceState* s, cudaStream_t st) {
+    static int occ = 0;
+    if (occ == 0) {
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+            &occ, expand_children_kernel<G2048_CHILDREN_COMPACT>, kChildWarps * 32, 0));
+        if (occ < 1) occ = 1;
+    }
+    const int grid = grid_for(a.n, kChildWarps * 32, s->sms, occ);
+    if (a.layout == G2048_CHILDREN_COMPACT)
+        expand_children_kernel<G2048_CHILDREN_COMPACT><<<grid, kChildWarps * 32, 0, st>>>(a);
+    else
+        expand_children_kernel<G2048_CHILDREN_DENSE><<<grid, kChildWarps * 32, 0, st>>>(a);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
 constexpr size_t kExpandSmemMinBoards = (size_t)1 << 17;
 
 extern "C" int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* rewards,
@@ -1200,20 +1218,7 @@ extern "C" int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* re
         }
         CU(cudaGetLastError());
         if (child_layout == G2048_CHILDREN_NONE) return G2048_OK;
-        // one wave: as many blocks as are resident at once (a partial second wave costs ~14 %)
-        static int occ = 0;
-        if (occ == 0) {
-            CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                &occ, expand_children_kernel<G2048_CHILDREN_COMPACT>, kChildWarps * 32, 0));
-            if (occ < 1) occ = 1;
-        }
-        const int grid = grid_for(n, kChildWarps * 32, s->sms, occ);
-        if (child_layout == G2048_CHILDREN_COMPACT)
-            expand_children_kernel<G2048_CHILDREN_COMPACT><<<grid, kChildWarps * 32, 0, st>>>(a);
-        else
-            expand_children_kernel<G2048_CHILDREN_DENSE><<<grid, kChildWarps * 32, 0, st>>>(a);
-        CU(cudaGetLastError());
-        return G2048_OK;
+        return launch_expand_children(a, s, st);
     };
     rc = launch();
     if (scratch) {
@@ -1221,6 +1226,23 @@ extern "C" int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* re
         if (rc == G2048_OK && fe != cudaSuccess) return cuda_fail(fe, "cudaFreeAsync(scratch)");
     }
     return rc;
+}
+
+extern "C" int g2048_expand_children(const uint64_t* after, const uint8_t* child_count,
+                                     const int64_t* child_offsets, uint64_t* children,
+                                     int child_layout, size_t n, void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!after || !child_count || !children) return G2048_EINVAL;
+    if (child_layout != G2048_CHILDREN_DENSE && child_layout != G2048_CHILDREN_COMPACT) return G2048_EINVAL;
+    if (child_layout == G2048_CHILDREN_COMPACT && !child_offsets) return G2048_EINVAL;
+    if (!aligned(after, 16) || !aligned(child_count, 4) || !aligned(children, 16)) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    ExpandArgs a{nullptr, const_cast<u64*>(reinterpret_cast<const u64*>(after)), nullptr, nullptr, nullptr,
+                 const_cast<uint8_t*>(child_count), reinterpret_cast<u64*>(children), child_offsets,
+                 child_layout, n, s->table, s->table_hashed, 1u};
+    return launch_expand_children(a, s, (cudaStream_t)stream);
 }
 
 __global__ void __launch_bounds__(256) after_state_kernel(const u64* __restrict__ boards,

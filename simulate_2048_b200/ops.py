@@ -179,15 +179,21 @@ def expand(boards: torch.Tensor, children: str = 'none', zero_fill: bool = True,
     ch = off = None
     with torch.cuda.device(dev):
         if layout == _cabi.CHILDREN_COMPACT:
-            # pass 1 sizes the children, pass 2 writes them (afterstates are recomputed: 8 B read)
-            check(lib().g2048_expand(_ptr(boards), None, None, None, None, _ptr(child_count), None,
-                                     None, _cabi.CHILDREN_NONE, n, _stream()))
+            # the moves run once and write every fixed-size output; their counts size the children,
+            # which g2048_expand_children then builds from the afterstates
+            check(lib().g2048_expand(_ptr(boards), _ptr(after), _ptr(rewards), _ptr(mask),
+                                     _ptr(num_empty), _ptr(child_count), None, None,
+                                     _cabi.CHILDREN_NONE, n, _stream()))
             per_env = child_count.to(torch.int64).sum(dim=1)
             incl = torch.cumsum(per_env, dim=0)
             off = (incl - per_env).contiguous()
             total = int(incl[-1].item()) if n else 0
             ch = torch.empty(total, dtype=torch.int64, device=dev)
-        elif layout == _cabi.CHILDREN_DENSE:
+            if total:
+                check(lib().g2048_expand_children(_ptr(after), _ptr(child_count), _ptr(off), _ptr(ch),
+                                                  layout, n, _stream()))
+            return ExpandOut(after, rewards, mask, num_empty, child_count, ch, off)
+        if layout == _cabi.CHILDREN_DENSE:
             ch = torch.empty((n, 4, 16, 2), dtype=torch.int64, device=dev)
         check(lib().g2048_expand(_ptr(boards), _ptr(after), _ptr(rewards), _ptr(mask),
                                  _ptr(num_empty), _ptr(child_count), _ptr(ch), _ptr(off), layout, n,

@@ -132,6 +132,37 @@ def test_expand_dense_writes_every_slot(T, ops, oracle):
     np.testing.assert_array_equal(host(ex.children), oracle.expand(boards, child_layout=1)['children'])
 
 
+def test_expand_children_from_earlier_afterstates(T, ops, oracle):
+    """g2048_expand_children rebuilds the children from the afterstates and counts of an earlier
+    call (the moves are paid once): identical to the one-call result, dense and compact, and the
+    argument checks of the entry point."""
+    from simulate_2048_b200 import _cabi
+    boards = synthetic_packed(7001, seed=31)
+    boards[::97] = synthetic_packed(len(boards[::97]), seed=8, max_exp=15)   # exact-path boards
+    d = dev(T, boards)
+    n = d.numel()
+    lib = ops.lib()
+    ptr = lambda t: None if t is None else t.data_ptr()
+    for layout, code in (('dense', 1), ('compact', 2)):
+        want = oracle.expand(boards, child_layout=code)
+        fixed = ops.expand(d, children='none')
+        np.testing.assert_array_equal(host(fixed.after), want['after'].reshape(n, 4))
+        if code == 1:
+            ch, off = T.full((n, 4, 16, 2), -1, dtype=T.int64, device='cuda'), None
+        else:
+            per_env = fixed.child_count.to(T.int64).sum(dim=1)
+            off = (T.cumsum(per_env, 0) - per_env).contiguous()
+            ch = T.full((int(per_env.sum().item()),), -1, dtype=T.int64, device='cuda')
+        rc = lib.g2048_expand_children(ptr(fixed.after), ptr(fixed.child_count), ptr(off), ptr(ch), code, n, None)
+        assert rc == 0
+        T.cuda.synchronize()
+        np.testing.assert_array_equal(host(ch).reshape(-1), np.asarray(want['children']).reshape(-1))
+    assert lib.g2048_expand_children(None, ptr(fixed.child_count), ptr(off), ptr(ch), 2, n, None) == _cabi.EINVAL
+    assert lib.g2048_expand_children(ptr(fixed.after), ptr(fixed.child_count), None, ptr(ch), 2, n, None) == _cabi.EINVAL
+    assert lib.g2048_expand_children(ptr(fixed.after), ptr(fixed.child_count), ptr(off), ptr(ch), 0, n, None) == _cabi.EINVAL
+    assert lib.g2048_expand_children(ptr(fixed.after), ptr(fixed.child_count), ptr(off), ptr(ch), 2, 0, None) == 0
+
+
 def test_after_state_vs_oracle(T, ops, oracle):
     boards = synthetic_packed(20000, seed=3)
     boards[:3] = pack_tiles(np.array([[[0] * 4] * 4, [[2] * 4] * 4, [[2, 4, 8, 16], [32, 64, 128, 0], [2, 4, 8, 16], [32, 64, 128, 256]]]))
