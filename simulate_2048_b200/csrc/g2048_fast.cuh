@@ -1,8 +1,9 @@
 // g2048_fast.cuh — the branch-free transition used by the HBM-bound step kernel.
 //
-// Measured on B200 (profiles/r01_microbench_pipes.txt): LOP3 / SHF / PRMT / ISETP / SEL issue at
-// 2 warp-instr/clk/SM (the "ALU" pipe), IMAD at 2 on the separate FMA pipe, integer adds at 4,
-// IMAD.HI at 1, POPC at 0.5, a random LDS.32 costs 3.5 clk.  ncu on the first version of the
+// Measured on B200 (profiles/r01_microbench_pipes.txt): LOP3 / SHF / PRMT / ISETP / SEL / IADD3
+// issue at 2 warp-instr/clk/SM (the "ALU" pipe; the probe's "IADD 4.0" is ptxas folding two adds
+// into one IADD3), IMAD at 2 on the separate FMA pipe, IMAD.HI / IMAD.WIDE at 1, POPC at 0.5, a
+// random LDS.32 costs 3.5 clk.  ncu on the first version of the
 // step kernel: ALU pipe 94 % busy, FMA pipe 10 %, 220 instructions per env (profiles/).  The
 // HBM roofline leaves ~1 clk per env-step per SM, so the transition is written to
 //   * never branch on data (actions are random: a divergent warp pays for every path),
