@@ -81,6 +81,8 @@ struct DeviceState {
 static DeviceState g_dev[64];
 static int g_impl = G2048_IMPL_AUTO;
 static int g_step_threads = 0;  // 0 = automatic: 640 with injected spawns (5 warps per scheduler at 96 registers: +1 %), 512 with Philox
+// programmatic dependent launch of the step kernel (environment G2048_PDL=0 turns it off)
+static int g_pdl = [] { const char* e = getenv("G2048_PDL"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
 static int g_step_groups = 1;   // groups of 4 envs per thread (1 or 2)  // tuning knob (g2048_set_tuning)
 
 static int current_state(DeviceState** out) {
@@ -474,6 +476,14 @@ __global__ void __launch_bounds__(kThreads, 1) step_lut_kernel(const StepArgs a)
     StepCursor c{a.boards_in, a.actions, a.spawns, a.boards_out, a.rewards, a.flags, a.env_offset};
     c.advance(t_begin * kTile + threadIdx.x * kPerThread);
 
+    // Programmatic dependent launch: everything above (table staging, orientation words, cursor
+    // set-up) reads nothing an earlier kernel of the stream wrote, so it may run while that kernel
+    // drains; its outputs are awaited here.  The dependents of THIS launch may be scheduled at
+    // once: they cannot become resident before our CTA leaves the SM (shared memory is full), and
+    // they wait at the same point for our stores.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
+
     TileBuf<kPhilox, kGroups> bufA, bufB;
     if (tiles != 0) load_tiles(bufA, c, 0);
 
@@ -586,11 +596,23 @@ extern "C" int g2048_step(const uint64_t* boards_in, const uint8_t* actions, con
         const int threads = g_step_threads ? g_step_threads : (spawns ? 640 : 512), groups = g_step_groups;
         const size_t tiles = n / ((size_t)threads * 4 * groups);
         const int grid = (int)(tiles < (size_t)s->sms ? (tiles ? tiles : 1) : (size_t)s->sms);
+        // launched with the programmatic-serialization attribute: back-to-back step launches
+        // overlap the next launch's latency and table staging with this launch's tail
+        cudaLaunchAttribute pdl[1];
+        pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        pdl[0].val.programmaticStreamSerializationAllowed = g_pdl;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.dynamicSmemBytes = (size_t)smem;
+        cfg.stream = st;
+        cfg.attrs = pdl;
+        cfg.numAttrs = 1;
 #define G2048_LAUNCH_STEP(PH, TH, GR)                                                                     \
     do {                                                                                                  \
         CU(cudaFuncSetAttribute(step_lut_kernel<PH, TH, GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 smem));                                                                   \
-        step_lut_kernel<PH, TH, GR><<<grid, TH, smem, st>>>(a);                                           \
+        cfg.blockDim = dim3(TH);                                                                          \
+        CU(cudaLaunchKernelEx(&cfg, step_lut_kernel<PH, TH, GR>, a));                                     \
     } while (0)
 #define G2048_LAUNCH_STEP_T(PH)                                          \
     do {                                                                 \
