@@ -1062,7 +1062,7 @@ __global__ void __launch_bounds__(256) expand_moves_gather_kernel(const ExpandAr
 constexpr int kChildWarps = 8;
 
 template <int kLayout>
-__global__ void __launch_bounds__(kChildWarps * 32, 5) expand_children_kernel(const ExpandArgs a) {
+__global__ void __launch_bounds__(kChildWarps * 32) expand_children_kernel(const ExpandArgs a) {
     // per warp: the records of a tile of 32 boards, loaded coalesced once (lane = board), then
     // read back by the whole warp board after board.  In that second phase a lane serves a FIXED
     // (action, rank) pair — action = lane / 8, rank = lane % 8 (+ 8 in the second pass) — so no
@@ -1114,17 +1114,8 @@ __global__ void __launch_bounds__(kChildWarps * 32, 5) expand_children_kernel(co
         s_meta[w][lane] = meta;
         __syncwarp();
         const u32 n_here = (u32)min((size_t)32, a.n - tile);
-        // the records of board k + 1 are read from shared memory while board k is expanded: the
-        // loop is otherwise one dependent LDS -> marker -> store chain per board (short_scoreboard
-        // was the top stall)
-        uint4 mt_next = s_meta[w][0], rec_next = s_rec[w][0][act];
-#pragma unroll 1
         for (u32 k = 0; k < n_here; ++k) {
-            const uint4 mt = mt_next;    // warp-uniform
-            const uint4 rec = rec_next;  // {after.lo, after.hi, n_lo, n_hi} of my action
-            const u32 kn = min(k + 1u, 31u);
-            mt_next = s_meta[w][kn];
-            rec_next = s_rec[w][kn][act];
+            const uint4 mt = s_meta[w][k];  // warp-uniform
             const u32 cc4 = mt.x;
             // dense layout: every one of the board's 128 slots is written (children, then zeros), so
             // the output needs no memset and DRAM sees full lines instead of partial 256-byte slots
@@ -1132,6 +1123,7 @@ __global__ void __launch_bounds__(kChildWarps * 32, 5) expand_children_kernel(co
             u64* const board_dst = a.children + (((unsigned long long)mt.w << 32) | mt.z);
             if (((cc4 & 0x01010101u) | (kLayout == G2048_CHILDREN_COMPACT ? (mt.z & 1u) : 0u)) == 0u) {
                 // even counts, 16-byte aligned destination: the common case
+                const uint4 rec = s_rec[w][k][act];
                 const u32 q = fast::prmt(cc4, 0u, byte_sel) >> 1;  // empty cells of my action
                 const u32 slot0 = (kLayout == G2048_CHILDREN_COMPACT) ? 2u * fast::prmt(mt.y, 0u, byte_sel) : 32u * act;
                 const u32 tiles_lo = __popc(rec.z);
