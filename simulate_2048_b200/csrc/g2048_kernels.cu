@@ -991,10 +991,16 @@ struct GlobalLut {
     }
 };
 
+struct MovesOut {
+    uint2 after4[4];  // afterstates {lo, hi} per action
+    int rew4[4];
+    u32 ne4, cc4;     // empties / child count of each afterstate, one byte per action
+    u32 flags;        // mask byte (LEGAL | DONE | OVERFLOW bits)
+};
+
 template <class Lut>
-__device__ __forceinline__ void expand_moves_board(const ExpandArgs& a, size_t i, const Lut& lut) {
+__device__ __forceinline__ MovesOut expand_moves_compute(const ExpandArgs& a, u64 packed, const Lut& lut) {
     constexpr fast::Orient kOrient[4] = G2048_ORIENT_TABLE;
-    const u64 packed = a.boards[i];
     const u32 lo = (u32)packed, hi = (u32)(packed >> 32);
     u32 m = 0, ovf = 0, ne4 = 0, cc4 = 0;
     uint2 after4[4];
@@ -1032,13 +1038,34 @@ __device__ __forceinline__ void expand_moves_board(const ExpandArgs& a, size_t i
             cc4 |= (moved ? (ne ? 2u * ne : 1u) : 0u) << (8 * act);
         }
     }
-    uint4* o = reinterpret_cast<uint4*>(a.after + i * 4);
-    o[0] = make_uint4(after4[0].x, after4[0].y, after4[1].x, after4[1].y);
-    o[1] = make_uint4(after4[2].x, after4[2].y, after4[3].x, after4[3].y);
-    if (a.rewards) *reinterpret_cast<int4*>(a.rewards + i * 4) = make_int4(rew4[0], rew4[1], rew4[2], rew4[3]);
-    if (a.num_empty) *reinterpret_cast<u32*>(a.num_empty + i * 4) = ne4;
-    *reinterpret_cast<u32*>(a.child_count + i * 4) = cc4;
-    if (a.mask) a.mask[i] = (uint8_t)(board_flags(m) | (ovf ? G2048_FLAG_OVERFLOW : 0u));
+    MovesOut r;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        r.after4[k] = after4[k];
+        r.rew4[k] = rew4[k];
+    }
+    r.ne4 = ne4;
+    r.cc4 = cc4;
+    r.flags = board_flags(m) | (ovf ? G2048_FLAG_OVERFLOW : 0u);
+    return r;
+}
+
+// the fixed-size outputs of board i, one wide store per field (NULL pointers are skipped)
+__device__ __forceinline__ void expand_moves_store(const ExpandArgs& a, size_t i, const MovesOut& r) {
+    if (a.after) {
+        uint4* o = reinterpret_cast<uint4*>(a.after + i * 4);
+        o[0] = make_uint4(r.after4[0].x, r.after4[0].y, r.after4[1].x, r.after4[1].y);
+        o[1] = make_uint4(r.after4[2].x, r.after4[2].y, r.after4[3].x, r.after4[3].y);
+    }
+    if (a.rewards) *reinterpret_cast<int4*>(a.rewards + i * 4) = make_int4(r.rew4[0], r.rew4[1], r.rew4[2], r.rew4[3]);
+    if (a.num_empty) *reinterpret_cast<u32*>(a.num_empty + i * 4) = r.ne4;
+    if (a.child_count) *reinterpret_cast<u32*>(a.child_count + i * 4) = r.cc4;
+    if (a.mask) a.mask[i] = (uint8_t)r.flags;
+}
+
+template <class Lut>
+__device__ __forceinline__ void expand_moves_board(const ExpandArgs& a, size_t i, const Lut& lut) {
+    expand_moves_store(a, i, expand_moves_compute(a, a.boards[i], lut));
 }
 
 // persistent, hashed table staged in shared memory
@@ -1061,16 +1088,102 @@ __global__ void __launch_bounds__(256) expand_moves_gather_kernel(const ExpandAr
 
 constexpr int kChildWarps = 8;
 
+// One warp's record of a tile of 32 boards in shared memory (lane = board while it is written).
+struct ChildTile {
+    uint4 rec[32][4];  // {after.lo, after.hi, n_lo, n_hi} per action
+    uint4 meta[32];    // {counts, first pair of each action, offset lo, offset hi}
+};
+
+__device__ __forceinline__ void expand_record(ChildTile& t, u32 lane, uint4 s01, uint4 s23, u32 cc4,
+                                              unsigned long long off) {
+    t.rec[lane][0] = make_uint4(s01.x, s01.y, fast::nz8(s01.x, 1u), fast::nz8(s01.y, 1u));
+    t.rec[lane][1] = make_uint4(s01.z, s01.w, fast::nz8(s01.z, 1u), fast::nz8(s01.w, 1u));
+    t.rec[lane][2] = make_uint4(s23.x, s23.y, fast::nz8(s23.x, 1u), fast::nz8(s23.y, 1u));
+    t.rec[lane][3] = make_uint4(s23.z, s23.w, fast::nz8(s23.z, 1u), fast::nz8(s23.w, 1u));
+    // pairs (= empty cells) in front of each action's segment, one byte per action
+    const u32 h = (cc4 >> 1) & 0x7F7F7F7Fu;
+    const u32 first4 = (h << 8) + (h << 16) + (h << 24);
+    t.meta[lane] = make_uint4(cc4, first4, (u32)off, (u32)(off >> 32));
+}
+
+// The children of the first n_here boards of a tile, written by the whole warp board after board.
+// A lane serves a FIXED (action, rank) pair — action = lane / 8, rank = lane % 8 (+ 8 in the
+// second pass) — so no per-child search for the segment is needed and the record is read once
+// per board.
+template <int kLayout>
+__device__ __forceinline__ void expand_children_tile(const ExpandArgs& a, const ChildTile& t, u32 n_here,
+                                                     u32 lane) {
+    const u32 act = lane >> 3, r0 = lane & 7u, byte_sel = 0x4440u + act;
+    for (u32 k = 0; k < n_here; ++k) {
+        const uint4 mt = t.meta[k];  // warp-uniform
+        const u32 cc4 = mt.x;
+        // dense layout: every one of the board's 128 slots is written (children, then zeros), so
+        // the output needs no memset and DRAM sees full lines instead of partial 256-byte slots
+        if (kLayout == G2048_CHILDREN_COMPACT && cc4 == 0u) continue;
+        u64* const board_dst = a.children + (((unsigned long long)mt.w << 32) | mt.z);
+        if (((cc4 & 0x01010101u) | (kLayout == G2048_CHILDREN_COMPACT ? (mt.z & 1u) : 0u)) == 0u) {
+            // even counts, 16-byte aligned destination: the common case
+            const uint4 rec = t.rec[k][act];
+            const u32 q = fast::prmt(cc4, 0u, byte_sel) >> 1;  // empty cells of my action
+            const u32 slot0 = (kLayout == G2048_CHILDREN_COMPACT) ? 2u * fast::prmt(mt.y, 0u, byte_sel) : 32u * act;
+            const u32 tiles_lo = __popc(rec.z);
+            const bool second = ((cc4 + 0x6F6F6F6Fu) & 0x80808080u) != 0u;  // some count > 16
+#pragma unroll
+            for (u32 pass = 0; pass < 2u; ++pass) {
+                if (kLayout == G2048_CHILDREN_COMPACT && pass == 1u && !second) break;  // warp-uniform
+                const u32 rank = r0 + 8u * pass;
+                if (kLayout == G2048_CHILDREN_DENSE && rank >= q) {
+                    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(
+                                     board_dst + slot0 + 2u * rank), "r"(0u)
+                                 : "memory");
+                } else if (rank < q) {
+                    bool in_hi;
+                    const u32 bit3 = fast::spawn_marker(rec.z, rec.w, tiles_lo, rank, 1u, in_hi);
+                    const u32 tl1 = bit3 >> 3;           // exponent 1 (tile 2) in the target nibble
+                    const u32 tl = in_hi ? 0u : tl1, th = in_hi ? tl1 : 0u;
+                    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(
+                                     board_dst + slot0 + 2u * rank),
+                                 "r"(rec.x + tl), "r"(rec.y + th), "r"(rec.x + 2u * tl), "r"(rec.y + 2u * th)
+                                 : "memory");
+                }
+            }
+        } else {
+            if (kLayout == G2048_CHILDREN_DENSE) {  // zero the board's slots first
+                asm volatile("st.global.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(board_dst + 2u * lane), "r"(0u) : "memory");
+                asm volatile("st.global.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(board_dst + 64u + 2u * lane), "r"(0u) : "memory");
+                __syncwarp();
+            }
+            if (lane < 4u) {
+                // Odd counts or an odd caller-supplied offset: one lane per action, serially.  A
+                // count of 1 (an afterstate without an empty cell) cannot follow a move; the exact
+                // path keeps the reference's convention (gameboard.py:158-159) for completeness.
+                const u32 cc = (cc4 >> (8u * lane)) & 0xFFu;
+                u32 before = 0;
+                for (u32 q = 0; q < lane; ++q) before += (cc4 >> (8u * q)) & 0xFFu;
+                u64* dst = board_dst + ((kLayout == G2048_CHILDREN_COMPACT) ? before : 32u * lane);
+                const uint4 rec = t.rec[k][lane];
+                const u64 st = ((u64)rec.y << 32) | rec.x;
+                if (cc == 1u) {
+                    *dst = st;
+                } else {
+                    u32 q = 0;
+                    for (u32 cell = 0; cell < 16u && q < cc; ++cell) {
+                        if ((st >> (4u * cell)) & 0xFull) continue;
+                        dst[q++] = st | (1ull << (4u * cell));
+                        dst[q++] = st | (2ull << (4u * cell));
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int kLayout>
 __global__ void __launch_bounds__(kChildWarps * 32) expand_children_kernel(const ExpandArgs a) {
     // per warp: the records of a tile of 32 boards, loaded coalesced once (lane = board), then
-    // read back by the whole warp board after board.  In that second phase a lane serves a FIXED
-    // (action, rank) pair — action = lane / 8, rank = lane % 8 (+ 8 in the second pass) — so no
-    // per-child search for the segment is needed and the record is read once per board.
-    __shared__ uint4 s_rec[kChildWarps][32][4];  // {after.lo, after.hi, n_lo, n_hi} per action
-    __shared__ uint4 s_meta[kChildWarps][32];    // {counts, first pair of each action, offset lo, hi}
+    // read back by the whole warp board after board
+    __shared__ ChildTile s_tile[kChildWarps];
     const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const u32 act = lane >> 3, r0 = lane & 7u, byte_sel = 0x4440u + act;
     const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
     const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
     // the records of the NEXT tile are fetched into registers while the current one is expanded
@@ -1097,85 +1210,44 @@ __global__ void __launch_bounds__(kChildWarps * 32) expand_children_kernel(const
     };
     TileRegs cur = fetch(warp * 32);
     for (size_t tile = warp * 32; tile < a.n; tile += n_warps * 32) {
-        uint4 meta = make_uint4(0u, 0u, 0u, 0u);
-        {
-            const uint4 s01 = cur.s01, s23 = cur.s23;
-            const u32 cc4 = cur.cc4;
-            s_rec[w][lane][0] = make_uint4(s01.x, s01.y, fast::nz8(s01.x, 1u), fast::nz8(s01.y, 1u));
-            s_rec[w][lane][1] = make_uint4(s01.z, s01.w, fast::nz8(s01.z, 1u), fast::nz8(s01.w, 1u));
-            s_rec[w][lane][2] = make_uint4(s23.x, s23.y, fast::nz8(s23.x, 1u), fast::nz8(s23.y, 1u));
-            s_rec[w][lane][3] = make_uint4(s23.z, s23.w, fast::nz8(s23.z, 1u), fast::nz8(s23.w, 1u));
-            // pairs (= empty cells) in front of each action's segment, one byte per action
-            const u32 h = (cc4 >> 1) & 0x7F7F7F7Fu;
-            const u32 first4 = (h << 8) + (h << 16) + (h << 24);
-            meta = make_uint4(cc4, first4, (u32)cur.off, (u32)(cur.off >> 32));
-        }
+        expand_record(s_tile[w], lane, cur.s01, cur.s23, cur.cc4, cur.off);
         cur = fetch(tile + n_warps * 32);  // in flight during the expansion below
-        s_meta[w][lane] = meta;
         __syncwarp();
-        const u32 n_here = (u32)min((size_t)32, a.n - tile);
-        for (u32 k = 0; k < n_here; ++k) {
-            const uint4 mt = s_meta[w][k];  // warp-uniform
-            const u32 cc4 = mt.x;
-            // dense layout: every one of the board's 128 slots is written (children, then zeros), so
-            // the output needs no memset and DRAM sees full lines instead of partial 256-byte slots
-            if (kLayout == G2048_CHILDREN_COMPACT && cc4 == 0u) continue;
-            u64* const board_dst = a.children + (((unsigned long long)mt.w << 32) | mt.z);
-            if (((cc4 & 0x01010101u) | (kLayout == G2048_CHILDREN_COMPACT ? (mt.z & 1u) : 0u)) == 0u) {
-                // even counts, 16-byte aligned destination: the common case
-                const uint4 rec = s_rec[w][k][act];
-                const u32 q = fast::prmt(cc4, 0u, byte_sel) >> 1;  // empty cells of my action
-                const u32 slot0 = (kLayout == G2048_CHILDREN_COMPACT) ? 2u * fast::prmt(mt.y, 0u, byte_sel) : 32u * act;
-                const u32 tiles_lo = __popc(rec.z);
-                const bool second = ((cc4 + 0x6F6F6F6Fu) & 0x80808080u) != 0u;  // some count > 16
-#pragma unroll
-                for (u32 pass = 0; pass < 2u; ++pass) {
-                    if (kLayout == G2048_CHILDREN_COMPACT && pass == 1u && !second) break;  // warp-uniform
-                    const u32 rank = r0 + 8u * pass;
-                    if (kLayout == G2048_CHILDREN_DENSE && rank >= q) {
-                        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(
-                                         board_dst + slot0 + 2u * rank), "r"(0u)
-                                     : "memory");
-                    } else if (rank < q) {
-                        bool in_hi;
-                        const u32 bit3 = fast::spawn_marker(rec.z, rec.w, tiles_lo, rank, 1u, in_hi);
-                        const u32 t = bit3 >> 3;             // exponent 1 (tile 2) in the target nibble
-                        const u32 tl = in_hi ? 0u : t, th = in_hi ? t : 0u;
-                        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(
-                                         board_dst + slot0 + 2u * rank),
-                                     "r"(rec.x + tl), "r"(rec.y + th), "r"(rec.x + 2u * tl), "r"(rec.y + 2u * th)
-                                     : "memory");
-                    }
-                }
-            } else {
-              if (kLayout == G2048_CHILDREN_DENSE) {  // zero the board's slots first
-                  asm volatile("st.global.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(board_dst + 2u * lane), "r"(0u) : "memory");
-                  asm volatile("st.global.v4.u32 [%0], {%1,%1,%1,%1};" ::"l"(board_dst + 64u + 2u * lane), "r"(0u) : "memory");
-                  __syncwarp();
-              }
-              if (lane < 4u) {
-                // Odd counts or an odd caller-supplied offset: one lane per action, serially.  A
-                // count of 1 (an afterstate without an empty cell) cannot follow a move; the exact
-                // path keeps the reference's convention (gameboard.py:158-159) for completeness.
-                const u32 cc = (cc4 >> (8u * lane)) & 0xFFu;
-                u32 before = 0;
-                for (u32 q = 0; q < lane; ++q) before += (cc4 >> (8u * q)) & 0xFFu;
-                u64* dst = board_dst + ((kLayout == G2048_CHILDREN_COMPACT) ? before : 32u * lane);
-                const uint4 rec = s_rec[w][k][lane];
-                const u64 st = ((u64)rec.y << 32) | rec.x;
-                if (cc == 1u) {
-                    *dst = st;
-                } else {
-                    u32 q = 0;
-                    for (u32 cell = 0; cell < 16u && q < cc; ++cell) {
-                        if ((st >> (4u * cell)) & 0xFull) continue;
-                        dst[q++] = st | (1ull << (4u * cell));
-                        dst[q++] = st | (2ull << (4u * cell));
-                    }
-                }
-              }
-            }
+        expand_children_tile<kLayout>(a, s_tile[w], (u32)min((size_t)32, a.n - tile), lane);
+        __syncwarp();
+    }
+}
+
+// Small batches: moves and children in ONE kernel (lane = board for the four moves through the
+// L2-resident hashed table, then the warp expands its 32 boards from shared memory).  Saves the
+// second launch and the trip of the records through global memory; large batches keep the two
+// kernels, because there the persistent moves kernel with the staged table is the faster half.
+constexpr int kFusedWarps = 2;  // small CTAs spread the 2048 warp-tiles of a 65536-board batch evenly over 148 SMs (1, 2, 4, 8 warps measure alike)
+
+template <int kLayout>
+__global__ void __launch_bounds__(kFusedWarps * 32) expand_fused_kernel(const ExpandArgs a) {
+    __shared__ ChildTile s_tile[kFusedWarps];
+    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const GlobalLut lut{a.table_hashed};
+    for (size_t tile = warp * 32; tile < a.n; tile += n_warps * 32) {
+        const size_t mine = tile + lane;
+        uint4 s01 = make_uint4(0u, 0u, 0u, 0u), s23 = s01;
+        u32 cc4 = 0u;
+        unsigned long long off = 0ull;
+        if (mine < a.n) {
+            const MovesOut r = expand_moves_compute(a, a.boards[mine], lut);
+            expand_moves_store(a, mine, r);
+            s01 = make_uint4(r.after4[0].x, r.after4[0].y, r.after4[1].x, r.after4[1].y);
+            s23 = make_uint4(r.after4[2].x, r.after4[2].y, r.after4[3].x, r.after4[3].y);
+            cc4 = r.cc4;
+            off = (kLayout == G2048_CHILDREN_COMPACT) ? (unsigned long long)a.child_offsets[mine]
+                                                      : (unsigned long long)mine * 128ull;
         }
+        expand_record(s_tile[w], lane, s01, s23, cc4, off);
+        __syncwarp();
+        expand_children_tile<kLayout>(a, s_tile[w], (u32)min((size_t)32, a.n - tile), lane);
         __syncwarp();
     }
 }
@@ -1216,6 +1288,19 @@ extern "C" int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* re
     int rc = current_state(&s);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    if (child_layout != G2048_CHILDREN_NONE && n < kExpandSmemMinBoards) {
+        // small batch: one fused kernel, the records never leave the SM (no scratch either)
+        const ExpandArgs a{reinterpret_cast<const u64*>(boards), reinterpret_cast<u64*>(after), rewards, mask,
+                           num_empty, child_count, reinterpret_cast<u64*>(children), child_offsets,
+                           child_layout, n, s->table, s->table_hashed, 1u};
+        const int grid = grid_for(n, kFusedWarps * 32, s->sms, 32 / kFusedWarps);
+        if (child_layout == G2048_CHILDREN_COMPACT)
+            expand_fused_kernel<G2048_CHILDREN_COMPACT><<<grid, kFusedWarps * 32, 0, st>>>(a);
+        else
+            expand_fused_kernel<G2048_CHILDREN_DENSE><<<grid, kFusedWarps * 32, 0, st>>>(a);
+        CU(cudaGetLastError());
+        return G2048_OK;
+    }
     // the children kernel reads the afterstates and counts back: stream-ordered scratch when the
     // caller does not want them
     void* scratch = nullptr;
