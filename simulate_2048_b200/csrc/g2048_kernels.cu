@@ -454,9 +454,10 @@ __device__ __forceinline__ void compute_store_tiles(const TileBuf<kPhilox, kGrou
                             c.flags + off + 4 * j);
 }
 
-// Persistent CTA (one per SM).  Each CTA owns a CONTIGUOUS range of tiles so that the next tile
-// of every stream is a compile-time offset away; the loop is unrolled by two tiles that ping-pong
-// between two register buffers (the loads of one tile are in flight while the other computes).
+// Persistent CTA (one per SM).  Each CTA owns a CONTIGUOUS range of warp-tiles so that the next
+// tile of every stream is a compile-time offset away; the loop is unrolled by two tiles that
+// ping-pong between two register buffers (the loads of one tile are in flight while the other
+// computes).
 template <bool kPhilox, int kThreads, int kGroups>
 __global__ void __launch_bounds__(kThreads, 1) step_lut_kernel(const StepArgs a) {
     u32* smem_tab = smem_words;
@@ -469,12 +470,19 @@ __global__ void __launch_bounds__(kThreads, 1) step_lut_kernel(const StepArgs a)
     if (threadIdx.x < 32)
         reinterpret_cast<u32*>(s_orient)[threadIdx.x] = reinterpret_cast<const u32*>(c_orient)[threadIdx.x];
 
-    const size_t full_tiles = a.n / kTile;
-    const size_t t_begin = full_tiles * blockIdx.x / gridDim.x;
-    const size_t t_end = full_tiles * (blockIdx.x + 1) / gridDim.x;
-    const size_t tiles = t_end - t_begin;
+    // Work is split in units of one WARP-tile (32 x kPerThread consecutive envs, so that every warp
+    // access stays aligned to whole 128-byte lines): CTA b owns the contiguous units
+    // [w_begin, w_end), warp w takes units w_begin + w, + kWarps, ...  The CTAs' shares then differ
+    // by at most one warp-tile (a split in whole CTA-tiles leaves 2 or 3 tiles per CTA at 2^20
+    // boards: 16 % of that launch); only the last trip of a CTA is partly filled.
+    constexpr size_t kWarps = kThreads / 32, kWarpEnvs = 32 * kPerThread;
+    const size_t wunits = a.n / kWarpEnvs;
+    const size_t w_begin = wunits * blockIdx.x / gridDim.x;
+    const size_t w_end = wunits * (blockIdx.x + 1) / gridDim.x;
+    const size_t mine = w_end - w_begin, wi = threadIdx.x >> 5;
+    const size_t tiles = mine > wi ? (mine - wi + kWarps - 1) / kWarps : 0;  // trips of this warp
     StepCursor c{a.boards_in, a.actions, a.spawns, a.boards_out, a.rewards, a.flags, a.env_offset};
-    c.advance(t_begin * kTile + threadIdx.x * kPerThread);
+    c.advance((w_begin + wi) * kWarpEnvs + (threadIdx.x & 31u) * kPerThread);
 
     // Programmatic dependent launch: everything above (table staging, orientation words, cursor
     // set-up) reads nothing an earlier kernel of the stream wrote, so it may run while that kernel
@@ -493,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, 1) step_lut_kernel(const StepArgs a)
     // Bounds are compares of the LOW WORD of the board cursor against precomputed ends (one ISETP
     // each; a 64-bit pointer compare is four instructions, and a 32-bit trip counter makes ptxas
     // build a jump table (BRX) for the three tests, which costs 12 %).  A CTA's range is far below
-    // 4 GiB and the cursor only moves in whole tiles, so equality of the low words is exact.
+    // 4 GiB and a warp's cursor only moves in whole tiles, so equality of the low words is exact.
     constexpr u32 kTileBytes = (u32)(kTile * sizeof(u64));
     const u32 end0 = (u32)reinterpret_cast<uintptr_t>(c.boards_in + tiles * kTile);
     const u32 end1 = end0 - kTileBytes, end2 = end0 - 2u * kTileBytes;
@@ -509,8 +517,8 @@ __global__ void __launch_bounds__(kThreads, 1) step_lut_kernel(const StepArgs a)
     }
 #undef G2048_CUR
 
-    // ragged tail (< one tile): spread over the CTAs, one env per thread through the exact path
-    for (size_t i = full_tiles * kTile + blockIdx.x * (size_t)kThreads + threadIdx.x; i < a.n;
+    // ragged tail (< one warp-tile): one env per thread through the exact path
+    for (size_t i = wunits * kWarpEnvs + blockIdx.x * (size_t)kThreads + threadIdx.x; i < a.n;
          i += (size_t)gridDim.x * kThreads) {
         const uint4 r = transition_slow<kPhilox>(a.boards_in[i], a.actions[i], kPhilox ? 0u : a.spawns[i],
                                                  a.seed, a.env_offset + i, a.step_base, a.table);
