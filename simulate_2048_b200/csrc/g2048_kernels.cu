@@ -602,8 +602,9 @@ extern "C" int g2048_step(const uint64_t* boards_in, const uint8_t* actions, con
     if (use_lut) {
         const int smem = (int)kStepSmemBytes;
         const int threads = g_step_threads ? g_step_threads : (spawns ? 640 : 512), groups = g_step_groups;
-        const size_t tiles = n / ((size_t)threads * 4 * groups);
-        const int grid = (int)(tiles < (size_t)s->sms ? (tiles ? tiles : 1) : (size_t)s->sms);
+        // one CTA per SM as soon as there is a warp-tile for each (the kernel splits in warp-tiles)
+        const size_t wunits = n / ((size_t)128 * groups);
+        const int grid = (int)(wunits < (size_t)s->sms ? (wunits ? wunits : 1) : (size_t)s->sms);
         // launched with the programmatic-serialization attribute: back-to-back step launches
         // overlap the next launch's latency and table staging with this launch's tail
         cudaLaunchAttribute pdl[1];
