@@ -743,9 +743,20 @@ extern "C" int g2048_env_step(uint64_t* boards, int32_t* step_count, uint8_t* do
 // ---------------------------------------------------------------------------------------------
 // mask / observe / pack / unpack / reset
 // ---------------------------------------------------------------------------------------------
+// four consecutive boards per thread: one 256-bit load and one 32-bit store, enough bytes in
+// flight per thread to cover the HBM latency (one board per thread reached 26 % of the peak)
 __global__ void __launch_bounds__(256) mask_kernel(const u64* __restrict__ boards,
-                                                   uint8_t* __restrict__ flags, size_t n) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+                                                   uint8_t* __restrict__ flags, size_t n, bool vec) {
+    const size_t quads = vec ? n / 4 : 0;
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < quads;
+         q += (size_t)gridDim.x * blockDim.x) {
+        const Boards4 b = ld_boards4(boards + 4 * q);
+        u32 f = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f |= board_flags(legal_mask(split(b.b[k]))) << (8 * k);
+        st_u32_stream(flags + 4 * q, f);
+    }
+    for (size_t i = quads * 4 + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
          i += (size_t)gridDim.x * blockDim.x)
         flags[i] = (uint8_t)board_flags(legal_mask(split(boards[i])));
 }
@@ -756,20 +767,45 @@ extern "C" int g2048_mask(const uint64_t* boards, uint8_t* flags, size_t n, void
     DeviceState* s;
     int rc = current_state(&s);
     if (rc) return rc;
-    mask_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const u64*>(boards), flags, n);
+    mask_kernel<<<grid_for((n + 3) / 4, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const u64*>(boards), flags, n, aligned(boards, 32) && aligned(flags, 4));
     CU(cudaGetLastError());
     return G2048_OK;
+}
+
+// Warp-cooperative 16-values-per-board writers (observe, unpack).  A warp takes 32 boards = 2 KiB
+// of output; lane l writes the 16-byte chunks l, l + 32, l + 64, l + 96 of it, i.e. row (q & 3) of
+// board (q >> 2) for chunk q, so every store instruction covers 512 contiguous bytes.  (One board
+// per thread writes 64 bytes at a 64-byte stride per lane: 14-40 % of the HBM peak.)  The board of a
+// chunk is re-read through L1 (8 distinct boards per load instruction).
+template <class Op>
+__device__ __forceinline__ void rows_of_tile(const u64* __restrict__ boards, size_t base, size_t n, u32 lane,
+                                             const Op& op) {
+#pragma unroll
+    for (u32 j = 0; j < 4; ++j) {
+        const u32 q = lane + 32u * j;
+        const size_t i = base + (q >> 2);
+        if (i < n) {
+            const u64 b = __ldg(boards + i);
+            op(base * 4 + q, (u32)(b >> (16u * (q & 3u))) & 0xFFFFu);   // chunk index, row nibbles
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) observe_kernel(const u64* __restrict__ boards,
                                                       float* __restrict__ obs,
                                                       uint8_t* __restrict__ max_exp, size_t n) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const Board b = split(boards[i]);
-        if (obs) write_obs(obs, i, b);
-        if (max_exp) max_exp[i] = (uint8_t)max_exponent(b);
+    const u32 lane = threadIdx.x & 31u;
+    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t base = warp * 32; base < n; base += n_warps * 32) {
+        if (obs)  // core.py:371-375: log2(tile)/16 = exponent * 0.0625f, exact in f32
+            rows_of_tile(boards, base, n, lane, [&](size_t chunk, u32 row) {
+                reinterpret_cast<float4*>(obs)[chunk] =
+                    make_float4((float)(row & 0xFu) * 0.0625f, (float)((row >> 4) & 0xFu) * 0.0625f,
+                                (float)((row >> 8) & 0xFu) * 0.0625f, (float)(row >> 12) * 0.0625f);
+            });
+        if (max_exp && base + lane < n) max_exp[base + lane] = (uint8_t)max_exponent(split(__ldg(boards + base + lane)));
     }
 }
 
@@ -786,9 +822,38 @@ extern "C" int g2048_observe(const uint64_t* boards, float* obs, uint8_t* max_ex
     return G2048_OK;
 }
 
-// one thread per (board, cell): `width` bytes with a single 1 (binary.py:47-49 eye(width)[log2])
+// One thread per 16 OUTPUT bytes (one 128-bit store): the bytes [16 g, 16 g + 16) of the flat
+// u8[n * 16 * width] array belong to at most two cells (width >= 16), each of which contributes a
+// single 1 at offset log2(tile) (binary.py:47-49 eye(width)[log2]).  (One thread per cell writing
+// `width` single bytes reached 2.5 % of the HBM peak.)
+template <int kWidth>   // 0 = run-time width
 __global__ void __launch_bounds__(256) onehot_kernel(const u64* __restrict__ boards,
-                                                     uint8_t* __restrict__ out, int width, size_t n) {
+                                                     uint8_t* __restrict__ out, int width_rt, size_t n) {
+    const u32 width = kWidth ? (u32)kWidth : (u32)width_rt;
+    const size_t groups = n * width;   // n * 16 * width / 16
+    for (size_t g = blockIdx.x * (size_t)blockDim.x + threadIdx.x; g < groups;
+         g += (size_t)gridDim.x * blockDim.x) {
+        const size_t first = g * 16;
+        const size_t cell = first / width;
+        const u32 k0 = (u32)(first - cell * width);   // position of byte 0 inside its cell
+        const u32 e0 = (u32)(__ldg(boards + (cell >> 4)) >> (4 * (cell & 15))) & 0xFu;
+        u32 w[4] = {0u, 0u, 0u, 0u};
+        const u32 p0 = e0 - k0;                        // byte of this group that holds cell's 1
+        if (p0 < 16u) w[p0 >> 2] |= 1u << (8u * (p0 & 3u));
+        const u32 rest = width - k0;                   // bytes of `cell` in this group (>= 1)
+        if (rest < 16u && cell + 1 < n * 16) {         // the group runs into the next cell
+            const size_t c1 = cell + 1;
+            const u32 e1 = (u32)(__ldg(boards + (c1 >> 4)) >> (4 * (c1 & 15))) & 0xFu;
+            const u32 p1 = rest + e1;
+            if (p1 < 16u) w[p1 >> 2] |= 1u << (8u * (p1 & 3u));
+        }
+        st_int4_stream(out + first, make_int4((int)w[0], (int)w[1], (int)w[2], (int)w[3]));
+    }
+}
+
+// fallback for an output that is not 16-byte aligned: one thread per (board, cell)
+__global__ void __launch_bounds__(256) onehot_bytes_kernel(const u64* __restrict__ boards,
+                                                           uint8_t* __restrict__ out, int width, size_t n) {
     const size_t total = n * 16;
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total;
          t += (size_t)gridDim.x * blockDim.x) {
@@ -805,45 +870,83 @@ extern "C" int g2048_observe_onehot(const uint64_t* boards, uint8_t* out, int wi
     DeviceState* s;
     int rc = current_state(&s);
     if (rc) return rc;
-    onehot_kernel<<<grid_for(n * 16, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const u64*>(boards), out, width, n);
+    const u64* b = reinterpret_cast<const u64*>(boards);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!aligned(out, 16))
+        onehot_bytes_kernel<<<grid_for(n * 16, 256, s->sms, 8), 256, 0, st>>>(b, out, width, n);
+    else if (width == 31)   // the reference's encodage_size (envs/twentyfortyeight.py:66): division by a constant
+        onehot_kernel<31><<<grid_for(n * 31, 256, s->sms, 8), 256, 0, st>>>(b, out, width, n);
+    else
+        onehot_kernel<0><<<grid_for(n * (size_t)width, 256, s->sms, 8), 256, 0, st>>>(b, out, width, n);
     CU(cudaGetLastError());
     return G2048_OK;
 }
 
+// tile value -> exponent; *bad is set for a value that is not 0 or a power of two in [2, 32768]
+__device__ __forceinline__ u32 tile_exponent(int32_t t, bool& bad) {
+    if (t == 0) return 0u;
+    if (t < 2 || t > 32768 || (t & (t - 1)) != 0) {
+        bad = true;
+        return 0u;
+    }
+    return 31u - __clz(t);
+}
+
+// Warp-cooperative: lane l reads the 16-byte chunks l, l + 32, ... of the warp's 2 KiB of tiles
+// (coalesced LDG.128), packs its row, and the four lanes of a board OR their rows together.
 __global__ void __launch_bounds__(256) pack_kernel(const int32_t* __restrict__ tiles,
                                                    u64* __restrict__ boards,
-                                                   int32_t* __restrict__ status, size_t n) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
-         i += (size_t)gridDim.x * blockDim.x) {
-        u64 b = 0;
-        bool bad = false;
+                                                   int32_t* __restrict__ status, size_t n, bool vec) {
+    const u32 lane = threadIdx.x & 31u;
+    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    bool bad = false;
+    for (size_t base = warp * 32; base < n; base += n_warps * 32) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            const int32_t t = tiles[i * 16 + c];
-            u32 e = 0;
-            if (t != 0) {
-                if (t < 2 || t > 32768 || (t & (t - 1)) != 0) bad = true;
-                else e = 31u - __clz(t);
+        for (u32 j = 0; j < 4; ++j) {
+            const u32 q = lane + 32u * j;
+            const size_t i = base + (q >> 2);
+            u32 lo = 0, hi = 0;
+            if (i < n) {
+                int4 t;
+                if (vec) {
+                    t = __ldg(reinterpret_cast<const int4*>(tiles) + base * 4 + q);
+                } else {
+                    const int32_t* p = tiles + (base * 4 + q) * 4;
+                    t = make_int4(p[0], p[1], p[2], p[3]);
+                }
+                const u32 row = tile_exponent(t.x, bad) | (tile_exponent(t.y, bad) << 4) |
+                                (tile_exponent(t.z, bad) << 8) | (tile_exponent(t.w, bad) << 12);
+                const u32 r = q & 3u;
+                lo = (r < 2u) ? row << (16u * r) : 0u;
+                hi = (r < 2u) ? 0u : row << (16u * (r - 2u));
             }
-            b |= (u64)e << (4 * c);
+            lo |= __shfl_xor_sync(0xFFFFFFFFu, lo, 1);
+            hi |= __shfl_xor_sync(0xFFFFFFFFu, hi, 1);
+            lo |= __shfl_xor_sync(0xFFFFFFFFu, lo, 2);
+            hi |= __shfl_xor_sync(0xFFFFFFFFu, hi, 2);
+            if (i < n && (q & 3u) == 0u) boards[i] = ((u64)hi << 32) | lo;
         }
-        boards[i] = b;
-        if (bad && status) *status = G2048_ERANGE;
     }
+    if (bad && status) *status = G2048_ERANGE;
 }
 
 __global__ void __launch_bounds__(256) unpack_kernel(const u64* __restrict__ boards,
-                                                     int32_t* __restrict__ tiles, size_t n) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const u64 b = boards[i];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            const u32 e = (u32)(b >> (4 * c)) & 0xFu;
-            tiles[i * 16 + c] = e ? (1 << e) : 0;
-        }
-    }
+                                                     int32_t* __restrict__ tiles, size_t n, bool vec) {
+    const u32 lane = threadIdx.x & 31u;
+    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t base = warp * 32; base < n; base += n_warps * 32)
+        rows_of_tile(boards, base, n, lane, [&](size_t chunk, u32 row) {
+            const u32 e0 = row & 0xFu, e1 = (row >> 4) & 0xFu, e2 = (row >> 8) & 0xFu, e3 = row >> 12;
+            const int4 v = make_int4(e0 ? 1 << e0 : 0, e1 ? 1 << e1 : 0, e2 ? 1 << e2 : 0, e3 ? 1 << e3 : 0);
+            if (vec) {
+                st_int4_stream(reinterpret_cast<int4*>(tiles) + chunk, v);
+            } else {
+                int32_t* p = tiles + chunk * 4;
+                p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
+            }
+        });
 }
 
 extern "C" int g2048_pack(const int32_t* tiles, uint64_t* boards, int32_t* status, size_t n,
@@ -854,7 +957,7 @@ extern "C" int g2048_pack(const int32_t* tiles, uint64_t* boards, int32_t* statu
     int rc = current_state(&s);
     if (rc) return rc;
     pack_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
-        tiles, reinterpret_cast<u64*>(boards), status, n);
+        tiles, reinterpret_cast<u64*>(boards), status, n, aligned(tiles, 16));
     CU(cudaGetLastError());
     return G2048_OK;
 }
@@ -866,7 +969,7 @@ extern "C" int g2048_unpack(const uint64_t* boards, int32_t* tiles, size_t n, vo
     int rc = current_state(&s);
     if (rc) return rc;
     unpack_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const u64*>(boards), tiles, n);
+        reinterpret_cast<const u64*>(boards), tiles, n, aligned(tiles, 16));
     CU(cudaGetLastError());
     return G2048_OK;
 }
