@@ -370,6 +370,57 @@ def test_reset_spawn_observe_pack_vs_oracle(T, ops, oracle, golden):
         ops.pack(dev(T, bad))
 
 
+def test_supporting_kernels_ragged_and_unaligned(T, ops, oracle):
+    """The wide-access kernels (mask, observe, one-hot, pack, unpack) on batch sizes that are not
+    multiples of their 4-board / 32-board tiles, and through pointers that only have the natural
+    alignment of their element type (scalar fall-backs of g2048_mask / pack / unpack / one-hot)."""
+    from simulate_2048_b200 import _cabi
+    lib = ops.lib()
+    for n in (1, 3, 31, 33, 127, 4099):
+        boards = synthetic_packed(n + 1, seed=100 + n)
+        boards[0] = 0xFEDCBA9876543210
+        d = dev(T, boards)
+        want_t = oracle.unpack(boards)
+        want_f = oracle.mask(boards) if hasattr(oracle, 'mask') else None
+        o_obs, o_mx = oracle.observe(boards)
+        for off in (0, 1):      # off = 1: boards pointer 8-byte aligned only
+            v = d[off:]
+            m = v.numel()
+            obs, mx = ops.observe(v.contiguous())
+            np.testing.assert_array_equal(obs.cpu().numpy(), o_obs[off:])
+            np.testing.assert_array_equal(mx.cpu().numpy(), o_mx[off:])
+            flags = T.full((m + 8,), 0xEE, dtype=T.uint8, device='cuda')
+            fv = flags[1 + off:1 + off + m]          # flags pointer 1-byte aligned
+            assert lib.g2048_mask(v.data_ptr(), fv.data_ptr(), m, None) == 0
+            ref = ops.legal_flags(v.contiguous())
+            T.cuda.synchronize()
+            np.testing.assert_array_equal(fv.cpu().numpy(), ref.cpu().numpy())
+            assert int(flags[off].item()) == 0xEE and int(flags[1 + off + m].item()) == 0xEE
+            if want_f is not None:
+                np.testing.assert_array_equal(ref.cpu().numpy(), want_f[off:])
+            tiles = T.full((m * 16 + 8,), -7, dtype=T.int32, device='cuda')
+            tv = tiles[1:1 + m * 16]                 # tiles pointer 4-byte aligned only
+            assert lib.g2048_unpack(v.data_ptr(), tv.data_ptr(), m, None) == 0
+            T.cuda.synchronize()
+            np.testing.assert_array_equal(tv.cpu().numpy().reshape(-1, 4, 4), want_t[off:])
+            assert int(tiles[0].item()) == -7 and int(tiles[1 + m * 16].item()) == -7
+            packed = T.zeros(m, dtype=T.int64, device='cuda')
+            assert lib.g2048_pack(tv.data_ptr(), packed.data_ptr(), None, m, None) == 0
+            T.cuda.synchronize()
+            np.testing.assert_array_equal(host(packed), boards[off:])
+            np.testing.assert_array_equal(host(ops.pack(tv.clone().reshape(m, 4, 4))), boards[off:])
+            for width in (16, 31, 64):
+                oh = ops.observe_onehot(v.contiguous(), width).cpu().numpy().reshape(m, 16, width)
+                exps = np.log2(np.maximum(want_t[off:].reshape(m, 16), 1)).astype(np.int64)
+                np.testing.assert_array_equal(oh, np.eye(width, dtype=np.uint8)[exps])
+                raw = T.full((m * 16 * width + 32,), 9, dtype=T.uint8, device='cuda')
+                rv = raw[3:3 + m * 16 * width]       # 1-byte aligned output: byte kernel
+                assert lib.g2048_observe_onehot(v.data_ptr(), rv.data_ptr(), width, m, None) == 0
+                T.cuda.synchronize()
+                np.testing.assert_array_equal(rv.cpu().numpy().reshape(m, 16, width), oh)
+                assert int(raw[2].item()) == 9 and int(raw[3 + m * 16 * width].item()) == 9
+
+
 def test_host_buffer_step_matches_device_path(T, ops, oracle):
     """g2048_step_host (host ndarrays in and out, chunked copy/compute pipeline) == oracle."""
     n = (1 << 23) + 12345  # three chunks, the last one ragged
