@@ -3,9 +3,11 @@
 // Hot path (BASELINE.json north_star): one batched 2048 transition per env
 //   board(u64) , action(u8) [, spawn(u8)]  ->  board(u64), reward(i32), flags(u8)
 // HBM-bound by design: 22 B/env (Philox) or 23 B/env (injected spawns).  Design:
-//   * persistent grid, one 512-thread CTA per SM over a contiguous range of tiles, 4 consecutive
-//     envs per thread so every stream is one wide access per thread: 256-bit board load/store
-//     (LDG.E.256 / STG.E.256), 128-bit reward store, 32-bit action / spawn / flags;
+//   * persistent grid, one 640-thread CTA per SM (512 with Philox) over a contiguous range of
+//     warp-tiles, 4 consecutive envs per thread so every stream is one wide access per thread:
+//     256-bit board load/store (LDG.E.256 / STG.E.256), 128-bit reward store, 32-bit action /
+//     spawn / flags; launched as a programmatic dependent, so the launch latency and table staging
+//     of launch N+1 overlap the tail of launch N;
 //   * the 57344-entry row table (224 KiB, hashed against bank conflicts) is staged into shared
 //     memory once per CTA by TMA bulk copies (cp.async.bulk, UBLKCP) that complete on an mbarrier
 //     while the first boards are already in flight; a move is then 4 LDS + 2 PRMT;
