@@ -1,4 +1,5 @@
-"""Device time and algorithmic GB/s of the supporting kernels at 2^24 boards (CUDA events, median of 7)."""
+"""Device time and algorithmic GB/s of the supporting kernels at 2^24 boards (CUDA events around five
+back-to-back calls, median of 7 samples)."""
 import statistics
 import sys
 
@@ -19,13 +20,15 @@ def timed(name, fn, bytes_per_board):
     fn()
     torch.cuda.synchronize()
     ms = []
-    for _ in range(7):
+    for _ in range(7):   # 6 back-to-back calls per sample: the queue stays full, host overhead drops out
         e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-        e[0].record()
         fn()
+        e[0].record()
+        for _ in range(5):
+            fn()
         e[1].record()
         torch.cuda.synchronize()
-        ms.append(e[0].elapsed_time(e[1]))
+        ms.append(e[0].elapsed_time(e[1]) / 5)
     t = statistics.median(ms)
     print(f'{name:28s} {t * 1e3:9.1f} us  {n * bytes_per_board / t / 1e6:8.0f} GB/s algorithmic (incl. allocation of the outputs)')
 
