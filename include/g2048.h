@@ -163,7 +163,8 @@ int g2048_expand_children(const uint64_t* after, const uint8_t* child_count,
 
 /* Chance children of given boards (gameboard.py:132 after_state, :174 after_state_lazy):
  * children[n*32] dense (slot 2k + v = k-th empty cell in row-major order, v: 0 -> tile 2,
- * 1 -> tile 4; a full board yields children[0] = the board itself), num_empty[n], and
+ * 1 -> tile 4; a full board yields children[0] = the board itself; every remaining slot is
+ * written as 0, so the buffer needs no memset), num_empty[n], and
  * empty_cells[n] (optional): 16-bit mask, bit c = flat cell c is empty. */
 int g2048_after_state(const uint64_t* boards, uint64_t* children, uint8_t* num_empty,
                       uint16_t* empty_cells, size_t n, void* stream);

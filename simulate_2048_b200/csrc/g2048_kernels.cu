@@ -1473,24 +1473,63 @@ extern "C" int g2048_expand_children(const uint64_t* after, const uint8_t* child
     return launch_expand_children(a, s, (cudaStream_t)stream);
 }
 
+// Warp-cooperative: a warp takes 32 boards = 8 KiB of children; lane l serves the FIXED rank
+// l & 15 and, in pass j, board 2 j + (l >> 4) of the tile, so every store instruction writes the 32
+// slots of two boards (512 contiguous bytes).  All 32 slots of a board are written — the children,
+// then zeros — so the caller needs no memset.  (One board per thread, first 2 E slots only, over a
+// zero-filled buffer reached 20 % of the HBM peak.)
 __global__ void __launch_bounds__(256) after_state_kernel(const u64* __restrict__ boards,
                                                           u64* __restrict__ children,
                                                           uint8_t* __restrict__ num_empty,
                                                           uint16_t* __restrict__ empty_cells, size_t n) {
+    const u32 lane = threadIdx.x & 31u, k = lane & 15u;
+    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t base = warp * 32; base < n; base += n_warps * 32) {
+        if ((num_empty || empty_cells) && base + lane < n) {
+            const u32 e = empty_cells16(split(__ldg(boards + base + lane)));
+            if (num_empty) num_empty[base + lane] = (uint8_t)__popc(e);
+            if (empty_cells) empty_cells[base + lane] = (uint16_t)e;
+        }
+        if (!children) continue;
+#pragma unroll 4
+        for (u32 j = 0; j < 16; ++j) {
+            const size_t bi = base + 2u * j + (lane >> 4);
+            if (bi >= n) continue;
+            const u64 p = __ldg(boards + bi);
+            const u32 lo = (u32)p, hi = (u32)(p >> 32);
+            const u32 nlo = fast::nz8(lo, 1u), nhi = fast::nz8(hi, 1u);
+            const u32 tiles_lo = __popc(nlo), ne = 16u - tiles_lo - __popc(nhi);
+            int4 v = make_int4(0, 0, 0, 0);
+            if (k < ne) {
+                bool in_hi;
+                const u32 t = fast::spawn_marker(nlo, nhi, tiles_lo, k, 1u, in_hi) >> 3;  // exponent 1 in the k-th empty cell
+                const u32 tl = in_hi ? 0u : t, th = in_hi ? t : 0u;
+                v = make_int4((int)(lo + tl), (int)(hi + th), (int)(lo + 2u * tl), (int)(hi + 2u * th));  // tile 2, then tile 4 (gameboard.py:162)
+            } else if (ne == 0u && k == 0u) {
+                v = make_int4((int)lo, (int)hi, 0, 0);  // gameboard.py:158-159: a full board is its own child
+            }
+            st_int4_stream(children + bi * 32 + 2u * k, v);
+        }
+    }
+}
+
+// children pointer with 8-byte alignment only: one board per thread, every slot written
+__global__ void __launch_bounds__(256) after_state_scalar_kernel(const u64* __restrict__ boards,
+                                                                 u64* __restrict__ children, size_t n) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
          i += (size_t)gridDim.x * blockDim.x) {
         const u64 p = boards[i];
         u32 e = empty_cells16(split(p));
-        if (num_empty) num_empty[i] = (uint8_t)__popc(e);
-        if (empty_cells) empty_cells[i] = (uint16_t)e;
-        if (!children) continue;
         u64* dst = children + i * 32;
-        if (e == 0u) dst[0] = p;  // gameboard.py:158-159
-        for (u32 k = 0; e; ++k, e &= e - 1u) {
+        u32 k = 0;
+        if (e == 0u) dst[k++] = p;  // gameboard.py:158-159
+        for (; e; e &= e - 1u) {
             const u32 cell = __ffs(e) - 1u;
-            dst[2 * k] = p | (1ull << (4 * cell));      // tile 2 first (gameboard.py:162)
-            dst[2 * k + 1] = p | (2ull << (4 * cell));  // then tile 4
+            dst[k++] = p | (1ull << (4 * cell));  // tile 2 first (gameboard.py:162)
+            dst[k++] = p | (2ull << (4 * cell));  // then tile 4
         }
+        for (; k < 32u; ++k) dst[k] = 0ull;
     }
 }
 
@@ -1501,9 +1540,19 @@ extern "C" int g2048_after_state(const uint64_t* boards, uint64_t* children, uin
     DeviceState* s;
     int rc = current_state(&s);
     if (rc) return rc;
-    after_state_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const u64*>(boards), reinterpret_cast<u64*>(children), num_empty,
-        empty_cells, n);
+    const u64* b = reinterpret_cast<const u64*>(boards);
+    u64* ch = reinterpret_cast<u64*>(children);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for(n, 256, s->sms, 8);
+    if (ch && !aligned(ch, 16)) {
+        after_state_scalar_kernel<<<grid, 256, 0, st>>>(b, ch, n);
+        ch = nullptr;  // the counts and masks below
+        if (!num_empty && !empty_cells) {
+            CU(cudaGetLastError());
+            return G2048_OK;
+        }
+    }
+    after_state_kernel<<<grid, 256, 0, st>>>(b, ch, num_empty, empty_cells, n);
     CU(cudaGetLastError());
     return G2048_OK;
 }

@@ -207,7 +207,7 @@ def after_state(boards: torch.Tensor, want_children: bool = True):
     _req(boards, torch.int64, 'boards')
     n = boards.numel()
     dev = boards.device
-    ch = torch.zeros((n, 16, 2), dtype=torch.int64, device=dev) if want_children else None
+    ch = torch.empty((n, 16, 2), dtype=torch.int64, device=dev) if want_children else None  # every slot is written
     ne = torch.empty(n, dtype=torch.uint8, device=dev)
     ec = torch.empty(n, dtype=torch.int16, device=dev)
     with torch.cuda.device(dev):

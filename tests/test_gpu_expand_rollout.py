@@ -171,6 +171,18 @@ def test_after_state_vs_oracle(T, ops, oracle):
     np.testing.assert_array_equal(host(ch).reshape(-1, 32), o_ch)
     np.testing.assert_array_equal(ne.cpu().numpy(), o_ne)
     np.testing.assert_array_equal(ec.cpu().numpy().view(np.uint16), o_ec)
+    # every slot is written (no memset needed), also for ragged sizes and a children pointer that is
+    # only 8-byte aligned (scalar kernel); nothing outside the n * 32 slots is touched
+    lib = ops.lib()
+    for n in (1, 17, 33, 4001):
+        d = dev(T, boards[:n])
+        for off in (0, 1):
+            buf = T.full((n * 32 + 4,), -1, dtype=T.int64, device='cuda')
+            view = buf[2 + off:2 + off + n * 32]
+            assert lib.g2048_after_state(d.data_ptr(), view.data_ptr(), None, None, n, None) == 0
+            T.cuda.synchronize()
+            np.testing.assert_array_equal(host(view).reshape(n, 32), o_ch[:n])
+            assert int(buf[1 + off].item()) == -1 and int(buf[2 + off + n * 32].item()) == -1
 
 
 # ------------------------------------------------------------------ rollout
