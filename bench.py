@@ -435,7 +435,7 @@ def run_ours(args):
     }
 
     # ---- e2e: pinned host buffers through g2048_step_host (H2D + kernel + D2H timed) ----
-    Be = 1 << args.e2e_log2
+    Be = min(1 << args.e2e_log2, B)
     h_b = ops.pinned_empty(Be, torch.int64)
     h_a = ops.pinned_empty(Be, torch.uint8)
     h_s = ops.pinned_empty(Be, torch.uint8)
@@ -644,7 +644,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--boards-log2', type=int, default=26)
-    ap.add_argument('--e2e-log2', type=int, default=24)
+    ap.add_argument('--e2e-log2', type=int, default=26,
+                    help='boards per end-to-end step (default: the same 2^26 batch as the device-resident measurement)')
     ap.add_argument('--quick', action='store_true', help='skip the secondary measurements')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline block')
     ap.add_argument('--ncu-traffic', type=float, default=None,
