@@ -30,7 +30,7 @@
 // on the fast path every row has nibbles <= 13, so a field is <= 8192 and the sum <= 32768.
 //
 // Every primitive has a host twin so the identical dataflow is unit-tested on the CPU
-// (tests/test_fast_path_host.py builds tools/fast_host_check.cpp against the oracle).
+// (tests/test_fast_path_host.py builds tests/fast_host_check.cpp against the oracle).
 #pragma once
 #include <cstdint>
 

@@ -1,6 +1,6 @@
 // fast_host_check.cpp — CPU check of simulate_2048_b200/csrc/g2048_fast.cuh against the oracle.
 // Build & run (tests/test_fast_path_host.py does this):
-//   g++ -O2 -std=c++17 -o tools/fast_host_check tools/fast_host_check.cpp oracle/libg2048_oracle.so
+//   g++ -O2 -std=c++17 -o /tmp/fast_host_check tests/fast_host_check.cpp oracle/libg2048_oracle.so
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

@@ -9,11 +9,11 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import c_oracle  # noqa: E402
 from simulate_2048_b200 import ops  # noqa: E402
-from tools.fuzz_step import gen_boards  # noqa: E402
+from tests.soak.fuzz_step import gen_boards  # noqa: E402
 
 
 def host(t):

@@ -6,7 +6,7 @@ path, near-empty boards, mid-game boards taken from capped device rollouts), wit
 bytes drawn from the WHOLE byte range (high action bits, invalid ranks, absolute-cell spawn bytes),
 and compares boards, rewards and flags of the injected-spawn and the Philox kernel with
 oracle/g2048_oracle.c (pthreads) bit for bit.  Test infrastructure: run under gpurun, prints one
-summary line per round and a JSON total (profiles/r01_fuzz_step.json keeps the last run).
+summary line per round and a JSON total (profiles/r01_fuzz_step.json keeps the last run; lives under tests/ because it uses oracle/).
 """
 import json
 import os
@@ -16,7 +16,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import c_oracle  # noqa: E402
 from simulate_2048_b200 import ops  # noqa: E402

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_fast_transition_matches_oracle_on_host(oracle, tmp_path):
     exe = str(tmp_path / 'fast_host_check')
     so = os.path.join(ROOT, 'oracle', 'libg2048_oracle.so')
-    subprocess.check_call(['g++', '-O2', '-std=c++17', '-o', exe, os.path.join(ROOT, 'tools', 'fast_host_check.cpp'),
+    subprocess.check_call(['g++', '-O2', '-std=c++17', '-o', exe, os.path.join(ROOT, 'tests', 'fast_host_check.cpp'),
                            so, '-Wl,-rpath,' + os.path.dirname(so)])
     out = subprocess.run([exe, '400000'], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
