@@ -17,9 +17,13 @@ One JSON line on stdout (rank 0):
              H2D and D2H copies inside the timed region
   roofline   algorithmic bytes per launch / mean launch time vs the measured HBM copy peak
   cpu_baseline  the CPU oracle port timed on this box's host cores (rank 0, N = 1)
-plus secondary measurements (philox mode, 1M latency, expand, rollout, self-play loop).
-`--impl reference` times the reference's CPU algorithm (NumPy port of the engine, one Python
-call per env as the reference runs it) on all host cores and prints the same line shape.
+plus, inside `roofline.other_kernels` (a key the driver's parse keeps), the Philox-mode step and
+BASELINE configs[3] — 2^24 fused rollouts sharded over ALL ranks with the statistics collective in
+the timed region, checked against an oracle-pinned vector — and secondary measurements (1M latency,
+expand, self-play loop, ...).
+`--impl reference` times the REAL reference engine (oracle/_ref, staged by oracle/make_ref.py; one
+Python call per env as its users run it) on all host cores and prints the same line shape; the
+NumPy port is the fallback when the reference was never staged (`kind` says which).
 """
 
 from __future__ import annotations
@@ -39,6 +43,7 @@ sys.path.insert(0, ROOT)
 
 BYTES_INJECTED = 23  # read board 8 + action 1 + spawn 1; write board 8 + reward 4 + flags 1
 BYTES_PHILOX = 22
+ROLLOUT_INSTR_PER_STEP = 190.0  # thread instructions per env-step of rollout_kernel (ncu, profiles/)
 METRIC = 'env_steps_per_sec'
 UNIT = 'env-steps/s'
 
@@ -153,11 +158,27 @@ class ClockSampler:
 # CPU baselines (oracle; the only place bench.py executes oracle/)
 # --------------------------------------------------------------------------------------------
 
+def cpu_engine():
+    """('reference', oracle.ref_engine) when the real reference is staged under oracle/_ref, else
+    ('port', oracle.np_engine)."""
+    from oracle import make_ref
+    if make_ref.available():
+        from oracle import ref_engine
+        return 'reference', ref_engine
+    from oracle import np_engine
+    return 'port', np_engine
+
+
+def engine_label(kind):
+    return ('the reference engine itself (oracle/_ref/twentyfortyeight, staged by oracle/make_ref.py)' if kind == 'reference'
+            else 'NumPy port of the reference engine (oracle/np_engine.py; the reference was not staged)')
+
+
 def _np_worker(args):
     tiles, actions, seed = args
-    from oracle import np_engine
+    _, eng = cpu_engine()
     t0 = time.perf_counter()
-    np_engine.step_boards(tiles, actions, seed)
+    eng.step_boards(tiles, actions, seed)
     return time.perf_counter() - t0
 
 
@@ -179,15 +200,17 @@ def numpy_port_rate(packed: np.ndarray, actions: np.ndarray, per_worker: int, wo
 
 
 def _np_expand_worker(tiles):
-    """Config 3 on the NumPy port: mask, four afterstates + rewards, every chance child."""
-    from oracle import np_engine
+    """Config 3 on the CPU engine: mask, four afterstates + rewards, every chance child."""
+    kind, eng = cpu_engine()
+    if kind == 'reference':
+        return eng.expand_boards(tiles)
     children = 0
     for b in tiles:
-        mask = np_engine.legal_actions_mask(b)
+        mask = eng.legal_actions_mask(b)
         for a in range(4):
-            after, _ = np_engine.latent_state(b, a)
+            after, _ = eng.latent_state(b, a)
             if mask[a]:
-                children += len(np_engine.after_state(np.array(after)))
+                children += len(eng.after_state(np.array(after)))
     return children
 
 
@@ -199,19 +222,20 @@ def numpy_expand_rate(packed: np.ndarray, per_worker: int, workers: int, pool):
     kids = sum(pool.map(_np_expand_worker, [tiles[w * per_worker:(w + 1) * per_worker] for w in range(workers)]))
     dt = time.perf_counter() - t0
     return {'boards_per_sec': total / dt, 'children_per_sec': kids / dt, 'cores': workers,
+            'kind': cpu_engine()[0],
             'sample': f'{total} boards of the config-2 set: legal_actions_mask + latent_state x4 + after_state '
-                      f'of every legal afterstate through oracle/np_engine.py, {dt:.1f} s'}
+                      f'of every legal afterstate, one Python call each, {dt:.1f} s'}
 
 
 def _games_worker(args):
     first, count = args
-    from oracle import np_engine
-    return np_engine.play_random_games(first, count)
+    return cpu_engine()[1].play_random_games(first, count)[:2]
 
 
 def config1_games(cores, n_games=1024):
-    """BASELINE configs[0]: 1024 random-policy games to game-over on the NumPy engine port
-    (reset(seed=g), uniform-legal policy), one process per core."""
+    """BASELINE configs[0]: 1024 random-policy games to game-over on the reference NumPy engine
+    (TwentyFortyEight.reset(seed=g) / .step, uniform-legal policy), one
+    process per core."""
     import multiprocessing as mp
     per = (n_games + cores - 1) // cores
     jobs = [(g, min(per, n_games - g)) for g in range(0, n_games, per)]
@@ -223,7 +247,9 @@ def config1_games(cores, n_games=1024):
     score = sum(r[1] for r in res)
     return {'games': n_games, 'env_steps': steps, 'seconds': dt, 'env_steps_per_sec': steps / dt,
             'mean_length': steps / n_games, 'mean_score': score / n_games, 'cores': cores,
-            'note': 'oracle/np_engine.py play_random_games (port of TwentyFortyEight.step + legal_actions)'}
+            'kind': cpu_engine()[0],
+            'note': 'play_random_games: TwentyFortyEight.reset(seed=g) + .step with a uniform policy over '
+                    'legal_actions, ' + engine_label(cpu_engine()[0])}
 
 
 def cpu_baseline_block(packed, actions, cores):
@@ -245,11 +271,12 @@ def cpu_baseline_block(packed, actions, cores):
     c_oracle.step(packed[: n_c // 8], actions[: n_c // 8], None, seed=2048, threads=1)
     c_rate1 = (n_c // 8) / (time.perf_counter() - t0)
     cfg1 = config1_games(cores)
+    kind = cpu_engine()[0]
     return {
         'config1_numpy_engine_1024_games': cfg1,
-        'value': rate, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-        'sample': f'NumPy port of the reference engine (oracle/np_engine.py next_state, one Python call '
-                  f'per env), {per_worker} boards x {cores} processes of the config-2 set, {dt:.1f} s',
+        'value': rate, 'unit': UNIT, 'cores': cores, 'kind': kind,
+        'sample': f'{engine_label(kind)}: next_state, one Python call '
+                  f'per env, {per_worker} boards x {cores} processes of the config-2 set, {dt:.1f} s',
         'single_core_value': rate1,
         'config3_numpy_expand': cfg3,
         'jax_on_cpu': 'unavailable in this image (jax / jaxlib are not installed and there is no network); '
@@ -286,15 +313,17 @@ def run_reference(args):
         dt = time.perf_counter() - t0
     envs = per_worker * cores * args.steps
     value = envs / dt
+    kind = cpu_engine()[0]
     sample = (f'{per_worker * cores} boards per step ({per_worker} x {cores} processes) of the config-2 '
-              f'synthetic set through the NumPy port of twentyfortyeight next_state')
+              f'synthetic set, one next_state call per board on {engine_label(kind)}')
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int64',
         'data': 'synthetic',
-        'config': {'workload': 'single batched 2048 step (configs[1]) on the CPU engine; bounded sample: ' + sample},
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'config': {'workload': 'single batched 2048 step (BASELINE configs[1]) on the CPU engine; bounded sample of '
+                               'the same workload as the GPU arm (which steps 2^26 boards per step): ' + sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -319,8 +348,12 @@ def run_ours(args):
         log(f'warning: --gpus {args.gpus} but WORLD_SIZE {world}')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    host_group = None
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
+        # ranks that wait for rank 0's rank-local measurements block on the HOST (gloo), not inside
+        # a spinning NCCL kernel
+        host_group = dist.new_group(backend='gloo')
     ops.init(local)
     if os.environ.get('G2048_STEP_THREADS'):
         ops.set_tuning(int(os.environ['G2048_STEP_THREADS']), int(os.environ.get('G2048_STEP_ENVS', '4')))
@@ -406,8 +439,45 @@ def run_ours(args):
     p_total, p_mean, _ = timed(step_phx, max(args.steps // 2, 5), 3)
     clocks.__exit__(None, None, None)
     philox = {'value': world * B * max(args.steps // 2, 5) / p_total, 'unit': UNIT,
-              'achieved_gbs': BYTES_PHILOX * B / p_mean / 1e9,
-              'frac': BYTES_PHILOX * B / p_mean / 1e9 / peak}
+              'bytes_per_env_step': BYTES_PHILOX, 'achieved_gbs': BYTES_PHILOX * B / p_mean / 1e9,
+              'frac': BYTES_PHILOX * B / p_mean / 1e9 / peak, 'mean_launch_ms': p_mean * 1e3,
+              'kernel': 'step_lut_kernel<true, 512, 1>',
+              'stream': 'Philox4x32-10, one block per env quad (include/g2048.h "Philox mode")'}
+
+    # ---- BASELINE configs[3]: fused rollouts to termination, 2^24 envs in total sharded over ALL
+    # ranks (strong scaling), the statistics collective inside the timed region, checked against the
+    # oracle-pinned vector of tests/golden/rollout_stats.json ----
+    from simulate_2048_b200 import parallel
+    n_roll = 1 << args.rollout_log2
+    ROLL_SEED = 2048
+
+    def sharded():
+        return parallel.sharded_rollout(n_roll, seed=ROLL_SEED, rank=rank, world=world, device=dev)
+    _, r_stats = sharded()
+    try:
+        with open(os.path.join(ROOT, 'tests', 'golden', 'rollout_stats.json')) as f:
+            want_stats = json.load(f)['stats'].get(str(n_roll))
+    except Exception:
+        want_stats = None
+    got_stats = [int(x) & (2**64 - 1) for x in r_stats.vector]
+    ro_total, ro_mean, ro_best = timed(sharded, 3, 1)
+    rollout = {
+        'envs_total': n_roll, 'envs_per_gpu': n_roll // world, 'scaling': 'strong', 'seed': ROLL_SEED,
+        'env_steps': r_stats.total_steps, 'mean_length': r_stats.total_steps / n_roll,
+        'ms': ro_total / 3 * 1e3, 'best_ms_rank0': ro_best * 1e3,
+        'env_steps_per_sec': r_stats.total_steps * 3 / ro_total, 'unit': UNIT,
+        'collective': 'one all_gather_into_tensor of the 24-word statistics vector per rollout (NCCL), '
+                      'inside the timed region' if world > 1 else 'none (1 GPU)',
+        'stats_equal_oracle': (got_stats == want_stats) if want_stats is not None else None,
+        'oracle_vector': 'tests/golden/rollout_stats.json (oracle/g2048_oracle.c orc_rollout_mt)',
+        'summary': r_stats.summary(),
+        'kernel': 'rollout_kernel<true, true, false, 768>: two games per lane, one queue per CTA + stealing',
+        # issue ceiling of one GPU: 148 SMs x 4 schedulers x 1 warp-instruction / clk x 32 lanes / instr per step
+        'issue_ceiling_per_gpu': 148 * 4 * 1.965e9 * 32 / ROLLOUT_INSTR_PER_STEP,
+        'instr_per_step': ROLLOUT_INSTR_PER_STEP,
+        'instr_per_step_source': 'stored: profiles/r02_rollout_ncu_summary.txt (ncu --set full), not measured in this run',
+    }
+    rollout['frac_of_issue_ceiling'] = rollout['env_steps_per_sec'] / (world * rollout['issue_ceiling_per_gpu'])
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -428,15 +498,17 @@ def run_ours(args):
                                                                     int(os.environ.get('G2048_STEP_ENVS', '4')) // 4),
                      'mean_launch_ms': mean_launch * 1e3,
                      'best_launch_ms': best_launch * 1e3,
-                     'algorithmic_bytes_per_launch': BYTES_INJECTED * B},
+                     'algorithmic_bytes_per_launch': BYTES_INJECTED * B,
+                     'traffic_source': 'stored: ncu --set full DRAM bytes per env (profiles/r01_traffic.json) x envs; '
+                                       'not measured in this run',
+                     'other_kernels': {'philox_step': philox, 'rollout_sharded': rollout}},
         'clocks': clocks.summary(),
         'gpu_launches': args.steps,
-        'philox_mode': philox,
     }
 
     # ---- e2e: pinned host buffers through g2048_step_host (H2D + kernel + D2H timed) ----
     Be = min(1 << args.e2e_log2, B)
-    h_b = ops.pinned_empty(Be, torch.int64)
+    h_b = ops.pinned_empty(Be, torch.int64)     # g2048_host_alloc: pinned, on the GPU's NUMA node if allowed
     h_a = ops.pinned_empty(Be, torch.uint8)
     h_s = ops.pinned_empty(Be, torch.uint8)
     h_b[:] = boards[:Be].cpu().numpy()
@@ -445,17 +517,32 @@ def run_ours(args):
     h_out = (ops.pinned_empty(Be, torch.int64).view(np.uint64), ops.pinned_empty(Be, torch.int32),
              ops.pinned_empty(Be, torch.uint8))
     e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        ops.step_host(h_b, h_a, h_s, env_offset=env_offset, out=h_out)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e_steps):
-        ops.step_host(h_b, h_a, h_s, env_offset=env_offset, out=h_out)  # synchronous
-    torch.cuda.synchronize()
-    e_total = max_over_ranks(time.perf_counter() - t0)
-    line['e2e'] = {'value': world * Be * e_steps / e_total, 'unit': UNIT,
+
+    def host_timed(fn):
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            fn()  # synchronous
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0)
+    e_total = host_timed(lambda: ops.step_host(h_b, h_a, h_s, env_offset=env_offset, out=h_out))
+    # the same copies on the same streams without the kernel: the PCIe / host-memory ceiling of this
+    # call on this box at this number of ranks
+    c_total = host_timed(lambda: ops.step_host_copies(h_b, h_a, h_s, h_out))
+    gpu_node, mem_node = ops.host_numa_info(h_b)
+    e_val, c_val = world * Be * e_steps / e_total, world * Be * e_steps / c_total
+    line['e2e'] = {'value': e_val, 'unit': UNIT,
                    'h2d_bytes_per_step': Be * 10, 'd2h_bytes_per_step': Be * 13,
                    'boards_per_step': Be, 'steps': e_steps, 'ms_per_step': e_total / e_steps * 1e3,
+                   'copy_ceiling': c_val, 'frac_of_copy_ceiling': e_val / c_val,
+                   'copy_ceiling_gbs_per_gpu': Be * 23 * e_steps / c_total / 1e9,
+                   'copy_ceiling_note': 'g2048_step_host_copies: the H2D and D2H copies of the same call on the same '
+                                        'four streams, no kernel, all ranks at once (max over ranks)',
+                   'host_buffers': {'alloc': 'g2048_host_alloc (mmap + mbind(MPOL_PREFERRED, GPU node) + cudaHostRegister)',
+                                    'gpu_numa_node': gpu_node, 'buffer_numa_node': mem_node,
+                                    'cpus_allowed': host_cores()},
                    'api': 'simulate_2048_b200.ops.step_host -> g2048_step_host (pinned host ndarrays in/out)'}
     del h_b, h_a, h_s, h_out
 
@@ -522,39 +609,47 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 _, mean_s, _ = timed(g.replay, 5, 3, collective=False)
                 return mean_s / calls
+            # compact: g2048_expand_compact — the child offsets are scanned on the device INSIDE the
+            # timed call (no count pass, no host round trip)
             t_c = graph_time(lambda: ops.expand(eb, children='compact', out=ex_c), reps)
             t_d = graph_time(lambda: ops.expand(eb, children='dense', out=ex_d), reps)
-            bytes_c = n_e * (8 + 8 + 1 + 32 + 16 + 4 + 4) + 8 * n_children
+            # the whole public call as a fresh caller makes it: allocation, launch, ONE host read of
+            # the total to size the result (wall clock, synchronised)
+            for _ in range(3):
+                ops.expand(eb, children='compact')
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(10):
+                ops.expand(eb, children='compact')
+            torch.cuda.synchronize()
+            t_call = (time.perf_counter() - t0) / 10
+            bytes_c = n_e * (8 + 8 + 1 + 32 + 16 + 4 + 4 + 8) + 8 * n_children
             exp_out[str(n_e)] = {
                 'children_per_board': n_children / n_e,
                 'compact': {'us_per_launch': t_c * 1e6, 'boards_per_sec': n_e / t_c, 'children_per_sec': n_children / t_c,
-                            'algorithmic_gbs': bytes_c / t_c / 1e9, 'frac_of_hbm_peak': bytes_c / t_c / 1e9 / peak},
+                            'algorithmic_gbs': bytes_c / t_c / 1e9, 'frac_of_hbm_peak': bytes_c / t_c / 1e9 / peak,
+                            'whole_call_us': t_call * 1e6},
                 'dense': {'us_per_launch': t_d * 1e6, 'boards_per_sec': n_e / t_d},
             }
             del ex_c, ex_d
-        exp_out['note'] = ('g2048_expand into preallocated outputs (two kernels: moves, children), device time per call '
-                           'from a CUDA graph of back-to-back calls; compact = children packed at child_offsets '
-                           '(offsets from a count pass + cumsum, not timed), dense = [N,4,16,2] slots')
+        exp_out['note'] = ('compact.us_per_launch: g2048_expand_compact into preallocated buffers — moves, device-side '
+                           'scan of the child totals (offsets are an output) and children in one asynchronous call '
+                           '(a single kernel below 2^17 boards), device time from a CUDA graph of back-to-back calls; '
+                           'compact.whole_call_us: ops.expand(boards, children="compact") from scratch, wall clock incl. '
+                           'allocation and the one host read that sizes the result; dense = [N,4,16,2] slots')
         extra['expand'] = exp_out
-        # config 4: fused rollouts to termination
-        n_roll = 1 << 20
-        ro = ops.rollout(n_roll, seed=1, per_env=False)
-        torch.cuda.synchronize()
-        r_steps = int(ro.stats[1].item())
-        _, ro_mean, _ = timed(lambda: ops.rollout(n_roll, seed=1, per_env=False), 3, 1, collective=False)
-        extra['rollout'] = {'envs': n_roll, 'env_steps_per_sec': r_steps / ro_mean,
-                            'mean_length': r_steps / n_roll, 'ms': ro_mean * 1e3}
-        # a larger batch amortises the tail (lanes whose last game ends early idle until the longest ends)
-        n_big = 1 << 24
-        ops.rollout(n_big, seed=1, per_env=False)
-        _, rb_mean, _ = timed(lambda: ops.rollout(n_big, seed=1, per_env=False), 2, 0, collective=False)
-        extra['rollout_16m'] = {'envs': n_big, 'env_steps_per_sec': r_steps / n_roll * n_big / rb_mean,
-                                'ms': rb_mean * 1e3, 'note': 'steps estimated from the mean length of the 1M run'}
-        try:  # integer-pipe utilisation of the rollout kernel from `ncu --set full` (profiles/)
-            with open(os.path.join(ROOT, 'profiles', 'r01_rollout_pipes.json')) as f:
-                extra['rollout']['integer_pipe_utilisation'] = json.load(f)
-        except Exception:
-            pass
+        # config 4 on ONE GPU at two batch sizes (the sharded run over all ranks is in
+        # roofline.other_kernels.rollout_sharded)
+        ro_out = {}
+        for lg in (20, 21):
+            n_r = 1 << lg
+            ro = ops.rollout(n_r, seed=1, per_env=False)
+            torch.cuda.synchronize()
+            r_steps = int(ro.stats[1].item())
+            _, ro_m, ro_b = timed(lambda: ops.rollout(n_r, seed=1, per_env=False), 3, 1, collective=False)
+            ro_out[str(n_r)] = {'env_steps': r_steps, 'ms': ro_m * 1e3, 'env_steps_per_sec': r_steps / ro_m,
+                                'best_env_steps_per_sec': r_steps / ro_b}
+        extra['rollout_one_gpu'] = ro_out
         # config 5: self-play stepping loop, N = 4096, 200 steps, three API calls per iteration
         from simulate_2048_b200 import game
         st = game.batched_reset(7, 4096, device=dev)
@@ -615,7 +710,8 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
+        torch.cuda.synchronize()
+        dist.barrier(group=host_group)   # host-side wait (gloo): no kernel spins on the idle GPUs
         dist.destroy_process_group()
     return 0
 
@@ -646,6 +742,8 @@ def main():
     ap.add_argument('--boards-log2', type=int, default=26)
     ap.add_argument('--e2e-log2', type=int, default=26,
                     help='boards per end-to-end step (default: the same 2^26 batch as the device-resident measurement)')
+    ap.add_argument('--rollout-log2', type=int, default=24,
+                    help='total envs of the sharded rollout (BASELINE configs[3]: 2^24 over all ranks)')
     ap.add_argument('--quick', action='store_true', help='skip the secondary measurements')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline block')
     ap.add_argument('--ncu-traffic', type=float, default=None,

@@ -14,8 +14,14 @@
  *   - Pointers are DEVICE pointers unless the function name ends in `_host`.
  *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream).
  *     All device entry points are asynchronous with respect to the host.
- *   - Re-entrant across streams and devices.  The only library state is a per-device,
- *     read-only row table that is built once on first use (or by g2048_init).
+ *   - Re-entrant across host threads, streams and devices.
+ *   State.  The library keeps (1) a per-device, read-only row table, built once under a lock at
+ *     the first call on that device (or by g2048_init); (2) a pool of host-pipeline resources
+ *     (4 streams + 2 Mi-env staging buffers, ~190 MB of device memory each) used by
+ *     g2048_step_host — a call borrows one and returns it, concurrent callers get their own;
+ *     (3) the table of blocks handed out by g2048_host_alloc; (4) two process-wide MEASUREMENT
+ *     knobs, g2048_set_impl / g2048_set_tuning (atomics, read once per call; meant for benchmarks
+ *     and tests, not for production callers).  g2048_shutdown releases (1) and (2).
  *
  * Board format (`uint64_t`, one board per word)
  *   cell (r,c), flat index i = 4r + c (row-major, the order of `argwhere`/`flatten` in
@@ -36,12 +42,16 @@
  *   A rank >= number of empties, or an occupied absolute cell, spawns nothing and raises
  *   G2048_FLAG_BADSPAWN.
  *
- * Philox mode (spawns == NULL): Philox4x32-10, key = (seed_lo, seed_hi) or the per-env
- *   key, counter = (env_lo, env_hi, step, tag) with env the GLOBAL env id
- *   (env_offset + i) — results do not depend on grid size, GPU count or fusion.
- *   word0 -> rank = mulhi(word0, n_empty); word1 < 0x1999999A -> tile 4 (p = 0.1);
- *   word2 -> rollout policy: mulhi(word2, n_legal)-th legal action.  Tags:
- *   0 = play step, 1 / 2 = first / second reset tile.
+ * Philox mode (spawns == NULL), stream layout v2: Philox4x32-10, key = (seed_lo, seed_hi) or the
+ *   per-env key.  ONE block serves the four consecutive envs of a quad: counter =
+ *   (quad_lo, quad_hi, step, tag) with quad = GLOBAL env id (env_offset + i) >> 2, and env e reads
+ *   word e & 3 — results do not depend on grid size, GPU count or fusion, and a thread that owns
+ *   four consecutive envs pays for one block.  The word w is read as a mixed-radix fraction:
+ *     rank  = hi32(w  * n_empty)   spawn cell among the empties,   f1 = lo32(w  * n_empty)
+ *     tile 4 iff hi32(f1 * 10) == 0 (p = 0.1),                      f2 = lo32(f1 * 10)
+ *     rollout policy: the NEXT action is the hi32(f2 * n_legal)-th legal action of the new board.
+ *   Tags: 0 = play step, 1 / 2 = first / second reset tile (step 0; the first rollout action is
+ *   digit 3 of the tag-2 word), 3 = first action of a rollout that starts from a given board.
  *
  * Flags byte (per env):
  */
@@ -55,7 +65,7 @@
 extern "C" {
 #endif
 
-#define G2048_ABI_VERSION 1
+#define G2048_ABI_VERSION 2
 
 #define G2048_FLAG_LEFT 0x01u     /* legal-action mask of the NEW board, bit a = action a */
 #define G2048_FLAG_UP 0x02u
@@ -76,7 +86,7 @@ extern "C" {
 #define G2048_PHILOX_TAG_STEP 0u
 #define G2048_PHILOX_TAG_RESET0 1u
 #define G2048_PHILOX_TAG_RESET1 2u
-#define G2048_PHILOX_FOUR_THRESHOLD 0x1999999Au /* word1 < threshold -> spawn a 4 */
+#define G2048_PHILOX_TAG_START 3u
 
 /* children layout for g2048_expand */
 #define G2048_CHILDREN_NONE 0
@@ -96,7 +106,10 @@ const char* g2048_last_cuda_error(void); /* thread-local text of the last CUDA f
 
 /* Build the per-device row table now (otherwise done lazily). device < 0 = current. */
 int g2048_init(int device);
-/* Select the row-move implementation used by g2048_step/g2048_env_step (process-wide). */
+/* Free the row tables and pooled host pipelines of every device.  Must not run concurrently with
+ * other calls; the library re-initialises itself lazily if it is used again. */
+int g2048_shutdown(void);
+/* Select the row-move implementation used by g2048_step (process-wide measurement knob). */
 int g2048_set_impl(int impl);
 /* Tuning knobs of the smem-table step kernel: threads per CTA (0 = automatic — 640 with injected
  * spawns, 512 with Philox — or 512, 640, 768, 1024; one CTA per SM) and consecutive envs per
@@ -110,7 +123,8 @@ int g2048_set_tuning(int step_threads, int envs_per_thread);
  *   env uses step_base), env_keys[n] or NULL (per-env 64-bit Philox key replacing seed),
  *   done_in[n] or NULL: a non-zero entry passes the env through (env.py:103-104):
  *   board unchanged, reward 0, DONE set.
- *   Outputs: boards_out[n] (may alias boards_in), rewards[n] (sum of merged tile values,
+ *   Outputs: boards_out[n] (may be the SAME pointer as boards_in: every thread reads its envs before
+ *   it writes them, and the loads carry no read-only (.nc) hint; partial overlap is not allowed), rewards[n] (sum of merged tile values,
  *   0 for an illegal move), flags[n].
  */
 int g2048_step(const uint64_t* boards_in, const uint8_t* actions, const uint8_t* spawns,
@@ -160,6 +174,21 @@ int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* rewards, uint
 int g2048_expand_children(const uint64_t* after, const uint8_t* child_count,
                           const int64_t* child_offsets, uint64_t* children, int child_layout,
                           size_t n, void* stream);
+
+/*
+ * g2048_expand with the compact children layout as ONE call without a host round trip: the
+ * per-board child totals are scanned on the device (n < 2^17: a single kernel launch, tiles
+ * chained by ticket + aggregate look-back; larger batches: moves, a three-kernel scan, children).
+ *   child_offsets[n] is an OUTPUT (exclusive prefix sum of the per-board totals, what a caller of
+ *   g2048_expand computes on the host side); children has room for `capacity` boards (> 0): a
+ *   board whose children would run past it writes none; total_out[2] (device, optional) receives
+ *   {total number of children, 1 if total > capacity else 0}.  The worst case is 120 per board
+ *   (4 actions x 15 empty cells x 2 values).  Other outputs as g2048_expand (NULL to skip).
+ */
+int g2048_expand_compact(const uint64_t* boards, uint64_t* after, int32_t* rewards, uint8_t* mask,
+                         uint8_t* num_empty, uint8_t* child_count, int64_t* child_offsets,
+                         uint64_t* children, size_t capacity, uint64_t* total_out, size_t n,
+                         void* stream);
 
 /* Chance children of given boards (gameboard.py:132 after_state, :174 after_state_lazy):
  * children[n*32] dense (slot 2k + v = k-th empty cell in row-major order, v: 0 -> tile 2,
@@ -215,8 +244,10 @@ int g2048_nstep_returns(const float* rewards, const float* values, const int32_t
                         size_t n, void* stream);
 
 /*
- * Fused random-policy rollout to termination, board in registers:
- *   policy = uniform over legal actions (Philox word2), spawns from Philox words 0/1.
+ * Fused random-policy rollout to termination, boards in registers:
+ *   policy = uniform over the legal actions (digit 3 of the previous step's word, see "Philox
+ *   mode"), spawns from digits 1 / 2 of the word of (env, step): the boards of a rollout are those
+ *   of g2048_step in Philox mode fed with the same actions.
  *   boards_io[n]: start boards if `from_reset` == 0 (updated to the final boards), else
  *   output only (games start from g2048_reset's Philox boards).
  *   score_out i64[n] (sum of rewards), steps_out i32[n], maxexp_out u8[n] — any may be NULL.
@@ -251,8 +282,17 @@ int g2048_row_table_host(uint16_t* result, uint32_t* reward, uint8_t* moved);
 int g2048_step_host(const uint64_t* boards_in, const uint8_t* actions, const uint8_t* spawns,
                     uint64_t seed, uint64_t env_offset, uint32_t step_base,
                     uint64_t* boards_out, int32_t* rewards, uint8_t* flags, size_t n);
-int g2048_host_alloc(void** ptr, size_t bytes); /* pinned host memory */
+/* The copies of g2048_step_host alone (same stages, same streams, no kernel): the PCIe ceiling of
+ * that call on this box, for reporting e2e against it. */
+int g2048_step_host_copies(const uint64_t* boards_in, const uint8_t* actions, const uint8_t* spawns,
+                           uint64_t* boards_out, int32_t* rewards, uint8_t* flags, size_t n);
+/* Pinned host memory for the CURRENT device: placed on the NUMA node the GPU hangs off when the
+ * process is allowed to (mmap + mbind(MPOL_PREFERRED) + first touch + cudaHostRegister; environment
+ * G2048_HOST_NUMA=0 or a refusal falls back to cudaHostAlloc).  Free with g2048_host_free. */
+int g2048_host_alloc(void** ptr, size_t bytes);
 int g2048_host_free(void* ptr);
+/* Diagnostics: NUMA node of the current GPU and of the page at `ptr` (-1 = unknown). */
+int g2048_host_numa_info(const void* ptr, int* gpu_node, int* mem_node);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,8 @@ def lib() -> C.CDLL:
         _lib.orc_legal_mask.restype = C.c_uint
         _lib.orc_legal_mask_values.restype = C.c_uint
         _lib.orc_rollout.restype = C.c_uint64
+        _lib.orc_philox_word.restype = C.c_uint32
+        _lib.orc_draw_spawn.restype = C.c_uint32
     return _lib
 
 
@@ -62,6 +64,18 @@ def philox4x32_10(ctr, key):
     out = np.zeros(4, dtype=np.uint32)
     lib().orc_philox4x32_10(_p(c), _p(k), _p(out))
     return out
+
+
+def philox_word(key: int, env: int, step: int, tag: int) -> int:
+    """The 32-bit word env reads at (step, tag): word env & 3 of the block of quad env >> 2."""
+    return int(lib().orc_philox_word(C.c_uint64(key), C.c_uint64(env), C.c_uint32(step), C.c_uint32(tag)))
+
+
+def draw_spawn(w: int, n_empty: int):
+    """(rank, four, remainder): the first two mixed-radix digits of a word."""
+    rank, four = C.c_uint32(0), C.c_uint32(0)
+    rem = lib().orc_draw_spawn(C.c_uint32(w), C.c_uint32(n_empty), C.byref(rank), C.byref(four))
+    return int(rank.value), bool(four.value), int(rem)
 
 
 def latent_state(board: int, action: int):

@@ -31,6 +31,7 @@ PROTOTYPES = {
     'g2048_error_string': (C.c_char_p, [C.c_int]),
     'g2048_last_cuda_error': (C.c_char_p, []),
     'g2048_init': (C.c_int, [C.c_int]),
+    'g2048_shutdown': (C.c_int, []),
     'g2048_set_impl': (C.c_int, [C.c_int]),
     'g2048_set_tuning': (C.c_int, [C.c_int, C.c_int]),
     'g2048_step': (C.c_int, [_P, _P, _P, _U64, _U64, _P, _U32, _P, _P, _P, _P, _P, _SZ, _P]),
@@ -38,6 +39,7 @@ PROTOTYPES = {
     'g2048_mask': (C.c_int, [_P, _P, _SZ, _P]),
     'g2048_expand': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _SZ, _P]),
     'g2048_expand_children': (C.c_int, [_P, _P, _P, _P, C.c_int, _SZ, _P]),
+    'g2048_expand_compact': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P, _SZ, _P]),
     'g2048_after_state': (C.c_int, [_P, _P, _P, _P, _SZ, _P]),
     'g2048_reset': (C.c_int, [_U64, _U64, _P, _P, _P, _SZ, _P]),
     'g2048_spawn': (C.c_int, [_P, _P, _U64, _U64, _P, _U32, _U32, _P, _SZ, _P]),
@@ -50,7 +52,9 @@ PROTOTYPES = {
     'g2048_unpack': (C.c_int, [_P, _P, _SZ, _P]),
     'g2048_row_table_host': (C.c_int, [_P, _P, _P]),
     'g2048_step_host': (C.c_int, [_P, _P, _P, _U64, _U64, _U32, _P, _P, _P, _SZ]),
+    'g2048_step_host_copies': (C.c_int, [_P, _P, _P, _P, _P, _P, _SZ]),
     'g2048_host_alloc': (C.c_int, [C.POINTER(C.c_void_p), _SZ]),
+    'g2048_host_numa_info': (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     'g2048_host_free': (C.c_int, [_P]),
 }
 
@@ -80,7 +84,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if handle.g2048_abi_version() != 1:
+        if handle.g2048_abi_version() != 2:
             raise ImportError('libg2048.so ABI version mismatch; rebuild it')
         _lib = handle
     return _lib

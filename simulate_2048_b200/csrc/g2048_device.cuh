@@ -293,7 +293,13 @@ __device__ __forceinline__ bool spawn_byte(Board& b, u32 zlo, u32 zhi, u32 byte)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 (Salmon et al. 2011).  key = (k0,k1); counter = (env_lo, env_hi, step, tag).
+// Philox4x32-10 (Salmon et al. 2011), stream layout v2 (include/g2048.h "Philox mode"):
+// ONE block serves the four consecutive envs of a quad — counter = (quad_lo, quad_hi, step, tag)
+// with quad = global env id >> 2, key = (k0, k1) — and env e reads word e & 3.  A thread of the step
+// kernel owns exactly one quad, so the ~42 instructions of a block are paid once per four envs.
+// The word is consumed as a mixed-radix fraction: rank = hi32(w * n_empty), f1 = lo32(w * n_empty);
+// tile 4 iff hi32(f1 * 10) == 0, f2 = lo32(f1 * 10); the rollout policy's next action is
+// hi32(f2 * n_legal).  Each step is one IMAD.WIDE.
 // ---------------------------------------------------------------------------------------------
 struct Philox4 {
     u32 x, y, z, w;
@@ -345,19 +351,46 @@ __device__ __forceinline__ Philox4 philox4x32_10(u32 c0, u32 c1, u32 c2, u32 c3,
     return Philox4{c0, c1, c2, c3};
 }
 
-__device__ __forceinline__ Philox4 philox_env(const PhiloxKeys& ks, u64 env, u32 step, u32 tag) {
-    return philox4x32_10((u32)env, (u32)(env >> 32), step, tag, ks);
+// the block of the quad that holds `env`
+__device__ __forceinline__ Philox4 philox_quad(const PhiloxKeys& ks, u64 env, u32 step, u32 tag) {
+    const u64 q = env >> 2;
+    return philox4x32_10((u32)q, (u32)(q >> 32), step, tag, ks);
+}
+__device__ __forceinline__ Philox4 philox_quad(u64 key, u64 env, u32 step, u32 tag) {
+    const u64 q = env >> 2;
+    return philox4x32_10((u32)q, (u32)(q >> 32), step, tag, (u32)key, (u32)(key >> 32));
+}
+// word j (0..3) of a block
+__device__ __forceinline__ u32 philox_pick(const Philox4& p, u32 j) {
+    const u32 a = (j & 1u) ? p.y : p.x, b = (j & 1u) ? p.w : p.z;
+    return (j & 2u) ? b : a;
+}
+// the word of one env
+__device__ __forceinline__ u32 philox_word(u64 key, u64 env, u32 step, u32 tag) {
+    return philox_pick(philox_quad(key, env, step, tag), (u32)env & 3u);
+}
+__device__ __forceinline__ u32 philox_word(const PhiloxKeys& ks, u64 env, u32 step, u32 tag) {
+    return philox_pick(philox_quad(ks, env, step, tag), (u32)env & 3u);
 }
 
-__device__ __forceinline__ Philox4 philox_env(u64 key, u64 env, u32 step, u32 tag) {
-    return philox4x32_10((u32)env, (u32)(env >> 32), step, tag, (u32)key, (u32)(key >> 32));
+// digits 1 and 2 of a word: spawn rank in [0, n) and the spawned exponent (2 for a tile 4, p = 0.1);
+// returns the remainder f2 (the next digit is the rollout policy's action)
+__device__ __forceinline__ u32 draw_spawn(u32 w, u32 n, u32& rank, u32& exp) {
+    const u64 p1 = (u64)w * n;
+    const u64 p2 = (u64)(u32)p1 * 10u;
+    rank = (u32)(p1 >> 32);
+    exp = (u32)(p2 >> 32) == 0u ? 2u : 1u;
+    return (u32)p2;
 }
 
-// Philox spawn: rank = mulhi(word0, n_empty), four iff word1 < 0x1999999A.
-__device__ __forceinline__ void spawn_philox(Board& b, u32 zlo, u32 zhi, const Philox4& p) {
+// Philox spawn on a board with at least one empty cell.  Returns the remainder f2.
+__device__ __forceinline__ u32 spawn_philox(Board& b, u32 zlo, u32 zhi, u32 w) {
     const u32 n = __popc(zlo) + __popc(zhi);
-    if (n == 0u) return;
-    spawn_rank(b, zlo, zhi, __umulhi(p.x, n), p.y < G2048_PHILOX_FOUR_THRESHOLD ? 2u : 1u);
+    if (n == 0u) return w;
+    u32 rank, exp;
+    const u32 rem = draw_spawn(w, n, rank, exp);
+    spawn_rank(b, zlo, zhi, rank, exp);
+    return rem;
 }
 
 __device__ __forceinline__ u32 max_exponent(Board b) {

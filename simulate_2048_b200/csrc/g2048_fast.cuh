@@ -159,6 +159,13 @@ G2048_HD u32 popc(u32 x) {
     return (u32)__builtin_popcount(x);
 #endif
 }
+// a * b as {hi, lo} in one instruction (IMAD.WIDE.U32): a digit of the mixed-radix random word
+// and its remainder (g2048_device.cuh, Philox section)
+G2048_HD void mul_wide(u32 a, u32 b, u32& hi, u32& lo) {
+    const u64 p = (u64)a * b;
+    hi = (u32)(p >> 32);
+    lo = (u32)p;
+}
 G2048_HD u32 mulhi(u32 a, u32 b) {
 #if defined(__CUDA_ARCH__)
     return __umulhi(a, b);
@@ -269,8 +276,9 @@ struct FastOut {
 // One transition on the fast path.
 //   lut(off) returns the u32 entry of the staged (hashed) row table at BYTE offset `off`.
 //   Preconditions (checked by the caller): !has_big_tile(lo, hi).
-//   rank = spawn rank among the empties (injected) — ignored when kPhilox (then w0 draws it);
-//   exp_mul = spawned exponent (1 or 2) << 29: the tile is the high word of marker * exp_mul;
+//   rank = spawn rank among the empties (injected), exp_mul = spawned exponent (1 or 2) << 29 (the
+//   tile is the high word of marker * exp_mul) — both ignored when kPhilox: then they are the first
+//   two mixed-radix digits of the env's random word w0;
 //   one = the run-time constant 1 (see add()).
 // ---- building blocks (also used by the fused rollout kernel) ---------------------------------
 
@@ -373,7 +381,12 @@ G2048_HD FastOut transition_fast(u32 lo, u32 hi, const Orient& o, u32 rank, u32 
     // ---- spawn on the rank-th empty cell (row-major) of the afterstate ----
     u32 nlo = nz8(al, one), nhi = nz8(ah, one);
     const u32 tiles_lo = popc(nlo), ne = 16u - (tiles_lo + popc(nhi));
-    if (kPhilox) rank = mulhi(w0, ne);
+    if (kPhilox) {
+        // digit 1 (base ne) = spawn rank, digit 2 (base 10) == 0 -> tile 4 (exponent 2)
+        u32 f1;
+        mul_wide(w0, ne, rank, f1);
+        exp_mul = mad(nonzero01(mulhi(f1, 10u)), 0xE0000000u, 0x40000000u);
+    }
     bool in_hi;
     const u32 g = spawn_prefix(nlo, nhi, tiles_lo, rank, one, in_hi);
     // a Philox rank is < ne by construction (and a move always leaves an empty cell)

@@ -21,7 +21,9 @@
 #include <cstdio>
 #include <cstring>
 #include <cstdlib>
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "g2048_device.cuh"
 #include "g2048_fast.cuh"
@@ -72,20 +74,30 @@ __global__ void build_table_kernel(u32* __restrict__ tab, u32* __restrict__ tab_
     }
 }
 
+// Library state (all of it; include/g2048.h "State"):
+//   g_dev[]   per-device row tables, built once under the device's mutex and published with a
+//             release store of `ready` (readers take the acquire load on every call);
+//   g_impl / g_step_threads / g_step_groups   process-wide measurement knobs (g2048_set_impl,
+//             g2048_set_tuning), atomics read once per call;
+//   g_pipes   pool of host-pipeline resources of g2048_step_host (streams + staging buffers),
+//             handed out under a mutex, returned after the call, freed by g2048_shutdown.
 struct DeviceState {
     std::mutex mu;
-    bool ready = false;
+    std::atomic<bool> ready{false};
     u32* table = nullptr;
     u32* table_hashed = nullptr;
     int sms = 0;
     size_t smem_optin = 0;
+    int children_occupancy = 1;  // resident CTAs per SM of expand_children_kernel
 };
 static DeviceState g_dev[64];
-static int g_impl = G2048_IMPL_AUTO;
-static int g_step_threads = 0;  // 0 = automatic: 640 with injected spawns (5 warps per scheduler at 96 registers: +1 %), 512 with Philox
+static std::atomic<int> g_impl{G2048_IMPL_AUTO};
+static std::atomic<int> g_step_threads{0};  // 0 = automatic: 640 with injected spawns (5 warps per scheduler at 96 registers: +1 %), 512 with Philox
 // programmatic dependent launch of the step kernel (environment G2048_PDL=0 turns it off)
-static int g_pdl = [] { const char* e = getenv("G2048_PDL"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
-static int g_step_groups = 1;   // groups of 4 envs per thread (1 or 2)  // tuning knob (g2048_set_tuning)
+static const int g_pdl = [] { const char* e = getenv("G2048_PDL"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
+static std::atomic<int> g_step_groups{1};   // groups of 4 envs per thread (1 or 2)  // tuning knob (g2048_set_tuning)
+
+static int device_occupancy(DeviceState& s);  // defined next to the kernels it measures
 
 static int current_state(DeviceState** out) {
     int dev = 0;
@@ -96,9 +108,9 @@ static int current_state(DeviceState** out) {
     }
     if (dev < 0 || dev >= 64) return G2048_EINVAL;
     DeviceState& s = g_dev[dev];
-    if (!s.ready) {
+    if (!s.ready.load(std::memory_order_acquire)) {
         std::lock_guard<std::mutex> lk(s.mu);
-        if (!s.ready) {
+        if (!s.ready.load(std::memory_order_relaxed)) {
             cudaDeviceProp p;
             CU(cudaGetDeviceProperties(&p, dev));
             if (p.major != 10) {
@@ -113,7 +125,9 @@ static int current_state(DeviceState** out) {
             build_table_kernel<<<kRows / 256, 256>>>(s.table, s.table_hashed);
             CU(cudaGetLastError());
             CU(cudaDeviceSynchronize());
-            s.ready = true;
+            int rc = device_occupancy(s);
+            if (rc) return rc;
+            s.ready.store(true, std::memory_order_release);
         }
     }
     *out = &s;
@@ -131,14 +145,14 @@ extern "C" int g2048_set_tuning(int step_threads, int envs_per_thread) {
         return G2048_EINVAL;
     if (envs_per_thread != 4 && envs_per_thread != 8) return G2048_EINVAL;
     if (step_threads == 640 && envs_per_thread == 8) return G2048_EINVAL;  // not instantiated
-    g_step_threads = step_threads;
-    g_step_groups = envs_per_thread / 4;
+    g_step_threads.store(step_threads);
+    g_step_groups.store(envs_per_thread / 4);
     return G2048_OK;
 }
 
 extern "C" int g2048_set_impl(int impl) {
     if (impl < G2048_IMPL_AUTO || impl > G2048_IMPL_GATHER) return G2048_EINVAL;
-    g_impl = impl;
+    g_impl.store(impl);
     return G2048_OK;
 }
 
@@ -149,9 +163,11 @@ struct Boards4 {
     u64 b[4];
 };
 
+// (no .nc: boards_out may alias boards_in, and PTX requires .nc data to stay read-only for the
+// whole kernel; a thread reads its four boards before it writes them, so plain loads are exact)
 __device__ __forceinline__ Boards4 ld_boards4(const u64* p) {
     Boards4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ld.global.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(r.b[0]), "=l"(r.b[1]), "=l"(r.b[2]), "=l"(r.b[3])
                  : "l"(p));
     return r;
@@ -235,9 +251,7 @@ __device__ __forceinline__ void transition(Board b, u32 action, u32 spawn, u64 k
     u32 rank, exp;
     bool ok = true;
     if (kPhilox) {
-        const Philox4 p = philox_env(key, env, step, G2048_PHILOX_TAG_STEP);
-        rank = __umulhi(p.x, n_empty);
-        exp = p.y < G2048_PHILOX_FOUR_THRESHOLD ? 2u : 1u;
+        draw_spawn(philox_word(key, env, step, G2048_PHILOX_TAG_STEP), n_empty, rank, exp);
     } else {
         exp = (spawn & 0x10u) ? 2u : 1u;
         rank = spawn & 0xFu;
@@ -399,6 +413,12 @@ __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 s
     Boards4 ob;
     int rws[4];
     u32 fl = 0;
+    // Philox: the thread's four envs are one quad (env0 is a multiple of 4), i.e. ONE block
+    u32 pw[4] = {0u, 0u, 0u, 0u};
+    if (kPhilox) {
+        const Philox4 p = philox_quad(a.keys, env0, a.step_base, G2048_PHILOX_TAG_STEP);
+        pw[0] = p.x; pw[1] = p.y; pw[2] = p.z; pw[3] = p.w;
+    }
     const u32 act4 = (actions << 5) & 0x60606060u;     // byte k = 32 * action_k (byte offset)
     const u32 rank4 = spawns & 0x0F0F0F0Fu;            // byte k = spawn rank
     const u32 exp4 = ((spawns & 0x10101010u) << 1) + 0x20202020u;       // byte k = exponent (1 or 2) << 5
@@ -409,12 +429,9 @@ __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 s
         fast::Orient o;
         o.mask = o0.x; o.mul_hi = o0.y; o.mul_lo = o0.z; o.sel_lo = o0.w;
         o.sel_hi = *reinterpret_cast<const u32*>(op + 16);
-        u32 rank = 0, exp_mul, w0 = 0;  // exp_mul = exponent << 29
+        u32 rank = 0, exp_mul = 0, w0 = 0;  // exp_mul = exponent << 29 (Philox: drawn inside)
         if (kPhilox) {
-            const Philox4 p = philox_env(a.keys, env0 + k, a.step_base, G2048_PHILOX_TAG_STEP);
-            w0 = p.x;
-            // word1 < 0x1999999A  <=>  mulhi(word1, 10) == 0   (0x1999999A * 10 = 2^32 + 4)
-            exp_mul = fast::mad(fast::nonzero01(__umulhi(p.y, 10u)), 0xE0000000u, 0x40000000u);
+            w0 = pw[k];
         } else {
             rank = fast::prmt(rank4, 0u, 0x4440u + k);
             exp_mul = fast::prmt(exp4, 0u, 0x0444u + (k << 12));  // byte k of exp4 into byte 3
@@ -597,13 +614,15 @@ extern "C" int g2048_step(const uint64_t* boards_in, const uint8_t* actions, con
     const bool plain = !step_ctr && !env_keys && !done_in;
     const bool vec_ok = aligned(boards_in, 32) && aligned(boards_out, 32) && aligned(rewards, 16) &&
                         aligned(actions, 4) && aligned(flags, 4) && (!spawns || aligned(spawns, 4));
-    bool use_lut = plain && vec_ok && s->smem_optin >= kStepSmemBytes;
-    if (g_impl == G2048_IMPL_AUTO) use_lut = use_lut && n >= kLutMinEnvs;
-    if (g_impl == G2048_IMPL_REGISTER || g_impl == G2048_IMPL_GATHER) use_lut = false;
+    // Philox: a thread's four envs must be one quad of the stream (one block per thread)
+    bool use_lut = plain && vec_ok && s->smem_optin >= kStepSmemBytes && (spawns || (env_offset & 3u) == 0u);
+    const int impl = g_impl.load(), tune_threads = g_step_threads.load(), tune_groups = g_step_groups.load();
+    if (impl == G2048_IMPL_AUTO) use_lut = use_lut && n >= kLutMinEnvs;
+    if (impl == G2048_IMPL_REGISTER || impl == G2048_IMPL_GATHER) use_lut = false;
 
     if (use_lut) {
         const int smem = (int)kStepSmemBytes;
-        const int threads = g_step_threads ? g_step_threads : (spawns ? 640 : 512), groups = g_step_groups;
+        const int threads = tune_threads ? tune_threads : (spawns ? 640 : 512), groups = tune_groups;
         // one CTA per SM as soon as there is a warp-tile for each (the kernel splits in warp-tiles)
         const size_t wunits = n / ((size_t)128 * groups);
         const int grid = (int)(wunits < (size_t)s->sms ? (wunits ? wunits : 1) : (size_t)s->sms);
@@ -644,7 +663,7 @@ extern "C" int g2048_step(const uint64_t* boards_in, const uint8_t* actions, con
 #undef G2048_LAUNCH_STEP
     } else {
         int grid = grid_for(n, 256, s->sms, 8);
-        if (g_impl == G2048_IMPL_REGISTER) {
+        if (impl == G2048_IMPL_REGISTER) {
             if (spawns) step_general_kernel<false, RegisterTable><<<grid, 256, 0, st>>>(a);
             else step_general_kernel<true, RegisterTable><<<grid, 256, 0, st>>>(a);
         } else {
@@ -993,7 +1012,7 @@ __device__ __forceinline__ Board reset_board(u64 key, u64 env, const uint8_t* sp
         if (spawn2) {
             spawn_byte(b, zlo, zhi, spawn2[t]);
         } else {
-            spawn_philox(b, zlo, zhi, philox_env(key, env, 0u, G2048_PHILOX_TAG_RESET0 + t));
+            spawn_philox(b, zlo, zhi, philox_word(key, env, 0u, G2048_PHILOX_TAG_RESET0 + t));
         }
     }
     return b;
@@ -1036,7 +1055,7 @@ __global__ void __launch_bounds__(256) spawn_kernel(u64* __restrict__ boards,
         bool ok = true;
         if ((zlo | zhi) != 0u) {  // a full board is returned unchanged (gameboard.py:277-278)
             if (spawns) ok = spawn_byte(b, zlo, zhi, spawns[i]);
-            else spawn_philox(b, zlo, zhi, philox_env(env_keys ? env_keys[i] : seed, env_offset + i, step, tag));
+            else spawn_philox(b, zlo, zhi, philox_word(env_keys ? env_keys[i] : seed, env_offset + i, step, tag));
             boards[i] = join(b);
         }
         if (flags) flags[i] = ok ? 0 : G2048_FLAG_BADSPAWN;
@@ -1077,6 +1096,9 @@ struct ExpandArgs {
     const u32* table;
     const u32* table_hashed;
     u32 one;  // run-time 1 (see StepArgs)
+    int64_t* offsets_out;  // g2048_expand_compact: the offsets are an OUTPUT (device-side scan)
+    size_t capacity;       // children buffer capacity in boards (0 = unlimited): a board whose
+                           // children would run past it writes none
 };
 
 __device__ __forceinline__ u32 empty_cells16(Board b) {
@@ -1326,6 +1348,9 @@ __global__ void __launch_bounds__(kChildWarps * 32) expand_children_kernel(const
             r.s23 = src[1];
             r.off = (kLayout == G2048_CHILDREN_COMPACT) ? (unsigned long long)a.child_offsets[mine]
                                                         : (unsigned long long)mine * 128ull;
+            if (kLayout == G2048_CHILDREN_COMPACT && a.capacity != 0 &&
+                r.off + ((r.cc4 * 0x01010101u) >> 24) > a.capacity)
+                r.cc4 = 0u;  // does not fit: nothing is written for this board
         }
         return r;
     };
@@ -1375,20 +1400,197 @@ __global__ void __launch_bounds__(kFusedWarps * 32) expand_fused_kernel(const Ex
 
 // the second kernel of the expansion: one wave, as many blocks as are resident at once (a partial
 // second wave costs ~14 %)
+static int device_occupancy(DeviceState& s) {
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &occ, expand_children_kernel<G2048_CHILDREN_COMPACT>, kChildWarps * 32, 0));
+    s.children_occupancy = occ < 1 ? 1 : occ;
+    return G2048_OK;
+}
+
 static int launch_expand_children(const ExpandArgs& a, const DeviceState* s, cudaStream_t st) {
-    static int occ = 0;
-    if (occ == 0) {
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-            &occ, expand_children_kernel<G2048_CHILDREN_COMPACT>, kChildWarps * 32, 0));
-        if (occ < 1) occ = 1;
-    }
-    const int grid = grid_for(a.n, kChildWarps * 32, s->sms, occ);
+    const int grid = grid_for(a.n, kChildWarps * 32, s->sms, s->children_occupancy);
     if (a.layout == G2048_CHILDREN_COMPACT)
         expand_children_kernel<G2048_CHILDREN_COMPACT><<<grid, kChildWarps * 32, 0, st>>>(a);
     else
         expand_children_kernel<G2048_CHILDREN_DENSE><<<grid, kChildWarps * 32, 0, st>>>(a);
     CU(cudaGetLastError());
     return G2048_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// compact expansion without a host round trip (g2048_expand_compact): the child offsets are an
+// exclusive scan of the per-board child totals, computed on the device.
+// ---------------------------------------------------------------------------------------------
+constexpr unsigned long long kAggValid = 1ull << 63;
+
+__device__ __forceinline__ u32 sum_bytes4(u32 x) { return (x * 0x01010101u) >> 24; }  // four counts <= 30
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Small batches: ONE launch.  A CTA takes a tile of 128 boards by ticket (so a tile only ever waits
+// for tiles that have already started: no dependence on co-residency), runs the four moves
+// (lane = board, hashed table gathered from L2), scans its child totals, publishes the tile
+// aggregate, sums the aggregates of all earlier tiles (every thread polls <= n_tiles / 128 entries,
+// all in flight at once) and then expands its boards from shared memory at prefix + local offset.
+// scratch[0] = ticket counter, scratch[2 + t] = aggregate of tile t | kAggValid (zeroed per call).
+constexpr int kScanWarps = 4;
+
+__global__ void __launch_bounds__(kScanWarps * 32) expand_compact_fused_kernel(const ExpandArgs a,
+                                                                             unsigned long long* scratch,
+                                                                             unsigned long long* total_out) {
+    __shared__ ChildTile s_tile[kScanWarps];
+    __shared__ u32 s_tile_id, s_warp_tot[kScanWarps];
+    __shared__ unsigned long long s_red[kScanWarps];
+    const u32 FULL = 0xFFFFFFFFu, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile_id = (u32)atomicAdd(&scratch[0], 1ull);
+    __syncthreads();
+    const size_t tile = s_tile_id, warp_base = tile * (kScanWarps * 32) + w * 32, mine = warp_base + lane;
+    const GlobalLut lut{a.table_hashed};
+    uint4 s01 = make_uint4(0u, 0u, 0u, 0u), s23 = s01;
+    u32 cc4 = 0u;
+    if (mine < a.n) {
+        const MovesOut r = expand_moves_compute(a, a.boards[mine], lut);
+        expand_moves_store(a, mine, r);
+        s01 = make_uint4(r.after4[0].x, r.after4[0].y, r.after4[1].x, r.after4[1].y);
+        s23 = make_uint4(r.after4[2].x, r.after4[2].y, r.after4[3].x, r.after4[3].y);
+        cc4 = r.cc4;
+    }
+    const u32 tot = sum_bytes4(cc4);
+    u32 inc = tot;  // inclusive scan over the warp
+#pragma unroll
+    for (u32 d = 1; d < 32u; d <<= 1) {
+        const u32 v = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += v;
+    }
+    if (lane == 31u) s_warp_tot[w] = inc;
+    __syncthreads();
+    u32 warp_off = 0u, cta_tot = 0u;
+#pragma unroll
+    for (u32 k = 0; k < (u32)kScanWarps; ++k) {
+        warp_off += k < w ? s_warp_tot[k] : 0u;
+        cta_tot += s_warp_tot[k];
+    }
+    unsigned long long* agg = scratch + 2;
+    if (threadIdx.x == 0) st_release_u64(&agg[tile], kAggValid | cta_tot);
+    unsigned long long part = 0ull;
+    for (size_t j = threadIdx.x; j < tile; j += (size_t)kScanWarps * 32) {
+        unsigned long long v;
+        do v = ld_acquire_u64(&agg[j]); while (!(v & kAggValid));
+        part += v & ~kAggValid;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) part += __shfl_xor_sync(FULL, part, off);
+    if (lane == 0u) s_red[w] = part;
+    __syncthreads();
+    unsigned long long prefix = 0ull;
+#pragma unroll
+    for (u32 k = 0; k < (u32)kScanWarps; ++k) prefix += s_red[k];
+    const unsigned long long off = prefix + warp_off + (inc - tot);
+    if (mine < a.n && a.offsets_out) a.offsets_out[mine] = (int64_t)off;
+    if (threadIdx.x == 0 && (tile + 1) * (size_t)(kScanWarps * 32) >= a.n && total_out) {  // the last tile
+        total_out[0] = prefix + cta_tot;
+        total_out[1] = (a.capacity != 0 && prefix + cta_tot > a.capacity) ? 1ull : 0ull;
+    }
+    if (a.capacity != 0 && off + tot > a.capacity) cc4 = 0u;
+    expand_record(s_tile[w], lane, s01, s23, cc4, off);
+    __syncwarp();
+    if (warp_base < a.n)
+        expand_children_tile<G2048_CHILDREN_COMPACT>(a, s_tile[w], (u32)min((size_t)32, a.n - warp_base), lane);
+}
+
+// Large batches: moves kernel (writes child_count), then a three-kernel scan of the per-board
+// totals (tile sums, scan of the tile sums by one CTA, per-tile apply), then the children kernel.
+constexpr int kScanThreads = 256, kScanPerThread = 4, kScanTileBoards = kScanThreads * kScanPerThread;
+
+// exclusive scan of one value per thread over the CTA; returns the CTA total through `total`
+template <int kThreads>
+__device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long* s_warp,
+                                                                   unsigned long long& total) {
+    const u32 FULL = 0xFFFFFFFFu, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    unsigned long long inc = v;
+#pragma unroll
+    for (u32 d = 1; d < 32u; d <<= 1) {
+        const unsigned long long x = __shfl_up_sync(FULL, inc, d);
+        if (lane >= d) inc += x;
+    }
+    if (lane == 31u) s_warp[w] = inc;
+    __syncthreads();
+    unsigned long long warp_off = 0ull;
+    total = 0ull;
+    for (u32 k = 0; k < (u32)(kThreads / 32); ++k) {
+        warp_off += k < w ? s_warp[k] : 0ull;
+        total += s_warp[k];
+    }
+    __syncthreads();  // s_warp may be reused by the caller's next scan
+    return warp_off + inc - v;
+}
+
+__device__ __forceinline__ uint4 load_counts4(const uint8_t* child_count, size_t board, size_t n) {
+    // child counts of boards board .. board + 3 (4 bytes each), zero past the end
+    if (board + 4 <= n) return *reinterpret_cast<const uint4*>(child_count + board * 4);
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    const u32* c = reinterpret_cast<const u32*>(child_count);
+    if (board < n) r.x = c[board];
+    if (board + 1 < n) r.y = c[board + 1];
+    if (board + 2 < n) r.z = c[board + 2];
+    return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint8_t* __restrict__ child_count,
+                                                                      unsigned long long* __restrict__ tile_sums,
+                                                                      size_t n, size_t tiles) {
+    __shared__ unsigned long long s_warp[kScanThreads / 32];
+    for (size_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const uint4 c = load_counts4(child_count, t * kScanTileBoards + threadIdx.x * kScanPerThread, n);
+        unsigned long long total;
+        block_exclusive_scan<kScanThreads>(sum_bytes4(c.x) + sum_bytes4(c.y) + sum_bytes4(c.z) + sum_bytes4(c.w),
+                                           s_warp, total);
+        if (threadIdx.x == 0) tile_sums[t] = total;
+    }
+}
+
+// one CTA: exclusive scan of the tile sums in place, chunk by chunk with a running carry
+__global__ void __launch_bounds__(1024) scan_top_kernel(unsigned long long* __restrict__ tile_sums, size_t tiles,
+                                                        size_t capacity, unsigned long long* __restrict__ total_out) {
+    __shared__ unsigned long long s_warp[32];
+    unsigned long long carry = 0ull;
+    for (size_t base = 0; base < tiles; base += 1024) {
+        const size_t j = base + threadIdx.x;
+        const unsigned long long v = j < tiles ? tile_sums[j] : 0ull;
+        unsigned long long total;
+        const unsigned long long ex = block_exclusive_scan<1024>(v, s_warp, total);
+        if (j < tiles) tile_sums[j] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0 && total_out) {
+        total_out[0] = carry;
+        total_out[1] = (capacity != 0 && carry > capacity) ? 1ull : 0ull;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint8_t* __restrict__ child_count,
+                                                                  const unsigned long long* __restrict__ tile_prefix,
+                                                                  int64_t* __restrict__ offsets, size_t n, size_t tiles) {
+    __shared__ unsigned long long s_warp[kScanThreads / 32];
+    for (size_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const size_t board = t * kScanTileBoards + threadIdx.x * kScanPerThread;
+        const uint4 c = load_counts4(child_count, board, n);
+        const u32 t0 = sum_bytes4(c.x), t1 = sum_bytes4(c.y), t2 = sum_bytes4(c.z), t3 = sum_bytes4(c.w);
+        unsigned long long total;
+        const unsigned long long ex = tile_prefix[t] + block_exclusive_scan<kScanThreads>(t0 + t1 + t2 + t3, s_warp, total);
+        if (board < n) offsets[board] = (int64_t)ex;
+        if (board + 1 < n) offsets[board + 1] = (int64_t)(ex + t0);
+        if (board + 2 < n) offsets[board + 2] = (int64_t)(ex + t0 + t1);
+        if (board + 3 < n) offsets[board + 3] = (int64_t)(ex + t0 + t1 + t2);
+    }
 }
 
 constexpr size_t kExpandSmemMinBoards = (size_t)1 << 17;
@@ -1471,6 +1673,71 @@ extern "C" int g2048_expand_children(const uint64_t* after, const uint8_t* child
                  const_cast<uint8_t*>(child_count), reinterpret_cast<u64*>(children), child_offsets,
                  child_layout, n, s->table, s->table_hashed, 1u};
     return launch_expand_children(a, s, (cudaStream_t)stream);
+}
+
+extern "C" int g2048_expand_compact(const uint64_t* boards, uint64_t* after, int32_t* rewards,
+                                    uint8_t* mask, uint8_t* num_empty, uint8_t* child_count,
+                                    int64_t* child_offsets, uint64_t* children, size_t capacity,
+                                    uint64_t* total_out, size_t n, void* stream) {
+    if (n == 0) {
+        if (total_out) CU(cudaMemsetAsync(total_out, 0, 16, (cudaStream_t)stream));
+        return G2048_OK;
+    }
+    if (!boards || !children || !child_offsets || capacity == 0) return G2048_EINVAL;
+    if (!aligned(after, 16) || !aligned(rewards, 16) || !aligned(num_empty, 4) || !aligned(child_count, 4) ||
+        !aligned(children, 16) || !aligned(child_offsets, 8) || !aligned(total_out, 8))
+        return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* tot = reinterpret_cast<unsigned long long*>(total_out);
+    if (n < kExpandSmemMinBoards) {
+        const size_t tiles = (n + kScanWarps * 32 - 1) / (kScanWarps * 32);
+        unsigned long long* scratch = nullptr;
+        CU(cudaMallocAsync(&scratch, (tiles + 2) * sizeof(unsigned long long), st));
+        auto launch = [&]() -> int {
+            CU(cudaMemsetAsync(scratch, 0, (tiles + 2) * sizeof(unsigned long long), st));
+            const ExpandArgs a{reinterpret_cast<const u64*>(boards), reinterpret_cast<u64*>(after), rewards, mask,
+                               num_empty, child_count, reinterpret_cast<u64*>(children), nullptr,
+                               G2048_CHILDREN_COMPACT, n, s->table, s->table_hashed, 1u, child_offsets, capacity};
+            expand_compact_fused_kernel<<<(unsigned)tiles, kScanWarps * 32, 0, st>>>(a, scratch, tot);
+            CU(cudaGetLastError());
+            return G2048_OK;
+        };
+        rc = launch();
+        const cudaError_t fe = cudaFreeAsync(scratch, st);
+        if (rc == G2048_OK && fe != cudaSuccess) return cuda_fail(fe, "cudaFreeAsync(scratch)");
+        return rc;
+    }
+    // large batch: moves -> scan of the child totals -> children
+    const size_t tiles = (n + kScanTileBoards - 1) / kScanTileBoards;
+    unsigned char* scratch = nullptr;  // [tile sums | afterstates | child counts] as needed
+    const size_t sums_bytes = (tiles * 8 + 15) / 16 * 16;
+    const size_t need = sums_bytes + (after ? 0 : n * 32) + (child_count ? 0 : n * 4);
+    CU(cudaMallocAsync(&scratch, need, st));
+    auto launch = [&]() -> int {
+        unsigned long long* sums = reinterpret_cast<unsigned long long*>(scratch);
+        u64* after_buf = after ? reinterpret_cast<u64*>(after) : reinterpret_cast<u64*>(scratch + sums_bytes);
+        uint8_t* count_buf = child_count ? child_count : scratch + sums_bytes + (after ? 0 : n * 32);
+        ExpandArgs a{reinterpret_cast<const u64*>(boards), after_buf, rewards, mask, num_empty, count_buf,
+                     reinterpret_cast<u64*>(children), child_offsets, G2048_CHILDREN_COMPACT, n, s->table,
+                     s->table_hashed, 1u, child_offsets, capacity};
+        CU(cudaFuncSetAttribute(expand_moves_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(kSmemTableBytes + 64u)));
+        expand_moves_smem_kernel<<<s->sms, 1024, kSmemTableBytes + 64u, st>>>(a);
+        CU(cudaGetLastError());
+        const int sgrid = (int)(tiles < (size_t)s->sms * 8 ? tiles : (size_t)s->sms * 8);
+        scan_tile_sums_kernel<<<sgrid, kScanThreads, 0, st>>>(count_buf, sums, n, tiles);
+        scan_top_kernel<<<1, 1024, 0, st>>>(sums, tiles, capacity, tot);
+        scan_apply_kernel<<<sgrid, kScanThreads, 0, st>>>(count_buf, sums, child_offsets, n, tiles);
+        CU(cudaGetLastError());
+        return launch_expand_children(a, s, st);
+    };
+    rc = launch();
+    const cudaError_t fe = cudaFreeAsync(scratch, st);
+    if (rc == G2048_OK && fe != cudaSuccess) return cuda_fail(fe, "cudaFreeAsync(scratch)");
+    return rc;
 }
 
 // Warp-cooperative: a warp takes 32 boards = 8 KiB of children; lane l serves the FIXED rank
@@ -1655,13 +1922,13 @@ extern "C" int g2048_nstep_returns(const float* rewards, const float* values, co
 }
 
 // ---------------------------------------------------------------------------------------------
-// fused random rollout: board, score, step counter live in registers until the game ends
+// fused random rollout: boards, scores and step counters live in registers until the game ends
 // ---------------------------------------------------------------------------------------------
 struct RolloutArgs {
     u64 seed, env_offset;
     size_t n;
+    size_t per_queue;  // env ids per CTA queue (roll_fetch)
     u32 max_steps;
-    int from_reset;
     u64* boards_io;
     int64_t* score_out;
     int32_t* steps_out;
@@ -1675,187 +1942,279 @@ struct RolloutArgs {
     PhiloxKeys keys;
 };
 
-// idx-th set bit (0-based) of a 4-bit mask
-__device__ __forceinline__ u32 pick_action(u32 mask, u32 idx) {
-    for (u32 i = 0; i < idx; ++i) mask &= mask - 1u;
-    return __ffs(mask) - 1u;
-}
-
-// Persistent lanes: every loop iteration is ONE game step for each lane that holds a live
-// game, so the step code runs convergent; lanes whose game ended pull the next env id at the
-// top of the loop (one warp-aggregated atomic for all lanes that need one).  Results are
-// keyed by the global env id and step, so they do not depend on which lane played the game.
-//
-// The step itself is the fast transition of g2048_fast.cuh (hashed table + per-action
-// orientation words in shared memory); boards holding a tile >= 16384 take the exact path.
-// pick[mask * 4 + k] = k-th legal action of `mask` (64-byte table, branch-free policy).
-struct RolloutSmem {
-    const u32* tab;          // hashed row table (fast path)
-    const uint4* orient;     // per-action orientation words
-    const uint8_t* pick;     // action pick table
-    u64* stats;              // per-CTA statistics (or nullptr)
-};
-
-__device__ __noinline__ uint4 rollout_move_slow(u64 board, u32 action, const u32* __restrict__ table) {
-    MoveResult m = move_action(split(board), action, GlobalTable{table});
-    return make_uint4(m.after.lo, m.after.hi, m.score, m.overflow ? 1u : 0u);
-}
-
-template <bool kFast>
-__device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RolloutSmem& sm,
-                                             unsigned long long* next) {
-    const u32 lane = threadIdx.x & 31u;
-    const u32 FULL = 0xFFFFFFFFu;
-    const u32 one = a.one;
-    bool active = false, exhausted = false;
-    size_t i = 0;
-    u64 env = 0, score = 0;
-    u32 lo = 0, hi = 0;
-    // phase 0 / 1: the two reset tiles are still to be placed (Philox tags 1 / 2, no move);
-    // phase 2: playing.  A new game therefore costs two ordinary loop iterations instead of a
-    // divergent reset path, and every lane of the warp runs the same instructions.
-    u32 phase = 2, step = 0, ovf = 0, mask = 0, nlo = 0, nhi = 0;
-    // per-lane statistics, flushed once at the end (the histogram goes to shared memory)
-    u64 st_steps = 0, st_score = 0, st_maxscore = 0;
-    u32 st_eps = 0, st_maxsteps = 0, st_capped = 0, st_ovf = 0;
-    const SmemLut lut{};
-    for (;;) {
-        const u32 need = __ballot_sync(FULL, !active && !exhausted);
-        if (need) {
-            unsigned long long base = 0;
-            const u32 leader = __ffs(need) - 1u;
-            if (lane == leader) base = atomicAdd(next, (unsigned long long)__popc(need));
-            base = __shfl_sync(FULL, base, leader);
-            if (!active && !exhausted) {
-                i = (size_t)base + __popc(need & ((1u << lane) - 1u));
-                if (i < a.n) {
-                    env = a.env_offset + i;
-                    score = 0;
-                    step = 0;
-                    ovf = 0;
-                    if (a.from_reset) {
-                        lo = hi = nlo = nhi = mask = 0u;
-                        phase = 0;
-                    } else {
-                        const Board b = split(a.boards_io[i]);
-                        lo = b.lo;
-                        hi = b.hi;
-                        nlo = fast::nz8(lo, one);
-                        nhi = fast::nz8(hi, one);
-                        mask = fast::legal_mask(lo, hi, nlo, nhi, one);
-                        phase = 2;
-                    }
-                    active = true;
-                } else {
-                    exhausted = true;
-                }
-            }
-        }
-        if (!__any_sync(FULL, active)) break;
-        if (!active) continue;
-        const bool playing = phase >= 2u;
-        if (playing && (mask == 0u || step >= a.max_steps)) {  // game over: emit the episode
-            if (a.trace) a.trace[i * a.trace_stride + min(step, a.trace_stride - 1u)] = 0;
-            const u32 mx = max_exponent(Board{lo, hi});
-            if (a.boards_io) a.boards_io[i] = ((u64)hi << 32) | lo;
-            if (a.score_out) a.score_out[i] = (int64_t)score;
-            if (a.steps_out) a.steps_out[i] = (int32_t)step;
-            if (a.maxexp_out) a.maxexp_out[i] = (uint8_t)mx;
-            if (sm.stats) atomicAdd(&sm.stats[8 + mx], 1ull);
-            st_eps += 1u;
-            st_steps += step;
-            st_score += score;
-            st_maxscore = max(st_maxscore, score);
-            st_maxsteps = max(st_maxsteps, step);
-            st_capped += (mask != 0u) ? 1u : 0u;
-            st_ovf += ovf;
-            active = false;
-            continue;
-        }
-        // one iteration: Philox draw; (playing) uniform-legal action + move; spawn; new mask
-        const Philox4 p = philox_env(a.keys, env, step, playing ? G2048_PHILOX_TAG_STEP : G2048_PHILOX_TAG_RESET0 + phase);
-        const u32 action = sm.pick[mask * 4u + __umulhi(p.z, (u32)__popc(mask))];
-        u32 al, ah, reward;
-        if (kFast && !fast::has_big_tile(lo, hi)) {
-            const uint4 o0 = sm.orient[2u * action];
-            fast::Orient o;
-            o.mask = o0.x; o.mul_hi = o0.y; o.mul_lo = o0.z; o.sel_lo = o0.w;
-            o.sel_hi = sm.orient[2u * action + 1u].x;
-            bool moved;
-            reward = fast::move_fast(lo, hi, o, lut, one, al, ah, moved);
-        } else {
-            const uint4 r = rollout_move_slow(((u64)hi << 32) | lo, action, a.table);
-            al = r.x; ah = r.y; reward = r.z; ovf |= playing ? r.w : 0u;
-        }
-        if (!playing) { al = lo; ah = hi; reward = 0u; }  // reset iterations only spawn
-        score += reward;
-        nlo = fast::nz8(al, one);
-        nhi = fast::nz8(ah, one);
-        const u32 tiles_lo = fast::popc(nlo), ne = 16u - (tiles_lo + fast::popc(nhi));
-        bool in_hi;
-        const u32 bit3 = fast::spawn_marker(nlo, nhi, tiles_lo, __umulhi(p.x, ne), one, in_hi);
-        const u32 exp = 2u - fast::nonzero01(__umulhi(p.y, 10u));  // word1 < 0x1999999A -> 4
-        const u32 tile = fast::shr<3>(bit3) * exp;
-        if (in_hi) { ah += tile; nhi += bit3; } else { al += tile; nlo += bit3; }
-        lo = al;
-        hi = ah;
-        if (playing && a.trace && step + 1u < a.trace_stride) {
-            const u32 cell = ((__ffs(bit3) - 1u) >> 2) + (in_hi ? 8u : 0u);
-            a.trace[i * a.trace_stride + step] =
-                (uint8_t)(0x80u | action | (cell << 2) | ((exp - 1u) << 6));
-        }
-        if (playing) ++step; else ++phase;
-        mask = fast::legal_mask(lo, hi, nlo, nhi, one);
-    }
-    if (sm.stats) {  // one flush per lane (warp-reduced first)
-        for (int off = 16; off; off >>= 1) {
-            st_eps += __shfl_xor_sync(FULL, st_eps, off);
-            st_steps += __shfl_xor_sync(FULL, st_steps, off);
-            st_score += __shfl_xor_sync(FULL, st_score, off);
-            st_capped += __shfl_xor_sync(FULL, st_capped, off);
-            st_ovf += __shfl_xor_sync(FULL, st_ovf, off);
-            st_maxscore = max(st_maxscore, (u64)__shfl_xor_sync(FULL, st_maxscore, off));
-            st_maxsteps = max(st_maxsteps, __shfl_xor_sync(FULL, st_maxsteps, off));
-        }
-        if (lane == 0) {
-            atomicAdd(&sm.stats[0], (u64)st_eps);
-            atomicAdd(&sm.stats[1], st_steps);
-            atomicAdd(&sm.stats[2], st_score);
-            atomicMax(&sm.stats[3], st_maxscore);
-            atomicMax(&sm.stats[4], (u64)st_maxsteps);
-            atomicAdd(&sm.stats[5], (u64)st_capped);
-            atomicAdd(&sm.stats[6], (u64)st_ovf);
-        }
-    }
-}
-
-// pick[mask * 4 + k] = k-th set bit of the 4-bit mask
+// pick[mask * 4 + k] = k-th set bit of the 4-bit mask (branch-free policy)
 __constant__ uint8_t c_pick[64] = {
     0, 0, 0, 0,  0, 0, 0, 0,  1, 0, 0, 0,  0, 1, 0, 0,  2, 0, 0, 0,  0, 2, 0, 0,  1, 2, 0, 0,  0, 1, 2, 0,
     3, 0, 0, 0,  0, 3, 0, 0,  1, 3, 0, 0,  0, 1, 3, 0,  2, 3, 0, 0,  0, 2, 3, 0,  1, 2, 3, 0,  0, 1, 2, 3};
 
-template <bool kSmem>
-__global__ void __launch_bounds__(1024, 1) rollout_kernel(const RolloutArgs a, unsigned long long* next) {
+// largest nibble of a board: byte-wise maxima of the even and odd nibbles (VIMNMX on packed bytes)
+__device__ __forceinline__ u32 max_exponent_fast(u32 lo, u32 hi) {
+    const u32 m4 = __vmaxu4(__vmaxu4(lo & 0x0F0F0F0Fu, (lo >> 4) & 0x0F0F0F0Fu),
+                            __vmaxu4(hi & 0x0F0F0F0Fu, (hi >> 4) & 0x0F0F0F0Fu));
+    const u32 m2 = __vmaxu4(m4, m4 >> 16);
+    return max(m2 & 0xFFu, (m2 >> 8) & 0xFFu);
+}
+
+// Exact out-of-line move for boards holding a tile >= 16384 (the branch-free register row move of
+// g2048_device.cuh, which also reports a 15+15 merge exactly).
+__device__ __noinline__ uint4 rollout_move_slow(u32 lo, u32 hi, u32 action) {
+    const MoveResult m = move_action(Board{lo, hi}, action, RegisterTable{});
+    return make_uint4(m.after.lo, m.after.hi, m.score, m.overflow ? 1u : 0u);
+}
+
+// Every lane plays kRollSlots games at once, one step of each per loop iteration: the two
+// dependent chains interleave (ILP 2 with 4 warps per scheduler instead of ILP 1 with 8), and a
+// game that ends is replaced at once from the global queue inside the (rare, divergent) episode
+// branch — no vote and no idle iteration on the common path.  Results are keyed by the global env
+// id and step, so they do not depend on which lane or slot played a game.
+//
+// One step (roll_step) = the fast transition of g2048_fast.cuh with the action drawn one step
+// ahead: the word of (env, step) places the tile (digits 1, 2) and, once the mask of the new board
+// is known, picks the NEXT action (digit 3) — so the policy costs one IMAD.HI and one LDS.  The two
+// reset tiles run through the same code as phases t = 0, 1 (Philox tags 1, 2, no move): a new game
+// costs two ordinary iterations instead of a divergent reset path.
+constexpr int kRollSlots = 2;
+
+struct RollSlot {
+    u32 lo, hi;     // board
+    u32 act;        // action of the next step (already drawn)
+    u32 t;          // 0, 1: reset tiles still to place; t >= 2: playing step t - 2
+    u32 qlo, qhi;   // Philox counter words 0, 1 = quad of the global env id
+    u32 j;          // env & 3: the word of the block this env reads
+    u32 ovf;
+    u64 score;
+    bool alive;
+};
+
+struct RollStats {  // per lane, flushed once at the end
+    u64 steps, score, maxscore;
+    u32 eps, maxsteps, capped, ovf;
+};
+
+struct RollShared {
+    const uint4* orient;  // per-action orientation words
+    const uint8_t* pick;  // action pick table
+    u32* hist;            // max-tile histogram of the CTA
+    u32* hint;            // queues this CTA has found empty (roll_fetch)
+};
+
+__device__ __forceinline__ u64 roll_env(const RollSlot& s) {
+    return ((u64)s.qhi << 34) | ((u64)s.qlo << 2) | s.j;
+}
+
+// the episode of slot `s` is over: write its results
+template <bool kTrace>
+__device__ __forceinline__ void roll_emit(const RollSlot& s, u32 mask, const RolloutArgs& a,
+                                          const RollShared& sm, RollStats& st) {
+    const size_t i = (size_t)(roll_env(s) - a.env_offset);
+    const u32 step = s.t - 2u;
+    if (kTrace) a.trace[i * a.trace_stride + min(step, a.trace_stride - 1u)] = 0;
+    const u32 mx = max_exponent_fast(s.lo, s.hi);
+    if (a.boards_io) a.boards_io[i] = ((u64)s.hi << 32) | s.lo;
+    if (a.score_out) a.score_out[i] = (int64_t)s.score;
+    if (a.steps_out) a.steps_out[i] = (int32_t)step;
+    if (a.maxexp_out) a.maxexp_out[i] = (uint8_t)mx;
+    if (sm.hist) atomicAdd(&sm.hist[mx], 1u);
+    st.eps += 1u;
+    st.steps += step;
+    st.score += s.score;
+    st.maxscore = max(st.maxscore, s.score);
+    st.maxsteps = max(st.maxsteps, step);
+    st.capped += (mask != 0u) ? 1u : 0u;
+    st.ovf += s.ovf;
+}
+
+// Next game for slot `s`.  The env range is cut into one queue per CTA (a counter each, `per`
+// consecutive ids): a CTA drains its own queue and then steals single ids from the others, so the
+// balance is that of one global queue while no counter is hit by more than one SM until the very
+// end.  (One counter for the whole grid serialises in L2: ~0.7 G atomics/s on one address capped
+// both the round-1 kernel and this one at ~92 G env-steps/s, `long_scoreboard` the top stall.)
+// `hint` (shared) = number of queues this CTA has already found empty.
+// kFromReset: the game starts on the empty board in phase 0.  Otherwise it starts from boards_io
+// with the first action drawn from the word of tag 3; a board that is already over is emitted here.
+template <bool kFromReset, bool kTrace>
+__device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, const RollShared& sm,
+                                           unsigned long long* next, RollStats& st) {
+    for (;;) {
+        size_t i = 0;
+        bool got = false;
+        for (;;) {
+            const u32 h = *reinterpret_cast<volatile u32*>(sm.hint);
+            if (h >= gridDim.x) break;
+            u32 q = blockIdx.x + h;
+            if (q >= gridDim.x) q -= gridDim.x;
+            const size_t lo = (size_t)q * a.per_queue;
+            const unsigned long long k = atomicAdd(&next[q], 1ull);
+            if (k < a.per_queue && lo + k < a.n) {
+                i = lo + (size_t)k;
+                got = true;
+                break;
+            }
+            atomicMax(sm.hint, h + 1u);
+        }
+        s.lo = s.hi = s.act = s.t = s.ovf = 0u;
+        s.score = 0;
+        if (!got) {
+            s.alive = false;
+            s.qlo = s.qhi = s.j = 0u;
+            return;
+        }
+        const u64 env = a.env_offset + i;
+        s.qlo = (u32)(env >> 2);
+        s.qhi = (u32)(env >> 34);
+        s.j = (u32)env & 3u;
+        s.alive = true;
+        if (kFromReset) return;
+        const Board b = split(a.boards_io[i]);
+        s.lo = b.lo;
+        s.hi = b.hi;
+        s.t = 2u;
+        const u32 mask = fast::legal_mask(b.lo, b.hi, fast::nz8(b.lo, a.one), fast::nz8(b.hi, a.one), a.one);
+        const u32 w = philox_word(a.keys, env, 0u, G2048_PHILOX_TAG_START);
+        s.act = sm.pick[mask * 4u + __umulhi(w, (u32)__popc(mask))];
+        if (mask != 0u && a.max_steps != 0u) return;
+        roll_emit<kTrace>(s, mask, a, sm, st);  // nothing to play
+    }
+}
+
+// one step (or reset phase) of slot `s`; returns the legal mask of the new board
+template <bool kTrace, class Lut>
+__device__ __forceinline__ u32 roll_step(RollSlot& s, const RolloutArgs& a, const RollShared& sm,
+                                         const Lut& lut) {
+    const u32 one = a.one;
+    const bool playing = s.t >= 2u;
+    const Philox4 p = philox4x32_10(s.qlo, s.qhi, playing ? s.t - 2u : 0u,
+                                    playing ? G2048_PHILOX_TAG_STEP : s.t + 1u, a.keys);
+    const u32 w = philox_pick(p, s.j);
+    u32 al, ah, reward;
+    // The fast move runs unconditionally — on the empty board when some tile is >= 16384 (such a
+    // row lies outside the staged table window) — and the exact out-of-line move then replaces
+    // its result.  The test is plain C: the lop3 asm of fast::has_big_tile crashes ptxas 12.9
+    // (SIGSEGV) once two slots are unrolled in this kernel.
+    const bool big = ((((s.lo << 1) & (s.lo << 2) & s.lo) | ((s.hi << 1) & (s.hi << 2) & s.hi)) & 0x88888888u) != 0u;
+    {
+        const uint4 o0 = sm.orient[2u * s.act];
+        fast::Orient o;
+        o.mask = o0.x; o.mul_hi = o0.y; o.mul_lo = o0.z; o.sel_lo = o0.w;
+        o.sel_hi = sm.orient[2u * s.act + 1u].x;
+        bool moved;
+        reward = fast::move_fast(big ? 0u : s.lo, big ? 0u : s.hi, o, lut, one, al, ah, moved);
+    }
+    if (big) {
+        const uint4 r = rollout_move_slow(s.lo, s.hi, s.act);
+        al = r.x; ah = r.y; reward = r.z;
+        s.ovf |= playing ? r.w : 0u;
+    }
+    if (!playing) { al = s.lo; ah = s.hi; reward = 0u; }  // reset phases only spawn
+    s.score += reward;
+    u32 nlo = fast::nz8(al, one), nhi = fast::nz8(ah, one);
+    const u32 tiles_lo = fast::popc(nlo), ne = 16u - (tiles_lo + fast::popc(nhi));
+    u32 rank, f1, tenth, f2;
+    fast::mul_wide(w, ne, rank, f1);      // digit 1: spawn rank
+    fast::mul_wide(f1, 10u, tenth, f2);   // digit 2: 0 -> tile 4
+    bool in_hi;
+    const u32 bit3 = fast::spawn_marker(nlo, nhi, tiles_lo, rank, one, in_hi);
+    const u32 exp = 2u - fast::nonzero01(tenth);
+    const u32 tile = fast::shr<3>(bit3) * exp;
+    if (in_hi) { ah += tile; nhi += bit3; } else { al += tile; nlo += bit3; }
+    if (kTrace) {
+        const u32 step = s.t - 2u;
+        if (playing && step + 1u < a.trace_stride) {
+            const u32 cell = ((__ffs(bit3) - 1u) >> 2) + (in_hi ? 8u : 0u);
+            a.trace[(size_t)(roll_env(s) - a.env_offset) * a.trace_stride + step] =
+                (uint8_t)(0x80u | s.act | (cell << 2) | ((exp - 1u) << 6));
+        }
+    }
+    const u32 mask = fast::legal_mask(al, ah, nlo, nhi, one);
+    // digit 3: the next action, the k-th legal one of the new board
+    const u32 act = sm.pick[mask * 4u + fast::mulhi(f2, fast::popc(mask))];
+    // a slot without a game stays frozen on the empty board
+    s.lo = s.alive ? al : 0u;
+    s.hi = s.alive ? ah : 0u;
+    s.t = s.alive ? s.t + 1u : 0u;
+    s.act = act;
+    return mask;
+}
+
+template <bool kFromReset, bool kTrace, class Lut>
+__device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RollShared& sm, const Lut& lut,
+                                             unsigned long long* next, u64* sh_stats) {
+    RollStats st{0ull, 0ull, 0ull, 0u, 0u, 0u, 0u};
+    RollSlot slot[kRollSlots];
+#pragma unroll
+    for (int k = 0; k < kRollSlots; ++k) roll_fetch<kFromReset, kTrace>(slot[k], a, sm, next, st);
+    for (;;) {
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < kRollSlots; ++k) any |= slot[k].alive;
+        if (!any) break;
+        u32 mask[kRollSlots];
+#pragma unroll
+        for (int k = 0; k < kRollSlots; ++k) mask[k] = roll_step<kTrace>(slot[k], a, sm, lut);
+#pragma unroll
+        for (int k = 0; k < kRollSlots; ++k) {
+            RollSlot& s = slot[k];
+            if (s.t >= 2u && (mask[k] == 0u || s.t - 2u >= a.max_steps)) {  // a frozen slot has t = 0
+                roll_emit<kTrace>(s, mask[k], a, sm, st);
+                roll_fetch<kFromReset, kTrace>(s, a, sm, next, st);
+            }
+        }
+    }
+    if (sh_stats) {  // one flush per warp
+        const u32 FULL = 0xFFFFFFFFu;
+        for (int off = 16; off; off >>= 1) {
+            st.eps += __shfl_xor_sync(FULL, st.eps, off);
+            st.steps += __shfl_xor_sync(FULL, st.steps, off);
+            st.score += __shfl_xor_sync(FULL, st.score, off);
+            st.capped += __shfl_xor_sync(FULL, st.capped, off);
+            st.ovf += __shfl_xor_sync(FULL, st.ovf, off);
+            st.maxscore = max(st.maxscore, (u64)__shfl_xor_sync(FULL, st.maxscore, off));
+            st.maxsteps = max(st.maxsteps, __shfl_xor_sync(FULL, st.maxsteps, off));
+        }
+        if ((threadIdx.x & 31u) == 0u) {
+            atomicAdd(&sh_stats[0], (u64)st.eps);
+            atomicAdd(&sh_stats[1], st.steps);
+            atomicAdd(&sh_stats[2], st.score);
+            atomicMax(&sh_stats[3], st.maxscore);
+            atomicMax(&sh_stats[4], (u64)st.maxsteps);
+            atomicAdd(&sh_stats[5], (u64)st.capped);
+            atomicAdd(&sh_stats[6], (u64)st.ovf);
+        }
+    }
+}
+
+template <bool kSmem, bool kFromReset, bool kTrace, int kThreads>
+__global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutArgs a, unsigned long long* next) {
     __shared__ u64 sh_stats[G2048_STATS_WORDS];
+    __shared__ u32 sh_hist[16];
     __shared__ __align__(16) uint4 sh_orient[8];
     __shared__ uint8_t sh_pick[64];
+    __shared__ u32 sh_hint;
     u64* bar = reinterpret_cast<u64*>(smem_words + kSmemRows);
     if (kSmem) table_stage_begin(smem_words, bar, a.table_hashed);
+    if (threadIdx.x == 0) sh_hint = 0u;
     if (threadIdx.x < G2048_STATS_WORDS) sh_stats[threadIdx.x] = 0;
+    if (threadIdx.x < 16) sh_hist[threadIdx.x] = 0;
     if (threadIdx.x < 32) reinterpret_cast<u32*>(sh_orient)[threadIdx.x] = reinterpret_cast<const u32*>(c_orient)[threadIdx.x];
     if (threadIdx.x < 64) sh_pick[threadIdx.x] = c_pick[threadIdx.x];
     if (kSmem) table_stage_wait(bar); else __syncthreads();
 
-    const RolloutSmem sm{smem_words, sh_orient, sh_pick, a.stats ? sh_stats : nullptr};
-    rollout_loop<kSmem>(a, sm, next);
+    const RollShared sm{sh_orient, sh_pick, a.stats ? sh_hist : nullptr, &sh_hint};
+    if (kSmem) rollout_loop<kFromReset, kTrace>(a, sm, SmemLut{}, next, a.stats ? sh_stats : nullptr);
+    else rollout_loop<kFromReset, kTrace>(a, sm, GlobalLut{a.table_hashed}, next, a.stats ? sh_stats : nullptr);
 
     __syncthreads();
     if (a.stats && threadIdx.x < G2048_STATS_WORDS) {
-        const u64 v = sh_stats[threadIdx.x];
+        const u64 v = threadIdx.x >= 8 ? (u64)sh_hist[threadIdx.x - 8] : sh_stats[threadIdx.x];
         if (threadIdx.x == 3 || threadIdx.x == 4) atomicMax(&a.stats[threadIdx.x], v);
         else if (v) atomicAdd(&a.stats[threadIdx.x], v);
     }
 }
+
+// persistent, one CTA per SM, table in shared memory: 768 threads x 2 slots at 85 registers
+// (environment G2048_ROLL_THREADS=512 selects the smaller CTA; a tuning knob for measurements)
+static int g_roll_threads = [] { const char* e = getenv("G2048_ROLL_THREADS"); return (e && atoi(e) == 512) ? 512 : 768; }();
+constexpr int kRollSmallThreads = 128;  // small batches: table gathered from L2
 
 extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint32_t max_steps,
                              int from_reset, uint64_t* boards_io, int64_t* score_out,
@@ -1868,22 +2227,39 @@ extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint3
     int rc = current_state(&s);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    RolloutArgs a{seed, env_offset, n, max_steps, from_reset, reinterpret_cast<u64*>(boards_io),
-                  score_out, steps_out, maxexp_out, reinterpret_cast<u64*>(stats_out), trace,
-                  trace_stride, s->table, s->table_hashed, 1u, philox_key_schedule(seed)};
-    unsigned long long* next = nullptr;
-    CU(cudaMallocAsync(&next, sizeof(unsigned long long), st));
-    auto launch = [&]() -> int {  // in a helper so that the counter is released on every path
-        CU(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
-        const bool smem = n >= (size_t)s->sms * 512 && s->smem_optin >= kSmemTableBytes + 64;
-        if (smem) {
-            const int bytes = (int)kSmemTableBytes + 64;
-            CU(cudaFuncSetAttribute(rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-            rollout_kernel<true><<<s->sms, 1024, bytes, st>>>(a, next);
-        } else {
-            int grid = grid_for(n, 512, s->sms, 1);
-            rollout_kernel<false><<<grid, 512, 0, st>>>(a, next);
-        }
+    const bool smem = n >= (size_t)s->sms * 512 && s->smem_optin >= kSmemTableBytes + 64;
+    const int bytes = smem ? (int)kSmemTableBytes + 64 : 0;
+    const int threads = smem ? g_roll_threads : kRollSmallThreads;
+    const int grid = smem ? s->sms : grid_for((n + kRollSlots - 1) / kRollSlots, kRollSmallThreads, s->sms, 8);
+    RolloutArgs a{seed, env_offset, n, (n + (size_t)grid - 1) / (size_t)grid, max_steps,
+                  reinterpret_cast<u64*>(boards_io), score_out, steps_out, maxexp_out,
+                  reinterpret_cast<u64*>(stats_out), trace, trace_stride, s->table, s->table_hashed, 1u,
+                  philox_key_schedule(seed)};
+    unsigned long long* next = nullptr;  // one queue counter per CTA
+    CU(cudaMallocAsync(&next, (size_t)grid * sizeof(unsigned long long), st));
+    auto launch = [&]() -> int {  // in a helper so that the counters are released on every path
+        CU(cudaMemsetAsync(next, 0, (size_t)grid * sizeof(unsigned long long), st));
+#define G2048_LAUNCH_ROLL(SM, FR, TR, TH)                                                                  \
+    do {                                                                                                   \
+        if (SM) CU(cudaFuncSetAttribute(rollout_kernel<SM, FR, TR, TH>,                                    \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));              \
+        rollout_kernel<SM, FR, TR, TH><<<grid, threads, bytes, st>>>(a, next);                             \
+    } while (0)
+#define G2048_LAUNCH_ROLL_T(SM, TH)                                   \
+    do {                                                              \
+        if (from_reset) {                                             \
+            if (trace) G2048_LAUNCH_ROLL(SM, true, true, TH);         \
+            else G2048_LAUNCH_ROLL(SM, true, false, TH);              \
+        } else {                                                      \
+            if (trace) G2048_LAUNCH_ROLL(SM, false, true, TH);        \
+            else G2048_LAUNCH_ROLL(SM, false, false, TH);             \
+        }                                                             \
+    } while (0)
+        if (smem && threads == 768) G2048_LAUNCH_ROLL_T(true, 768);
+        else if (smem) G2048_LAUNCH_ROLL_T(true, 512);
+        else G2048_LAUNCH_ROLL_T(false, kRollSmallThreads);
+#undef G2048_LAUNCH_ROLL_T
+#undef G2048_LAUNCH_ROLL
         CU(cudaGetLastError());
         return G2048_OK;
     };
@@ -1921,11 +2297,11 @@ extern "C" int g2048_row_table_host(uint16_t* result, uint32_t* reward, uint8_t*
     row_table_kernel<<<kRows / 256, 256>>>(d_res, d_rew, d_mv);
     CU(cudaGetLastError());
     // cross-check the packed entries actually used by the kernels
-    static u32 h_tab[kRows];
+    std::vector<u32> h_tab(kRows);
     CU(cudaMemcpy(result, d_res, kRows * 2, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(reward, d_rew, kRows * 4, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(moved, d_mv, kRows, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(h_tab, s->table, kRows * 4, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h_tab.data(), s->table, kRows * 4, cudaMemcpyDeviceToHost));
     cudaFree(d_res);
     cudaFree(d_rew);
     cudaFree(d_mv);
@@ -1938,38 +2314,127 @@ extern "C" int g2048_row_table_host(uint16_t* result, uint32_t* reward, uint8_t*
 }
 
 // ---------------------------------------------------------------------------------------------
-// host-buffer transition: chunked H2D -> kernel -> D2H pipeline over 3 streams
+// host-buffer transition: chunked H2D -> kernel -> D2H pipeline over 4 streams
 // ---------------------------------------------------------------------------------------------
 namespace {
 struct HostPipe {
     static constexpr int kSlots = 4;
     static constexpr size_t kChunk = (size_t)1 << 21;  // capacity of a slot (envs); the stage size is chosen at run time
-    bool ready = false;
-    cudaStream_t stream[kSlots];
-    uint64_t *d_in[kSlots], *d_out[kSlots];
-    uint8_t *d_act[kSlots], *d_spn[kSlots], *d_flg[kSlots];
-    int32_t* d_rew[kSlots];
+    int dev = -1;
+    cudaStream_t stream[kSlots] = {};
+    uint64_t *d_in[kSlots] = {}, *d_out[kSlots] = {};
+    uint8_t *d_act[kSlots] = {}, *d_spn[kSlots] = {}, *d_flg[kSlots] = {};
+    int32_t* d_rew[kSlots] = {};
 };
-thread_local HostPipe g_pipe[64];
 
-int pipe_get(HostPipe** out) {
+// Pool of pipes: a call takes one for its device (creating it on first use), returns it when done.
+// Concurrent callers each get their own; g2048_shutdown frees the pooled ones.
+std::mutex g_pipe_mu;
+std::vector<HostPipe*> g_pipes[64];
+
+void pipe_destroy(HostPipe* p) {
+    for (int i = 0; i < HostPipe::kSlots; ++i) {
+        if (p->stream[i]) cudaStreamDestroy(p->stream[i]);
+        cudaFree(p->d_in[i]); cudaFree(p->d_out[i]); cudaFree(p->d_act[i]);
+        cudaFree(p->d_spn[i]); cudaFree(p->d_flg[i]); cudaFree(p->d_rew[i]);
+    }
+    delete p;
+}
+
+int pipe_create(HostPipe* p) {
+    for (int i = 0; i < HostPipe::kSlots; ++i) {
+        CU(cudaStreamCreateWithFlags(&p->stream[i], cudaStreamNonBlocking));
+        CU(cudaMalloc(&p->d_in[i], HostPipe::kChunk * 8));
+        CU(cudaMalloc(&p->d_out[i], HostPipe::kChunk * 8));
+        CU(cudaMalloc(&p->d_act[i], HostPipe::kChunk));
+        CU(cudaMalloc(&p->d_spn[i], HostPipe::kChunk));
+        CU(cudaMalloc(&p->d_flg[i], HostPipe::kChunk));
+        CU(cudaMalloc(&p->d_rew[i], HostPipe::kChunk * 4));
+    }
+    return G2048_OK;
+}
+
+int pipe_acquire(HostPipe** out) {
     int dev = 0;
     CU(cudaGetDevice(&dev));
-    HostPipe& p = g_pipe[dev];
-    if (!p.ready) {
-        for (int i = 0; i < HostPipe::kSlots; ++i) {
-            CU(cudaStreamCreateWithFlags(&p.stream[i], cudaStreamNonBlocking));
-            CU(cudaMalloc(&p.d_in[i], HostPipe::kChunk * 8));
-            CU(cudaMalloc(&p.d_out[i], HostPipe::kChunk * 8));
-            CU(cudaMalloc(&p.d_act[i], HostPipe::kChunk));
-            CU(cudaMalloc(&p.d_spn[i], HostPipe::kChunk));
-            CU(cudaMalloc(&p.d_flg[i], HostPipe::kChunk));
-            CU(cudaMalloc(&p.d_rew[i], HostPipe::kChunk * 4));
+    if (dev < 0 || dev >= 64) return G2048_EINVAL;
+    {
+        std::lock_guard<std::mutex> lk(g_pipe_mu);
+        if (!g_pipes[dev].empty()) {
+            *out = g_pipes[dev].back();
+            g_pipes[dev].pop_back();
+            return G2048_OK;
         }
-        p.ready = true;
     }
-    *out = &p;
+    HostPipe* p = new HostPipe();
+    p->dev = dev;
+    const int rc = pipe_create(p);
+    if (rc) {
+        pipe_destroy(p);
+        return rc;
+    }
+    *out = p;
     return G2048_OK;
+}
+
+void pipe_release(HostPipe* p) {
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    g_pipes[p->dev].push_back(p);
+}
+
+// envs per pipeline stage (<= kChunk); environment G2048_HOST_CHUNK_LOG2 overrides
+size_t host_chunk() {
+    const char* e = getenv("G2048_HOST_CHUNK_LOG2");
+    const int lg = e ? atoi(e) : 21;
+    return (lg >= 12 && lg <= 21) ? ((size_t)1 << lg) : HostPipe::kChunk;
+}
+
+// kCompute = false: the same copies on the same streams without the kernel (the PCIe ceiling of
+// the call, g2048_step_host_copies)
+int step_host_impl(bool compute, const uint64_t* boards_in, const uint8_t* actions, const uint8_t* spawns,
+                   uint64_t seed, uint64_t env_offset, uint32_t step_base, uint64_t* boards_out,
+                   int32_t* rewards, uint8_t* flags, size_t n) {
+    if (n == 0) return G2048_OK;
+    if (!boards_in || !actions || !boards_out || !rewards || !flags) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    HostPipe* p;
+    rc = pipe_acquire(&p);
+    if (rc) return rc;
+    const size_t chunk = host_chunk();
+    auto run = [&]() -> int {
+        size_t done = 0;
+        int slot = 0;
+        while (done < n) {
+            const size_t m = (n - done < chunk) ? n - done : chunk;
+            cudaStream_t st = p->stream[slot];
+            // stream order makes reuse of this slot's buffers safe (previous chunk's D2H precedes)
+            CU(cudaMemcpyAsync(p->d_in[slot], boards_in + done, m * 8, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(p->d_act[slot], actions + done, m, cudaMemcpyHostToDevice, st));
+            if (spawns) CU(cudaMemcpyAsync(p->d_spn[slot], spawns + done, m, cudaMemcpyHostToDevice, st));
+            if (compute) {
+                const int r = g2048_step(p->d_in[slot], p->d_act[slot], spawns ? p->d_spn[slot] : nullptr, seed,
+                                         env_offset + done, nullptr, step_base, nullptr, nullptr, p->d_out[slot],
+                                         p->d_rew[slot], p->d_flg[slot], m, st);
+                if (r) return r;
+            }
+            CU(cudaMemcpyAsync(boards_out + done, p->d_out[slot], m * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(rewards + done, p->d_rew[slot], m * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(flags + done, p->d_flg[slot], m, cudaMemcpyDeviceToHost, st));
+            done += m;
+            slot = (slot + 1) % HostPipe::kSlots;
+        }
+        return G2048_OK;
+    };
+    rc = run();
+    // drain every stream before the pipe goes back to the pool, whatever happened above
+    for (int i = 0; i < HostPipe::kSlots; ++i) {
+        const cudaError_t e = cudaStreamSynchronize(p->stream[i]);
+        if (e != cudaSuccess && rc == G2048_OK) rc = cuda_fail(e, "cudaStreamSynchronize(host pipe)");
+    }
+    pipe_release(p);
+    return rc;
 }
 }  // namespace
 
@@ -1977,50 +2442,141 @@ extern "C" int g2048_step_host(const uint64_t* boards_in, const uint8_t* actions
                                const uint8_t* spawns, uint64_t seed, uint64_t env_offset,
                                uint32_t step_base, uint64_t* boards_out, int32_t* rewards,
                                uint8_t* flags, size_t n) {
-    if (n == 0) return G2048_OK;
-    if (!boards_in || !actions || !boards_out || !rewards || !flags) return G2048_EINVAL;
-    DeviceState* s;
-    int rc = current_state(&s);
-    if (rc) return rc;
-    HostPipe* p;
-    rc = pipe_get(&p);
-    if (rc) return rc;
-    static size_t chunk = 0;  // envs per pipeline stage (<= kChunk); env G2048_HOST_CHUNK_LOG2 overrides
-    if (chunk == 0) {
-        const char* e = getenv("G2048_HOST_CHUNK_LOG2");
-        const int lg = e ? atoi(e) : 21;
-        chunk = (lg >= 12 && lg <= 21) ? ((size_t)1 << lg) : HostPipe::kChunk;
-    }
-    size_t done = 0;
-    int slot = 0;
-    while (done < n) {
-        const size_t m = (n - done < chunk) ? n - done : chunk;
-        cudaStream_t st = p->stream[slot];
-        // stream order makes reuse of this slot's buffers safe (previous chunk's D2H precedes)
-        CU(cudaMemcpyAsync(p->d_in[slot], boards_in + done, m * 8, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(p->d_act[slot], actions + done, m, cudaMemcpyHostToDevice, st));
-        if (spawns) CU(cudaMemcpyAsync(p->d_spn[slot], spawns + done, m, cudaMemcpyHostToDevice, st));
-        rc = g2048_step(p->d_in[slot], p->d_act[slot], spawns ? p->d_spn[slot] : nullptr, seed,
-                        env_offset + done, nullptr, step_base, nullptr, nullptr, p->d_out[slot],
-                        p->d_rew[slot], p->d_flg[slot], m, st);
-        if (rc) return rc;
-        CU(cudaMemcpyAsync(boards_out + done, p->d_out[slot], m * 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(rewards + done, p->d_rew[slot], m * 4, cudaMemcpyDeviceToHost, st));
-        CU(cudaMemcpyAsync(flags + done, p->d_flg[slot], m, cudaMemcpyDeviceToHost, st));
-        done += m;
-        slot = (slot + 1) % HostPipe::kSlots;
-    }
-    for (int i = 0; i < HostPipe::kSlots; ++i) CU(cudaStreamSynchronize(p->stream[i]));
-    return G2048_OK;
+    return step_host_impl(true, boards_in, actions, spawns, seed, env_offset, step_base, boards_out, rewards,
+                          flags, n);
 }
 
+extern "C" int g2048_step_host_copies(const uint64_t* boards_in, const uint8_t* actions,
+                                      const uint8_t* spawns, uint64_t* boards_out, int32_t* rewards,
+                                      uint8_t* flags, size_t n) {
+    return step_host_impl(false, boards_in, actions, spawns, 0, 0, 0, boards_out, rewards, flags, n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pinned host memory, placed on the NUMA node of the current GPU when the kernel allows it
+// ---------------------------------------------------------------------------------------------
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+#include <map>
+
+namespace {
+struct HostBlock {
+    size_t bytes;
+    bool mapped;  // mmap + cudaHostRegister (else cudaHostAlloc)
+};
+std::mutex g_host_mu;
+std::map<void*, HostBlock> g_host_blocks;
+
+// NUMA node of the PCI device behind CUDA device `dev` (sysfs), -1 if unknown
+int gpu_numa_node(int dev) {
+    char bus[64] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, dev) != cudaSuccess) return -1;
+    for (char* c = bus; *c; ++c)
+        if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+    char path[160];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+
+// node that holds the page at `p` (get_mempolicy with MPOL_F_NODE | MPOL_F_ADDR), -1 if unknown
+int page_numa_node(const void* p) {
+    int node = -1;
+    if (syscall(SYS_get_mempolicy, &node, nullptr, 0ul, p, 3ul /* MPOL_F_NODE | MPOL_F_ADDR */) != 0) return -1;
+    return node;
+}
+}  // namespace
+
 extern "C" int g2048_host_alloc(void** ptr, size_t bytes) {
-    if (!ptr) return G2048_EINVAL;
-    CU(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+    if (!ptr || bytes == 0) return G2048_EINVAL;
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    const int node = gpu_numa_node(dev);
+    const char* off = getenv("G2048_HOST_NUMA");
+    if (node >= 0 && node < 64 && !(off && atoi(off) == 0)) {
+        const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+        const size_t len = (bytes + page - 1) / page * page;
+        void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p != MAP_FAILED) {
+            const unsigned long mask = 1ul << node;
+            // MPOL_PREFERRED (1): place on the GPU's node when the cpuset allows it, never fail hard
+            (void)syscall(SYS_mbind, p, len, 1, &mask, 65ul, 0u);
+            memset(p, 0, len);  // first touch under the policy
+            if (cudaHostRegister(p, len, cudaHostRegisterPortable) == cudaSuccess) {
+                std::lock_guard<std::mutex> lk(g_host_mu);
+                g_host_blocks[p] = HostBlock{len, true};
+                *ptr = p;
+                return G2048_OK;
+            }
+            (void)cudaGetLastError();
+            munmap(p, len);
+        }
+    }
+    CU(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable));
+    std::lock_guard<std::mutex> lk(g_host_mu);
+    g_host_blocks[*ptr] = HostBlock{bytes, false};
     return G2048_OK;
 }
 
 extern "C" int g2048_host_free(void* ptr) {
-    CU(cudaFreeHost(ptr));
+    if (!ptr) return G2048_OK;
+    HostBlock b{0, false};
+    {
+        std::lock_guard<std::mutex> lk(g_host_mu);
+        auto it = g_host_blocks.find(ptr);
+        if (it == g_host_blocks.end()) return G2048_EINVAL;
+        b = it->second;
+        g_host_blocks.erase(it);
+    }
+    if (b.mapped) {
+        CU(cudaHostUnregister(ptr));
+        munmap(ptr, b.bytes);
+    } else {
+        CU(cudaFreeHost(ptr));
+    }
+    return G2048_OK;
+}
+
+extern "C" int g2048_host_numa_info(const void* ptr, int* gpu_node, int* mem_node) {
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (gpu_node) *gpu_node = gpu_numa_node(dev);
+    if (mem_node) *mem_node = ptr ? page_numa_node(ptr) : -1;
+    return G2048_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// shutdown: release every device resource the library holds
+// ---------------------------------------------------------------------------------------------
+extern "C" int g2048_shutdown(void) {
+    int keep = 0;
+    const bool have_dev = cudaGetDevice(&keep) == cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lk(g_pipe_mu);
+        for (int d = 0; d < 64; ++d) {
+            if (g_pipes[d].empty()) continue;
+            cudaSetDevice(d);
+            for (HostPipe* p : g_pipes[d]) pipe_destroy(p);
+            g_pipes[d].clear();
+        }
+    }
+    for (int d = 0; d < 64; ++d) {
+        DeviceState& s = g_dev[d];
+        std::lock_guard<std::mutex> lk(s.mu);
+        if (!s.ready.load(std::memory_order_acquire)) continue;
+        cudaSetDevice(d);
+        cudaDeviceSynchronize();
+        cudaFree(s.table);
+        cudaFree(s.table_hashed);
+        s.table = s.table_hashed = nullptr;
+        s.ready.store(false, std::memory_order_release);
+    }
+    if (have_dev) cudaSetDevice(keep);
+    (void)cudaGetLastError();
     return G2048_OK;
 }

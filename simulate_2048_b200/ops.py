@@ -20,7 +20,7 @@ from ._cabi import check, lib
 __all__ = [
     'StepOut', 'ExpandOut', 'RolloutOut', 'step', 'env_step', 'legal_flags', 'expand', 'reset',
     'observe', 'observe_onehot', 'nstep_returns', 'expect', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'step_host', 'row_table', 'set_impl', 'set_tuning', 'init',
-    'pinned_empty',
+    'pinned_empty', 'host_numa_info', 'step_host_copies', 'shutdown',
 ]
 
 
@@ -147,26 +147,58 @@ class ExpandOut(NamedTuple):
     mask: torch.Tensor         # uint8[N] legal | done | overflow
     num_empty: torch.Tensor    # uint8[N,4]
     child_count: torch.Tensor  # uint8[N,4]
-    children: Optional[torch.Tensor]       # int64[N,4,16,2] dense or int64[total] compact
+    children: Optional[torch.Tensor]       # int64[N,4,16,2] dense or int64[total or capacity] compact
     child_offsets: Optional[torch.Tensor]  # int64[N] (compact)
+    total: Optional[torch.Tensor] = None   # int64[2] on the device (compact): {children, overflowed}
+
+
+CHILDREN_PER_BOARD_MAX = 120  # 4 actions x 15 empty cells x 2 values
+
+
+def _expand_compact(boards, after, rewards, mask, num_empty, child_count, offsets, children, total):
+    check(lib().g2048_expand_compact(_ptr(boards), _ptr(after), _ptr(rewards), _ptr(mask), _ptr(num_empty),
+                                     _ptr(child_count), _ptr(offsets), _ptr(children), children.numel(),
+                                     _ptr(total), boards.numel(), _stream()))
 
 
 def expand(boards: torch.Tensor, children: str = 'none', zero_fill: bool = True,
-           out: Optional[ExpandOut] = None) -> ExpandOut:
-    """MCTS leaf expansion (g2048_expand): mask, the four afterstates + rewards and every chance
-    child of each legal afterstate (gameboard.py:132 after_state order: cell-major, 2 then 4;
-    probability of a child = {0.9, 0.1} / num_empty).  The dense layout writes every slot (the
-    slots beyond ``child_count`` hold 0), so no memset is needed; ``zero_fill`` is kept for
-    callers of the earlier signature and ignored."""
+           out: Optional[ExpandOut] = None, capacity: Optional[int] = None,
+           child_offsets: Optional[torch.Tensor] = None) -> ExpandOut:
+    """MCTS leaf expansion (g2048_expand / g2048_expand_compact): mask, the four afterstates +
+    rewards and every chance child of each legal afterstate (gameboard.py:132 after_state order:
+    cell-major, 2 then 4; probability of a child = {0.9, 0.1} / num_empty).
+
+    ``children='dense'`` writes every slot (those beyond ``child_count`` hold 0: no memset needed);
+    ``zero_fill`` is kept for callers of the earlier signature and ignored.
+
+    ``children='compact'`` packs the children of board i at ``child_offsets[i]``.  The offsets are
+    computed on the device in the same call (no host round trip):
+      * default: one launch into a buffer sized from an estimate, then ONE host read of the total
+        to return an exactly sized ``children`` tensor (a second launch only if the estimate was
+        too small);
+      * ``capacity=k`` or ``out=`` (buffers of an earlier call, any board contents): fully
+        asynchronous; ``children`` keeps its capacity, ``total`` (device int64[2]) holds the number
+        of valid children and an overflow flag — a board that does not fit writes nothing;
+      * ``child_offsets=`` (caller-supplied, with ``out=``): the offsets are an INPUT and the
+        children buffer must be large enough for them (g2048_expand)."""
     _req(boards, torch.int64, 'boards')
     n = boards.numel()
     dev = boards.device
     layout = {'none': _cabi.CHILDREN_NONE, 'dense': _cabi.CHILDREN_DENSE,
               'compact': _cabi.CHILDREN_COMPACT}[children]
-    if out is not None:  # reuse a previous result's buffers (same n and layout): no allocation
+    if out is not None:  # reuse a previous result's buffers: no allocation
         if out.after.shape[0] != n or (layout != _cabi.CHILDREN_NONE and out.children is None):
             raise ValueError('out: buffers do not match this call')
         with torch.cuda.device(dev):
+            if layout == _cabi.CHILDREN_COMPACT and child_offsets is None:
+                total = out.total if out.total is not None else torch.empty(2, dtype=torch.int64, device=dev)
+                _req(out.child_offsets, torch.int64, 'out.child_offsets', n)
+                _expand_compact(boards, out.after, out.rewards, out.mask, out.num_empty, out.child_count,
+                                out.child_offsets, out.children, total)
+                return out._replace(total=total)
+            if layout == _cabi.CHILDREN_COMPACT:
+                _req(child_offsets, torch.int64, 'child_offsets', n)
+                out = out._replace(child_offsets=child_offsets)
             check(lib().g2048_expand(_ptr(boards), _ptr(out.after), _ptr(out.rewards), _ptr(out.mask),
                                      _ptr(out.num_empty), _ptr(out.child_count), _ptr(out.children),
                                      _ptr(out.child_offsets), layout, n, _stream()))
@@ -179,20 +211,22 @@ def expand(boards: torch.Tensor, children: str = 'none', zero_fill: bool = True,
     ch = off = None
     with torch.cuda.device(dev):
         if layout == _cabi.CHILDREN_COMPACT:
-            # the moves run once and write every fixed-size output; their counts size the children,
-            # which g2048_expand_children then builds from the afterstates
-            check(lib().g2048_expand(_ptr(boards), _ptr(after), _ptr(rewards), _ptr(mask),
-                                     _ptr(num_empty), _ptr(child_count), None, None,
-                                     _cabi.CHILDREN_NONE, n, _stream()))
-            per_env = child_count.to(torch.int64).sum(dim=1)
-            incl = torch.cumsum(per_env, dim=0)
-            off = (incl - per_env).contiguous()
-            total = int(incl[-1].item()) if n else 0
-            ch = torch.empty(total, dtype=torch.int64, device=dev)
-            if total:
-                check(lib().g2048_expand_children(_ptr(after), _ptr(child_count), _ptr(off), _ptr(ch),
-                                                  layout, n, _stream()))
-            return ExpandOut(after, rewards, mask, num_empty, child_count, ch, off)
+            off = torch.empty(n, dtype=torch.int64, device=dev)
+            total = torch.zeros(2, dtype=torch.int64, device=dev)
+            if n == 0:
+                return ExpandOut(after, rewards, mask, num_empty, child_count,
+                                 torch.empty(0, dtype=torch.int64, device=dev), off, total)
+            fixed = capacity is not None
+            cap = int(capacity) if fixed else min(CHILDREN_PER_BOARD_MAX * n, 72 * n + 4096)
+            ch = torch.empty(max(cap, 1), dtype=torch.int64, device=dev)
+            _expand_compact(boards, after, rewards, mask, num_empty, child_count, off, ch, total)
+            if fixed:
+                return ExpandOut(after, rewards, mask, num_empty, child_count, ch, off, total)
+            count, over = (int(x) for x in total.tolist())  # the one host read: sizes the result
+            if over:  # the estimate was too small: once more with the exact size
+                ch = torch.empty(count, dtype=torch.int64, device=dev)
+                _expand_compact(boards, after, rewards, mask, num_empty, child_count, off, ch, total)
+            return ExpandOut(after, rewards, mask, num_empty, child_count, ch[:count], off, total)
         if layout == _cabi.CHILDREN_DENSE:
             ch = torch.empty((n, 4, 16, 2), dtype=torch.int64, device=dev)
         check(lib().g2048_expand(_ptr(boards), _ptr(after), _ptr(rewards), _ptr(mask),
@@ -369,10 +403,37 @@ def unpack(boards: torch.Tensor) -> torch.Tensor:
     return tiles
 
 
-def pinned_empty(n: int, dtype: torch.dtype) -> np.ndarray:
-    """NumPy array backed by pinned host memory (full PCIe bandwidth for step_host).
-    The array keeps the torch storage alive through its ``base``."""
-    return torch.empty(n, dtype=dtype).pin_memory().numpy()
+_NP_DTYPES = {torch.int64: np.int64, torch.int32: np.int32, torch.uint8: np.uint8, torch.float32: np.float32}
+
+
+def pinned_empty(n: int, dtype, device: Optional[int] = None) -> np.ndarray:
+    """NumPy array backed by pinned host memory from ``g2048_host_alloc``: full PCIe bandwidth for
+    ``step_host``, placed on the NUMA node of ``device`` (default: the current CUDA device) when the
+    process is allowed to.  The block is returned to the library when the array and all its views
+    are gone."""
+    import ctypes
+    import weakref
+    np_dtype = np.dtype(_NP_DTYPES.get(dtype, dtype))
+    nbytes = max(int(n) * np_dtype.itemsize, 1)
+    p = ctypes.c_void_p()
+    with torch.cuda.device(torch.cuda.current_device() if device is None else device):
+        check(lib().g2048_host_alloc(ctypes.byref(p), nbytes))
+    buf = (ctypes.c_uint8 * nbytes).from_address(p.value)
+    weakref.finalize(buf, lib().g2048_host_free, ctypes.c_void_p(p.value))
+    return np.frombuffer(buf, dtype=np_dtype, count=int(n))
+
+
+def host_numa_info(arr: Optional[np.ndarray] = None):
+    """(NUMA node of the current GPU, NUMA node holding ``arr``'s first page); -1 = unknown."""
+    import ctypes
+    g, m = ctypes.c_int(-1), ctypes.c_int(-1)
+    check(lib().g2048_host_numa_info(None if arr is None else arr.ctypes.data, ctypes.byref(g), ctypes.byref(m)))
+    return g.value, m.value
+
+
+def shutdown() -> None:
+    """Release the library's device resources (g2048_shutdown); it re-initialises lazily."""
+    check(lib().g2048_shutdown())
 
 
 def step_host(boards: np.ndarray, actions: np.ndarray, spawns: Optional[np.ndarray] = None, *,
@@ -392,6 +453,16 @@ def step_host(boards: np.ndarray, actions: np.ndarray, spawns: Optional[np.ndarr
                                 seed & (2**64 - 1), env_offset, step_base & 0xFFFFFFFF,
                                 ob.ctypes.data, orw.ctypes.data, ofl.ctypes.data, n))
     return ob, orw, ofl
+
+
+def step_host_copies(boards: np.ndarray, actions: np.ndarray, spawns: Optional[np.ndarray], out) -> None:
+    """The host<->device copies of ``step_host`` without the kernel (g2048_step_host_copies): the
+    PCIe ceiling of that call, measured with the same buffers."""
+    b = np.ascontiguousarray(boards).view(np.uint64).reshape(-1)
+    ob, orw, ofl = out
+    check(lib().g2048_step_host_copies(b.ctypes.data, actions.ctypes.data,
+                                       None if spawns is None else spawns.ctypes.data,
+                                       ob.ctypes.data, orw.ctypes.data, ofl.ctypes.data, b.size))
 
 
 def row_table():

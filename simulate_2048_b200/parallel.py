@@ -62,12 +62,13 @@ class EpisodeStats:
     capped: int
     overflow: int
     max_tile_hist: Dict[int, int]
+    vector: Tuple[int, ...] = ()   # the raw 24 words
 
     @classmethod
     def from_vector(cls, v) -> 'EpisodeStats':
         w = [int(x) for x in v.tolist()]
         hist = {(1 << e if e else 0): w[8 + e] for e in range(16) if w[8 + e]}
-        return cls(w[0], w[1], w[2], w[3], w[4], w[5], w[6], hist)
+        return cls(w[0], w[1], w[2], w[3], w[4], w[5], w[6], hist, tuple(w))
 
     def summary(self) -> Dict[str, float]:
         """The quantities self_play.evaluate_games reports (self_play.py:503-521)."""

@@ -13,7 +13,7 @@ void orc_row_table(uint16_t* result, uint32_t* reward, uint8_t* moved);
 void orc_step(const uint64_t* boards_in, const uint8_t* actions, const uint8_t* spawns, uint64_t seed,
               uint64_t env_offset, const uint32_t* step_ctr, uint32_t step_base, const uint64_t* env_keys,
               const uint8_t* done_in, uint64_t* boards_out, int32_t* rewards, uint8_t* flags, size_t n);
-void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+uint32_t orc_philox_word(uint64_t key, uint64_t env, uint32_t step, uint32_t tag);
 }
 
 using namespace g2048::fast;
@@ -70,10 +70,8 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < n; ++i) {
         const u32 lo = (u32)boards[i], hi = (u32)(boards[i] >> 32);
         if (has_big_tile(lo, hi)) continue;
-        const uint64_t env = off + i;
-        uint32_t ctr[4] = {(uint32_t)env, (uint32_t)(env >> 32), 7, 0}, key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, w[4];
-        orc_philox4x32_10(ctr, key, w);
-        FastOut f = transition_fast<true>(lo, hi, orient[act[i] & 3], 0, (2u - nonzero01(mulhi(w[1], 10u))) << 29, w[0], lut, 1u);
+        const uint32_t w = orc_philox_word(seed, off + i, 7, 0);
+        FastOut f = transition_fast<true>(lo, hi, orient[act[i] & 3], 0, 0, w, lut, 1u);
         const uint64_t got = ((uint64_t)f.hi << 32) | f.lo;
         if (got != out[i] || (int32_t)f.reward != rw[i] || (uint8_t)f.flags != fl[i]) {
             if (bad < 20)

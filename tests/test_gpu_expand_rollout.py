@@ -114,9 +114,44 @@ def test_expand_odd_child_offsets(T, ops):
     total = ex.children.numel()
     shifted = ex._replace(children=T.full((total + 1,), -1, dtype=T.int64, device='cuda'),
                           child_offsets=ex.child_offsets + 1)
-    ops.expand(boards, children='compact', out=shifted)
+    ops.expand(boards, children='compact', out=shifted, child_offsets=ex.child_offsets + 1)
     assert int(shifted.children[0].item()) == -1
     np.testing.assert_array_equal(host(shifted.children[1:]), host(ex.children))
+
+
+@pytest.mark.parametrize('n', [1, 127, 129, 40000, (1 << 17) + 1025])
+def test_expand_compact_device_scan(T, ops, oracle, n):
+    """g2048_expand_compact: offsets scanned on the device (single-launch look-back below 2^17
+    boards, three-kernel scan above), no host round trip; buffers of an earlier call are reused
+    with DIFFERENT boards (the offsets are recomputed, never stale); a capacity that is too small
+    raises the overflow flag and never writes past the buffer."""
+    b1 = synthetic_packed(n, seed=3 * n + 1)
+    b2 = synthetic_packed(n, seed=3 * n + 2, max_exp=4)
+    w1, w2 = oracle.expand(b1, child_layout=2), oracle.expand(b2, child_layout=2)
+    cap = max(len(w1['children']), len(w2['children'])) + 5
+    ex = ops.expand(dev(T, b1), children='compact', capacity=cap)
+    assert ex.total.tolist() == [len(w1['children']), 0]
+    np.testing.assert_array_equal(ex.child_offsets.cpu().numpy(), w1['child_offsets'])
+    np.testing.assert_array_equal(host(ex.children[:len(w1['children'])]), w1['children'])
+    ex.children.fill_(-1)
+    ex2 = ops.expand(dev(T, b2), children='compact', out=ex)       # same buffers, other boards
+    assert ex2.total.tolist() == [len(w2['children']), 0]
+    np.testing.assert_array_equal(ex2.child_offsets.cpu().numpy(), w2['child_offsets'])
+    np.testing.assert_array_equal(host(ex2.children[:len(w2['children'])]), w2['children'])
+    np.testing.assert_array_equal(ex2.child_count.cpu().numpy(), w2['child_count'])
+    assert (host(ex2.children[len(w2['children']):]).view(np.int64) == -1).all()
+    # too small: boards that fit are written, nothing beyond the capacity is touched
+    small = max(len(w1['children']) // 2, 1)
+    guard = T.full((small + 64,), -1, dtype=T.int64, device='cuda')
+    tight = ex._replace(children=guard[:small])
+    got = ops.expand(dev(T, b1), children='compact', out=tight)
+    assert got.total.tolist() == [len(w1['children']), 1]
+    assert (guard[small:].cpu().numpy() == -1).all()
+    fits = w1['child_offsets'] + w1['child_count'].reshape(n, 4).sum(axis=1) <= small
+    k = n if fits.all() else int(np.argmin(fits))   # offsets are monotone: the first k boards fit
+    if k:
+        end = int(w1['child_offsets'][k - 1] + w1['child_count'].reshape(n, 4)[k - 1].sum())
+        np.testing.assert_array_equal(host(guard[:end]), w1['children'][:end])
 
 
 def test_expand_dense_writes_every_slot(T, ops, oracle):
@@ -223,6 +258,17 @@ def test_rollout_trace_replays_through_step(T, ops, oracle):
         score += np.where(alive, res.rewards.cpu().numpy(), 0)
     np.testing.assert_array_equal(boards, host(out.boards))
     np.testing.assert_array_equal(score, out.score.cpu().numpy())
+    # "results do not depend on fusion": the same games through g2048_step in PHILOX mode, fed with
+    # the trace's actions, draw the same tiles (word of (env, step), digits 1 and 2)
+    boards = oracle.reset(n, seed=7)
+    alive = np.ones(n, bool)
+    for t in range(int(out.steps.max().item())):
+        byte = trace[:, t]
+        alive &= byte != 0
+        res = ops.step(dev(T, boards), dev(T, (byte & 3).astype(np.uint8)), None, seed=7, step_base=t,
+                       done_in=dev(T, (~alive).astype(np.uint8)))
+        boards = host(res.boards)
+    np.testing.assert_array_equal(boards, host(out.boards))
 
 
 def test_rollout_sharding_invariance_and_caps(T, ops, oracle):
@@ -245,6 +291,25 @@ def test_rollout_sharding_invariance_and_caps(T, ops, oracle):
     want = oracle.rollout(3000, seed=1, from_reset=False, boards=start)
     np.testing.assert_array_equal(host(got.boards), want['boards'])
     np.testing.assert_array_equal(got.score.cpu().numpy(), want['score'])
+
+
+def test_rollout_stats_match_oracle_fixture(T, ops):
+    """The statistics vector of BASELINE config 4 at 2^16, 2^20 and 2^21 envs (seed 2048) equals the
+    oracle-computed vector bench.py checks the sharded run against — also when the range is split
+    in two unequal shards and combined as parallel.reduce_stats does."""
+    import json
+    import os
+    from simulate_2048_b200.parallel import combine_stats
+    here = os.path.dirname(os.path.abspath(__file__))
+    fix = json.load(open(os.path.join(here, 'golden', 'rollout_stats.json')))
+    for n in (1 << 16, 1 << 20, 1 << 21):
+        out = ops.rollout(n, seed=fix['seed'], per_env=False)
+        assert [int(x) for x in out.stats.cpu().numpy().view(np.uint64)] == fix['stats'][str(n)]
+    n, cut = 1 << 20, 300001
+    a = ops.rollout(cut, seed=fix['seed'], per_env=False)
+    b = ops.rollout(n - cut, seed=fix['seed'], env_offset=cut, per_env=False)
+    both = combine_stats(T.stack([a.stats, b.stats]))
+    assert [int(x) for x in both.cpu().numpy().view(np.uint64)] == fix['stats'][str(n)]
 
 
 def test_rollout_statistics_sanity(T, ops):
