@@ -7,7 +7,7 @@ import threading
 import numpy as np
 import pytest
 
-from helpers import synthetic_packed, valid_spawn_bytes
+from tests.helpers import synthetic_packed, valid_spawn_bytes
 
 pytestmark = pytest.mark.gpu
 

@@ -5,7 +5,7 @@ restatement in between.  Through the C ABI (ops.* are one-line ctypes calls)."""
 import numpy as np
 import pytest
 
-from helpers import pack_tiles, synthetic_packed
+from tests.helpers import pack_tiles, synthetic_packed
 
 pytestmark = pytest.mark.gpu
 
