@@ -51,7 +51,8 @@
  *     tile 4 iff hi32(f1 * 10) == 0 (p = 0.1),                      f2 = lo32(f1 * 10)
  *     rollout policy: the NEXT action is the hi32(f2 * n_legal)-th legal action of the new board.
  *   Tags: 0 = play step, 1 / 2 = first / second reset tile (step 0; the first rollout action is
- *   digit 3 of the tag-2 word), 3 = first action of a rollout that starts from a given board.
+ *   digit 3 of the tag-2 word), 3 = first action of a rollout that starts from a given board,
+ *   4 = the action draw of g2048_selfplay_step (step = the env's step_count).
  *
  * Flags byte (per env):
  */
@@ -87,6 +88,7 @@ extern "C" {
 #define G2048_PHILOX_TAG_RESET0 1u
 #define G2048_PHILOX_TAG_RESET1 2u
 #define G2048_PHILOX_TAG_START 3u
+#define G2048_PHILOX_TAG_POLICY 4u
 
 /* children layout for g2048_expand */
 #define G2048_CHILDREN_NONE 0
@@ -148,6 +150,35 @@ int g2048_env_step(uint64_t* boards, int32_t* step_count, uint8_t* done, float* 
                    uint64_t env_offset, const uint64_t* env_keys, float* rewards,
                    uint8_t* flags, float* obs, int32_t* max_tile, uint8_t* legal, size_t n,
                    void* stream);
+
+/*
+ * One self-play iteration in ONE call (self_play.py:314-368: observation, legal mask, sample_action,
+ * batched_step and the per-step trajectory appends), in place on a GameState:
+ *   1. action: drawn from `policy` f32[n*4] exactly as core.py:381-424 sample_action builds its
+ *      distribution (illegal actions masked with the legal mask of the CURRENT board, renormalised,
+ *      uniform over the legal actions when the mass is below 1e-8, softmax(log(p + 1e-8) /
+ *      temperature), argmax when temperature < 0.01), f32 arithmetic; the draw is the inverse CDF at
+ *      the top 24 bits of the env's Philox word of (seed, env, step_count, tag 4).  `actions_in`
+ *      u8[n] (optional) replaces the draw.
+ *   2. record (optional, row t = *t_dev of time-major buffers [capacity][n], skipped when
+ *      t >= capacity): tr_obs f32[.,16] and tr_legal u8[.,4] of the board the action was chosen on,
+ *      tr_actions, tr_policies f32[.,4] (the `policy` input), tr_values (`values` f32[n] or 0),
+ *      tr_active (0 for an env that was already done), lengths i32[n] += active, tr_rewards after
+ *      the step.  *t_dev is incremented by a trailing one-thread kernel (same stream).
+ *   3. step as g2048_env_step (spawns u8[n] injected or NULL for Philox tag 0), with the optional
+ *      outputs rewards f32[n], norm_rewards f32[n] (twentyfortyeight/utils/normalize.py:6:
+ *      log2(reward)/16, 0 for reward 0), obs f32[n*16], legal u8[n*4], max_tile i32[n] of the NEW
+ *      state, actions_out u8[n], probs_out f32[n*4] (the distribution of step 1).
+ * Floating point: the distribution agrees with an f32 NumPy evaluation to 1e-6 (logf / expf).
+ */
+int g2048_selfplay_step(uint64_t* boards, int32_t* step_count, uint8_t* done, float* total_reward,
+                        const float* policy, const float* values, const uint8_t* actions_in,
+                        const uint8_t* spawns, float temperature, uint64_t seed, uint64_t env_offset,
+                        int32_t* t_dev, uint32_t capacity, float* tr_obs, uint8_t* tr_legal,
+                        uint8_t* tr_actions, float* tr_rewards, float* tr_policies, float* tr_values,
+                        uint8_t* tr_active, int32_t* lengths, float* rewards, float* norm_rewards,
+                        float* obs, uint8_t* legal, int32_t* max_tile, uint8_t* actions_out,
+                        float* probs_out, size_t n, void* stream);
 
 /* Legal mask + done of boards (gamemove.py:45, core.py:275/:305); flags has the LEGAL/DONE bits. */
 int g2048_mask(const uint64_t* boards, uint8_t* flags, size_t n, void* stream);

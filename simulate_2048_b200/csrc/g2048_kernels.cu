@@ -762,6 +762,195 @@ extern "C" int g2048_env_step(uint64_t* boards, int32_t* step_count, uint8_t* do
 }
 
 // ---------------------------------------------------------------------------------------------
+// One self-play iteration in one launch: action sampling (core.py:381-424),
+// GameState step (env.py:79-133), the next observation / legal mask, and the trajectory record
+// (self_play.py:346-368: observation and policy the action was drawn from, action, reward, value).
+// ---------------------------------------------------------------------------------------------
+struct SelfplayArgs {
+    u64* boards;
+    int32_t* step_count;
+    uint8_t* done;
+    float* total_reward;
+    const float* policy;        // f32[n*4] search / network policy (core.py:381 `policy`)
+    const float* values;        // f32[n] root values to record, or NULL
+    const uint8_t* actions_in;  // u8[n]: use these actions instead of sampling, or NULL
+    const uint8_t* spawns;      // injected spawn bytes, or NULL (Philox)
+    float temperature;
+    u64 seed, env_offset;
+    // trajectory buffers, time-major [capacity][n] (any may be NULL); row = *t_dev
+    const int32_t* t_dev;
+    u32 capacity;
+    float* tr_obs;
+    uint8_t* tr_legal;
+    uint8_t* tr_actions;
+    float* tr_rewards;
+    float* tr_policies;
+    float* tr_values;
+    uint8_t* tr_active;
+    int32_t* lengths;
+    // outputs describing the NEW state (any may be NULL)
+    float* rewards;
+    float* norm_rewards;  // utils/normalize.py:6: log2(reward) / 16, 0 for reward 0
+    float* obs;
+    uint8_t* legal;
+    int32_t* max_tile;
+    uint8_t* actions_out;
+    float* probs_out;     // f32[n*4]: the distribution the action was drawn from
+    size_t n;
+    const u32* table;
+};
+
+// core.py:401-421 in f32: mask, renormalise (uniform over the legal actions when the mass is below
+// 1e-8), then softmax(log(p + 1e-8) / temperature) or the one-hot of the argmax when temperature < 0.01
+__device__ __forceinline__ void action_distribution(const float4 pol, u32 mask, float temperature, float out[4]) {
+    const float p[4] = {pol.x, pol.y, pol.z, pol.w};
+    float m[4], total = 0.0f, n_legal = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const bool legal = (mask >> a) & 1u;
+        m[a] = legal ? p[a] : 0.0f;
+        total += m[a];
+        n_legal += legal ? 1.0f : 0.0f;
+    }
+    const float inv_legal = 1.0f / fmaxf(n_legal, 1.0f);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) m[a] = total < 1e-8f ? (((mask >> a) & 1u) ? inv_legal : 0.0f) : m[a] / total;
+    if (temperature < 0.01f) {
+        int best = 0;  // argmax, first maximum (jnp.argmax)
+#pragma unroll
+        for (int a = 1; a < 4; ++a)
+            if (m[a] > m[best]) best = a;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) out[a] = a == best ? 1.0f : 0.0f;
+        return;
+    }
+    float z[4], zmax = -INFINITY, sum = 0.0f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        z[a] = logf(m[a] + 1e-8f) / temperature;
+        zmax = fmaxf(zmax, z[a]);
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        z[a] = expf(z[a] - zmax);
+        sum += z[a];
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) out[a] = z[a] / sum;
+}
+
+// inverse CDF with a 24-bit uniform from the env's word of tag 4; never returns an action of
+// probability 0 (rounding in the running sum cannot push the draw past the last positive entry)
+__device__ __forceinline__ u32 sample_from(const float q[4], u32 w) {
+    const float u = (float)(w >> 8) * (1.0f / 16777216.0f);
+    float c = 0.0f;
+    u32 last = 0;
+#pragma unroll
+    for (u32 a = 0; a < 4; ++a) {
+        if (q[a] > 0.0f) {
+            c += q[a];
+            last = a;
+            if (u < c) return a;
+        }
+    }
+    return last;
+}
+
+template <bool kPhilox>
+__global__ void __launch_bounds__(256) selfplay_step_kernel(const SelfplayArgs a) {
+    const GlobalTable T{a.table};
+    const u32 t = a.t_dev ? (u32)*a.t_dev : 0u;
+    const bool rec = a.t_dev && t < a.capacity;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const Board b = split(a.boards[i]);
+        const bool was_done = a.done[i] != 0;
+        const int sc = a.step_count[i];
+        const u32 mask = legal_mask(b);
+        const size_t row = (size_t)t * a.n + i;
+        // ---- the action (core.py:381-424) ----
+        float q[4] = {0.25f, 0.25f, 0.25f, 0.25f};
+        u32 action;
+        if (a.actions_in) {
+            action = a.actions_in[i] & 3u;
+        } else {
+            action_distribution(*reinterpret_cast<const float4*>(a.policy + i * 4), mask, a.temperature, q);
+            action = sample_from(q, philox_word(a.seed, a.env_offset + i, (u32)sc, G2048_PHILOX_TAG_POLICY));
+        }
+        if (a.actions_out) a.actions_out[i] = (uint8_t)action;
+        if (a.probs_out) *reinterpret_cast<float4*>(a.probs_out + i * 4) = make_float4(q[0], q[1], q[2], q[3]);
+        // ---- record what the policy saw (self_play.py:346-353) ----
+        if (rec) {
+            if (a.tr_obs) write_obs(a.tr_obs, row, b);
+            if (a.tr_legal)
+                reinterpret_cast<u32*>(a.tr_legal)[row] = (mask & 1u) | ((mask & 2u) << 7) | ((mask & 4u) << 14) | ((mask & 8u) << 21);
+            if (a.tr_actions) a.tr_actions[row] = (uint8_t)action;
+            if (a.tr_policies) {
+                const float4 pol = a.policy ? *reinterpret_cast<const float4*>(a.policy + i * 4) : make_float4(q[0], q[1], q[2], q[3]);
+                *reinterpret_cast<float4*>(a.tr_policies + row * 4) = pol;
+            }
+            if (a.tr_values) a.tr_values[row] = a.values ? a.values[i] : 0.0f;
+            if (a.tr_active) a.tr_active[row] = was_done ? 0 : 1;
+            if (a.lengths && !was_done) a.lengths[i] += 1;
+        }
+        // ---- the step (env.py:79-133) ----
+        Board nb = b;
+        u32 r = 0, f;
+        if (was_done) {
+            f = mask | G2048_FLAG_DONE;
+        } else {
+            transition<GlobalTable, kPhilox>(b, action, kPhilox ? 0u : a.spawns[i], a.seed, a.env_offset + i, (u32)sc,
+                                             T, nb, r, f);
+            a.boards[i] = join(nb);
+            a.step_count[i] = sc + 1;
+            a.done[i] = (f & G2048_FLAG_DONE) ? 1 : 0;
+            a.total_reward[i] = a.total_reward[i] + (float)r;
+        }
+        if (rec && a.tr_rewards) a.tr_rewards[row] = (float)r;
+        if (a.rewards) a.rewards[i] = (float)r;
+        if (a.norm_rewards) a.norm_rewards[i] = r ? log2f((float)r) * 0.0625f : 0.0f;
+        if (a.obs) write_obs(a.obs, i, nb);
+        if (a.max_tile) {
+            const u32 e = max_exponent(nb);
+            a.max_tile[i] = e ? (1 << e) : 0;
+        }
+        if (a.legal) reinterpret_cast<u32*>(a.legal)[i] = (f & 1u) | ((f & 2u) << 7) | ((f & 4u) << 14) | ((f & 8u) << 21);
+    }
+}
+
+__global__ void advance_counter_kernel(int32_t* t) { *t += 1; }
+
+extern "C" int g2048_selfplay_step(uint64_t* boards, int32_t* step_count, uint8_t* done, float* total_reward,
+                                   const float* policy, const float* values, const uint8_t* actions_in,
+                                   const uint8_t* spawns, float temperature, uint64_t seed, uint64_t env_offset,
+                                   int32_t* t_dev, uint32_t capacity, float* tr_obs, uint8_t* tr_legal,
+                                   uint8_t* tr_actions, float* tr_rewards, float* tr_policies, float* tr_values,
+                                   uint8_t* tr_active, int32_t* lengths, float* rewards, float* norm_rewards,
+                                   float* obs, uint8_t* legal, int32_t* max_tile, uint8_t* actions_out,
+                                   float* probs_out, size_t n, void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!boards || !step_count || !done || !total_reward) return G2048_EINVAL;
+    if (!policy && !actions_in) return G2048_EINVAL;
+    if (!aligned(policy, 16) || !aligned(probs_out, 16) || !aligned(obs, 16) || !aligned(tr_obs, 16) ||
+        !aligned(tr_policies, 16) || !aligned(legal, 4) || !aligned(tr_legal, 4))
+        return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    const SelfplayArgs a{reinterpret_cast<u64*>(boards), step_count, done, total_reward, policy, values, actions_in,
+                         spawns, temperature, seed, env_offset, t_dev, capacity, tr_obs, tr_legal, tr_actions,
+                         tr_rewards, tr_policies, tr_values, tr_active, lengths, rewards, norm_rewards, obs, legal,
+                         max_tile, actions_out, probs_out, n, s->table};
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = grid_for(n, 256, s->sms, 8);
+    if (spawns) selfplay_step_kernel<false><<<grid, 256, 0, st>>>(a);
+    else selfplay_step_kernel<true><<<grid, 256, 0, st>>>(a);
+    if (t_dev) advance_counter_kernel<<<1, 1, 0, st>>>(t_dev);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // mask / observe / pack / unpack / reset
 // ---------------------------------------------------------------------------------------------
 // four consecutive boards per thread: one 256-bit load and one 32-bit store, enough bytes in
@@ -1932,8 +2121,7 @@ struct RolloutArgs {
     u64* boards_io;
     int64_t* score_out;
     int32_t* steps_out;
-    uint8_t* maxexp_out;
-    u64* stats;
+    uint8_t* ovf_out;  // one byte per env, zero-filled: set when the episode saw a 15+15 merge
     uint8_t* trace;
     u32 trace_stride;
     const u32* table;
@@ -1947,14 +2135,6 @@ __constant__ uint8_t c_pick[64] = {
     0, 0, 0, 0,  0, 0, 0, 0,  1, 0, 0, 0,  0, 1, 0, 0,  2, 0, 0, 0,  0, 2, 0, 0,  1, 2, 0, 0,  0, 1, 2, 0,
     3, 0, 0, 0,  0, 3, 0, 0,  1, 3, 0, 0,  0, 1, 3, 0,  2, 3, 0, 0,  0, 2, 3, 0,  1, 2, 3, 0,  0, 1, 2, 3};
 
-// largest nibble of a board: byte-wise maxima of the even and odd nibbles (VIMNMX on packed bytes)
-__device__ __forceinline__ u32 max_exponent_fast(u32 lo, u32 hi) {
-    const u32 m4 = __vmaxu4(__vmaxu4(lo & 0x0F0F0F0Fu, (lo >> 4) & 0x0F0F0F0Fu),
-                            __vmaxu4(hi & 0x0F0F0F0Fu, (hi >> 4) & 0x0F0F0F0Fu));
-    const u32 m2 = __vmaxu4(m4, m4 >> 16);
-    return max(m2 & 0xFFu, (m2 >> 8) & 0xFFu);
-}
-
 // Exact out-of-line move for boards holding a tile >= 16384 (the branch-free register row move of
 // g2048_device.cuh, which also reports a 15+15 merge exactly).
 __device__ __noinline__ uint4 rollout_move_slow(u32 lo, u32 hi, u32 action) {
@@ -1963,10 +2143,14 @@ __device__ __noinline__ uint4 rollout_move_slow(u32 lo, u32 hi, u32 action) {
 }
 
 // Every lane plays kRollSlots games at once, one step of each per loop iteration: the two
-// dependent chains interleave (ILP 2 with 4 warps per scheduler instead of ILP 1 with 8), and a
-// game that ends is replaced at once from the global queue inside the (rare, divergent) episode
-// branch — no vote and no idle iteration on the common path.  Results are keyed by the global env
-// id and step, so they do not depend on which lane or slot played a game.
+// dependent chains interleave (ILP 2 with 6 warps per scheduler instead of ILP 1 with 8), and a
+// game that ends is replaced at once from the queues inside the (divergent) episode branch — no
+// vote and no idle iteration on the common path.  That branch is taken by a warp in about every
+// fourth slot-step (32 lanes x 1 / 118 steps), so it is kept to three stores and one atomic: the
+// per-episode results go to per-env arrays (the caller's or scratch) and a second, HBM-bound
+// kernel (rollout_stats_kernel) derives the max tile, the capped flag and the 24 statistics words
+// from them.  Results are keyed by the global env id and step, so they do not depend on which
+// lane or slot played a game.
 //
 // One step (roll_step) = the fast transition of g2048_fast.cuh with the action drawn one step
 // ahead: the word of (env, step) places the tile (digits 1, 2) and, once the mask of the new board
@@ -1986,15 +2170,9 @@ struct RollSlot {
     bool alive;
 };
 
-struct RollStats {  // per lane, flushed once at the end
-    u64 steps, score, maxscore;
-    u32 eps, maxsteps, capped, ovf;
-};
-
 struct RollShared {
     const uint4* orient;  // per-action orientation words
     const uint8_t* pick;  // action pick table
-    u32* hist;            // max-tile histogram of the CTA
     u32* hint;            // queues this CTA has found empty (roll_fetch)
 };
 
@@ -2002,60 +2180,62 @@ __device__ __forceinline__ u64 roll_env(const RollSlot& s) {
     return ((u64)s.qhi << 34) | ((u64)s.qlo << 2) | s.j;
 }
 
-// the episode of slot `s` is over: write its results
+// the episode of slot `s` is over: its per-env results (rollout_stats_kernel does the rest)
 template <bool kTrace>
-__device__ __forceinline__ void roll_emit(const RollSlot& s, u32 mask, const RolloutArgs& a,
-                                          const RollShared& sm, RollStats& st) {
+__device__ __forceinline__ void roll_emit(const RollSlot& s, const RolloutArgs& a) {
     const size_t i = (size_t)(roll_env(s) - a.env_offset);
     const u32 step = s.t - 2u;
     if (kTrace) a.trace[i * a.trace_stride + min(step, a.trace_stride - 1u)] = 0;
-    const u32 mx = max_exponent_fast(s.lo, s.hi);
     if (a.boards_io) a.boards_io[i] = ((u64)s.hi << 32) | s.lo;
     if (a.score_out) a.score_out[i] = (int64_t)s.score;
     if (a.steps_out) a.steps_out[i] = (int32_t)step;
-    if (a.maxexp_out) a.maxexp_out[i] = (uint8_t)mx;
-    if (sm.hist) atomicAdd(&sm.hist[mx], 1u);
-    st.eps += 1u;
-    st.steps += step;
-    st.score += s.score;
-    st.maxscore = max(st.maxscore, s.score);
-    st.maxsteps = max(st.maxsteps, step);
-    st.capped += (mask != 0u) ? 1u : 0u;
-    st.ovf += s.ovf;
+    if (s.ovf && a.ovf_out) a.ovf_out[i] = 1;  // zero-filled by the host side
 }
 
-// Next game for slot `s`.  The env range is cut into one queue per CTA (a counter each, `per`
-// consecutive ids): a CTA drains its own queue and then steals single ids from the others, so the
-// balance is that of one global queue while no counter is hit by more than one SM until the very
-// end.  (One counter for the whole grid serialises in L2: ~0.7 G atomics/s on one address capped
-// both the round-1 kernel and this one at ~92 G env-steps/s, `long_scoreboard` the top stall.)
-// `hint` (shared) = number of queues this CTA has already found empty.
+// The own queue is empty: steal single ids from the other CTAs' queues, in ring order from the
+// first one this CTA has not yet seen empty (`hint`, shared).  Rare (the end of a launch).
+__device__ __noinline__ bool roll_steal(const RolloutArgs& a, unsigned long long* next, u32* hint, size_t* out) {
+    for (;;) {
+        const u32 h = *reinterpret_cast<volatile u32*>(hint);
+        if (h >= gridDim.x) return false;
+        u32 q = blockIdx.x + h;
+        if (q >= gridDim.x) q -= gridDim.x;
+        const unsigned long long k = atomicAdd(&next[q], 1ull);
+        const size_t i = (size_t)q * a.per_queue + (size_t)k;
+        if (k < a.per_queue && i < a.n) {
+            *out = i;
+            return true;
+        }
+        atomicMax(hint, h + 1u);
+    }
+}
+
+// Next game for slot `s`.  The env range is cut into one queue per CTA (a counter each, `per_queue`
+// consecutive ids): a CTA drains its own queue and then steals from the others, so the balance is
+// that of one global queue while no counter is shared between SMs until the very end.
 // kFromReset: the game starts on the empty board in phase 0.  Otherwise it starts from boards_io
 // with the first action drawn from the word of tag 3; a board that is already over is emitted here.
 template <bool kFromReset, bool kTrace>
 __device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, const RollShared& sm,
-                                           unsigned long long* next, RollStats& st) {
+                                           unsigned long long* next) {
     for (;;) {
-        size_t i = 0;
-        bool got = false;
-        for (;;) {
-            const u32 h = *reinterpret_cast<volatile u32*>(sm.hint);
-            if (h >= gridDim.x) break;
-            u32 q = blockIdx.x + h;
-            if (q >= gridDim.x) q -= gridDim.x;
-            const size_t lo = (size_t)q * a.per_queue;
-            const unsigned long long k = atomicAdd(&next[q], 1ull);
-            if (k < a.per_queue && lo + k < a.n) {
-                i = lo + (size_t)k;
-                got = true;
-                break;
+        size_t i;
+        bool got;
+        if (*reinterpret_cast<volatile u32*>(sm.hint) == 0u) {
+            const unsigned long long k = atomicAdd(&next[blockIdx.x], 1ull);
+            i = (size_t)blockIdx.x * a.per_queue + (size_t)k;
+            got = k < a.per_queue && i < a.n;
+            if (!got) {
+                atomicMax(sm.hint, 1u);
+                got = roll_steal(a, next, sm.hint, &i);
             }
-            atomicMax(sm.hint, h + 1u);
+        } else {
+            got = roll_steal(a, next, sm.hint, &i);
         }
         s.lo = s.hi = s.act = s.t = s.ovf = 0u;
         s.score = 0;
+        s.alive = got;
         if (!got) {
-            s.alive = false;
             s.qlo = s.qhi = s.j = 0u;
             return;
         }
@@ -2063,7 +2243,6 @@ __device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, co
         s.qlo = (u32)(env >> 2);
         s.qhi = (u32)(env >> 34);
         s.j = (u32)env & 3u;
-        s.alive = true;
         if (kFromReset) return;
         const Board b = split(a.boards_io[i]);
         s.lo = b.lo;
@@ -2073,7 +2252,7 @@ __device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, co
         const u32 w = philox_word(a.keys, env, 0u, G2048_PHILOX_TAG_START);
         s.act = sm.pick[mask * 4u + __umulhi(w, (u32)__popc(mask))];
         if (mask != 0u && a.max_steps != 0u) return;
-        roll_emit<kTrace>(s, mask, a, sm, st);  // nothing to play
+        roll_emit<kTrace>(s, a);  // nothing to play
     }
 }
 
@@ -2128,21 +2307,22 @@ __device__ __forceinline__ u32 roll_step(RollSlot& s, const RolloutArgs& a, cons
     const u32 mask = fast::legal_mask(al, ah, nlo, nhi, one);
     // digit 3: the next action, the k-th legal one of the new board
     const u32 act = sm.pick[mask * 4u + fast::mulhi(f2, fast::popc(mask))];
-    // a slot without a game stays frozen on the empty board
-    s.lo = s.alive ? al : 0u;
-    s.hi = s.alive ? ah : 0u;
-    s.t = s.alive ? s.t + 1u : 0u;
+    // A slot without a game (the queues are empty) keeps stepping a dummy game that is never
+    // emitted: once that board is stuck, the no-op move leaves no empty cell, the spawn marker is 0
+    // and nothing changes any more — cheaper than freezing the slot with three selects per step.
+    s.lo = al;
+    s.hi = ah;
+    s.t += 1u;
     s.act = act;
     return mask;
 }
 
 template <bool kFromReset, bool kTrace, class Lut>
 __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RollShared& sm, const Lut& lut,
-                                             unsigned long long* next, u64* sh_stats) {
-    RollStats st{0ull, 0ull, 0ull, 0u, 0u, 0u, 0u};
+                                             unsigned long long* next) {
     RollSlot slot[kRollSlots];
 #pragma unroll
-    for (int k = 0; k < kRollSlots; ++k) roll_fetch<kFromReset, kTrace>(slot[k], a, sm, next, st);
+    for (int k = 0; k < kRollSlots; ++k) roll_fetch<kFromReset, kTrace>(slot[k], a, sm, next);
     for (;;) {
         bool any = false;
 #pragma unroll
@@ -2154,64 +2334,90 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RollSha
 #pragma unroll
         for (int k = 0; k < kRollSlots; ++k) {
             RollSlot& s = slot[k];
-            if (s.t >= 2u && (mask[k] == 0u || s.t - 2u >= a.max_steps)) {  // a frozen slot has t = 0
-                roll_emit<kTrace>(s, mask[k], a, sm, st);
-                roll_fetch<kFromReset, kTrace>(s, a, sm, next, st);
+            if (s.alive && s.t >= 2u && (mask[k] == 0u || s.t - 2u >= a.max_steps)) {
+                roll_emit<kTrace>(s, a);
+                roll_fetch<kFromReset, kTrace>(s, a, sm, next);
             }
-        }
-    }
-    if (sh_stats) {  // one flush per warp
-        const u32 FULL = 0xFFFFFFFFu;
-        for (int off = 16; off; off >>= 1) {
-            st.eps += __shfl_xor_sync(FULL, st.eps, off);
-            st.steps += __shfl_xor_sync(FULL, st.steps, off);
-            st.score += __shfl_xor_sync(FULL, st.score, off);
-            st.capped += __shfl_xor_sync(FULL, st.capped, off);
-            st.ovf += __shfl_xor_sync(FULL, st.ovf, off);
-            st.maxscore = max(st.maxscore, (u64)__shfl_xor_sync(FULL, st.maxscore, off));
-            st.maxsteps = max(st.maxsteps, __shfl_xor_sync(FULL, st.maxsteps, off));
-        }
-        if ((threadIdx.x & 31u) == 0u) {
-            atomicAdd(&sh_stats[0], (u64)st.eps);
-            atomicAdd(&sh_stats[1], st.steps);
-            atomicAdd(&sh_stats[2], st.score);
-            atomicMax(&sh_stats[3], st.maxscore);
-            atomicMax(&sh_stats[4], (u64)st.maxsteps);
-            atomicAdd(&sh_stats[5], (u64)st.capped);
-            atomicAdd(&sh_stats[6], (u64)st.ovf);
         }
     }
 }
 
 template <bool kSmem, bool kFromReset, bool kTrace, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutArgs a, unsigned long long* next) {
-    __shared__ u64 sh_stats[G2048_STATS_WORDS];
-    __shared__ u32 sh_hist[16];
     __shared__ __align__(16) uint4 sh_orient[8];
     __shared__ uint8_t sh_pick[64];
     __shared__ u32 sh_hint;
     u64* bar = reinterpret_cast<u64*>(smem_words + kSmemRows);
     if (kSmem) table_stage_begin(smem_words, bar, a.table_hashed);
     if (threadIdx.x == 0) sh_hint = 0u;
-    if (threadIdx.x < G2048_STATS_WORDS) sh_stats[threadIdx.x] = 0;
-    if (threadIdx.x < 16) sh_hist[threadIdx.x] = 0;
     if (threadIdx.x < 32) reinterpret_cast<u32*>(sh_orient)[threadIdx.x] = reinterpret_cast<const u32*>(c_orient)[threadIdx.x];
     if (threadIdx.x < 64) sh_pick[threadIdx.x] = c_pick[threadIdx.x];
     if (kSmem) table_stage_wait(bar); else __syncthreads();
 
-    const RollShared sm{sh_orient, sh_pick, a.stats ? sh_hist : nullptr, &sh_hint};
-    if (kSmem) rollout_loop<kFromReset, kTrace>(a, sm, SmemLut{}, next, a.stats ? sh_stats : nullptr);
-    else rollout_loop<kFromReset, kTrace>(a, sm, GlobalLut{a.table_hashed}, next, a.stats ? sh_stats : nullptr);
+    const RollShared sm{sh_orient, sh_pick, &sh_hint};
+    if (kSmem) rollout_loop<kFromReset, kTrace>(a, sm, SmemLut{}, next);
+    else rollout_loop<kFromReset, kTrace>(a, sm, GlobalLut{a.table_hashed}, next);
+}
 
+// Second kernel of a rollout: max tile, capped flag and the 24 statistics words from the per-env
+// results (HBM-bound: 21 bytes per episode).  An episode that ended with a legal action left was
+// stopped by max_steps.
+__global__ void __launch_bounds__(256) rollout_stats_kernel(const u64* __restrict__ boards,
+                                                            const int64_t* __restrict__ score,
+                                                            const int32_t* __restrict__ steps,
+                                                            const uint8_t* __restrict__ ovf,
+                                                            uint8_t* __restrict__ maxexp_out,
+                                                            u64* __restrict__ stats, size_t n) {
+    __shared__ u64 sh[G2048_STATS_WORDS];
+    if (threadIdx.x < G2048_STATS_WORDS) sh[threadIdx.x] = 0;
     __syncthreads();
-    if (a.stats && threadIdx.x < G2048_STATS_WORDS) {
-        const u64 v = threadIdx.x >= 8 ? (u64)sh_hist[threadIdx.x - 8] : sh_stats[threadIdx.x];
-        if (threadIdx.x == 3 || threadIdx.x == 4) atomicMax(&a.stats[threadIdx.x], v);
-        else if (v) atomicAdd(&a.stats[threadIdx.x], v);
+    u64 t_steps = 0, t_score = 0, t_maxscore = 0;
+    u32 t_eps = 0, t_maxsteps = 0, t_capped = 0, t_ovf = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const Board b = split(boards[i]);
+        const u32 mx = max_exponent(b);
+        if (maxexp_out) maxexp_out[i] = (uint8_t)mx;
+        if (!stats) continue;
+        const u64 sc = (u64)score[i];
+        const u32 st = (u32)steps[i];
+        atomicAdd(&sh[8 + mx], 1ull);
+        t_eps += 1u;
+        t_steps += st;
+        t_score += sc;
+        t_maxscore = max(t_maxscore, sc);
+        t_maxsteps = max(t_maxsteps, st);
+        t_capped += legal_mask(b) != 0u ? 1u : 0u;
+        t_ovf += ovf[i] ? 1u : 0u;
+    }
+    if (!stats) return;
+    const u32 FULL = 0xFFFFFFFFu;
+    for (int off = 16; off; off >>= 1) {
+        t_eps += __shfl_xor_sync(FULL, t_eps, off);
+        t_steps += __shfl_xor_sync(FULL, t_steps, off);
+        t_score += __shfl_xor_sync(FULL, t_score, off);
+        t_capped += __shfl_xor_sync(FULL, t_capped, off);
+        t_ovf += __shfl_xor_sync(FULL, t_ovf, off);
+        t_maxscore = max(t_maxscore, (u64)__shfl_xor_sync(FULL, t_maxscore, off));
+        t_maxsteps = max(t_maxsteps, __shfl_xor_sync(FULL, t_maxsteps, off));
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        atomicAdd(&sh[0], (u64)t_eps);
+        atomicAdd(&sh[1], t_steps);
+        atomicAdd(&sh[2], t_score);
+        atomicMax(&sh[3], t_maxscore);
+        atomicMax(&sh[4], (u64)t_maxsteps);
+        atomicAdd(&sh[5], (u64)t_capped);
+        atomicAdd(&sh[6], (u64)t_ovf);
+    }
+    __syncthreads();
+    if (threadIdx.x < G2048_STATS_WORDS) {
+        const u64 v = sh[threadIdx.x];
+        if (threadIdx.x == 3 || threadIdx.x == 4) atomicMax(&stats[threadIdx.x], v);
+        else if (v) atomicAdd(&stats[threadIdx.x], v);
     }
 }
 
-// persistent, one CTA per SM, table in shared memory: 768 threads x 2 slots at 85 registers
+// persistent, one CTA per SM, table in shared memory: 768 threads x 2 slots
 // (environment G2048_ROLL_THREADS=512 selects the smaller CTA; a tuning knob for measurements)
 static int g_roll_threads = [] { const char* e = getenv("G2048_ROLL_THREADS"); return (e && atoi(e) == 512) ? 512 : 768; }();
 constexpr int kRollSmallThreads = 128;  // small batches: table gathered from L2
@@ -2231,14 +2437,29 @@ extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint3
     const int bytes = smem ? (int)kSmemTableBytes + 64 : 0;
     const int threads = smem ? g_roll_threads : kRollSmallThreads;
     const int grid = smem ? s->sms : grid_for((n + kRollSlots - 1) / kRollSlots, kRollSmallThreads, s->sms, 8);
-    RolloutArgs a{seed, env_offset, n, (n + (size_t)grid - 1) / (size_t)grid, max_steps,
-                  reinterpret_cast<u64*>(boards_io), score_out, steps_out, maxexp_out,
-                  reinterpret_cast<u64*>(stats_out), trace, trace_stride, s->table, s->table_hashed, 1u,
-                  philox_key_schedule(seed)};
-    unsigned long long* next = nullptr;  // one queue counter per CTA
-    CU(cudaMallocAsync(&next, (size_t)grid * sizeof(unsigned long long), st));
-    auto launch = [&]() -> int {  // in a helper so that the counters are released on every path
+    // scratch (stream-ordered): the queue counters, and the per-env arrays the statistics pass reads
+    // when the caller does not ask for them
+    const bool post = stats_out || maxexp_out;
+    const size_t counters = ((size_t)grid * 8 + 15) / 16 * 16;
+    const size_t sz_boards = (post && !boards_io) ? n * 8 : 0, sz_score = (post && !score_out) ? n * 8 : 0;
+    const size_t sz_steps = (post && !steps_out) ? (n * 4 + 15) / 16 * 16 : 0, sz_ovf = post ? n : 0;
+    unsigned char* scratch = nullptr;
+    CU(cudaMallocAsync(&scratch, counters + sz_boards + sz_score + sz_steps + sz_ovf, st));
+    auto launch = [&]() -> int {  // in a helper so that the scratch is released on every path
+        unsigned long long* next = reinterpret_cast<unsigned long long*>(scratch);
+        unsigned char* p = scratch + counters;
+        u64* boards_buf = boards_io ? reinterpret_cast<u64*>(boards_io) : (sz_boards ? reinterpret_cast<u64*>(p) : nullptr);
+        p += sz_boards;
+        int64_t* score_buf = score_out ? score_out : (sz_score ? reinterpret_cast<int64_t*>(p) : nullptr);
+        p += sz_score;
+        int32_t* steps_buf = steps_out ? steps_out : (sz_steps ? reinterpret_cast<int32_t*>(p) : nullptr);
+        p += sz_steps;
+        uint8_t* ovf_buf = sz_ovf ? p : nullptr;
         CU(cudaMemsetAsync(next, 0, (size_t)grid * sizeof(unsigned long long), st));
+        if (ovf_buf) CU(cudaMemsetAsync(ovf_buf, 0, n, st));
+        const RolloutArgs a{seed, env_offset, n, (n + (size_t)grid - 1) / (size_t)grid, max_steps, boards_buf,
+                            score_buf, steps_buf, ovf_buf, trace, trace_stride, s->table, s->table_hashed, 1u,
+                            philox_key_schedule(seed)};
 #define G2048_LAUNCH_ROLL(SM, FR, TR, TH)                                                                  \
     do {                                                                                                   \
         if (SM) CU(cudaFuncSetAttribute(rollout_kernel<SM, FR, TR, TH>,                                    \
@@ -2261,11 +2482,16 @@ extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint3
 #undef G2048_LAUNCH_ROLL_T
 #undef G2048_LAUNCH_ROLL
         CU(cudaGetLastError());
+        if (post) {
+            rollout_stats_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, st>>>(
+                boards_buf, score_buf, steps_buf, ovf_buf, maxexp_out, reinterpret_cast<u64*>(stats_out), n);
+            CU(cudaGetLastError());
+        }
         return G2048_OK;
     };
     rc = launch();
-    const cudaError_t fe = cudaFreeAsync(next, st);
-    if (rc == G2048_OK && fe != cudaSuccess) return cuda_fail(fe, "cudaFreeAsync(next)");
+    const cudaError_t fe = cudaFreeAsync(scratch, st);
+    if (rc == G2048_OK && fe != cudaSuccess) return cuda_fail(fe, "cudaFreeAsync(rollout scratch)");
     return rc;
 }
 

@@ -18,7 +18,7 @@ from . import _cabi
 from ._cabi import check, lib
 
 __all__ = [
-    'StepOut', 'ExpandOut', 'RolloutOut', 'step', 'env_step', 'legal_flags', 'expand', 'reset',
+    'StepOut', 'ExpandOut', 'RolloutOut', 'step', 'env_step', 'selfplay_step', 'legal_flags', 'expand', 'reset',
     'observe', 'observe_onehot', 'nstep_returns', 'expect', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'step_host', 'row_table', 'set_impl', 'set_tuning', 'init',
     'pinned_empty', 'host_numa_info', 'step_host_copies', 'shutdown',
 ]
@@ -130,6 +130,47 @@ def env_step(boards: torch.Tensor, step_count: torch.Tensor, done: torch.Tensor,
                                    _ptr(actions), _ptr(spawns), seed & (2**64 - 1), env_offset,
                                    _ptr(env_keys), _ptr(rewards), _ptr(flags), _ptr(obs),
                                    _ptr(max_tile), _ptr(legal), n, _stream()))
+
+
+def selfplay_step(boards: torch.Tensor, step_count: torch.Tensor, done: torch.Tensor,
+                  total_reward: torch.Tensor, policy: Optional[torch.Tensor] = None, *,
+                  values: Optional[torch.Tensor] = None, actions: Optional[torch.Tensor] = None,
+                  spawns: Optional[torch.Tensor] = None, temperature: float = 1.0, seed: int = 0,
+                  env_offset: int = 0, record=None, rewards=None, norm_rewards=None, obs=None, legal=None,
+                  max_tile=None, actions_out=None, probs_out=None) -> None:
+    """One self-play iteration in one call (g2048_selfplay_step): sample an action per env from
+    ``policy`` f32[N,4] (core.py:381 sample_action semantics; ``actions`` u8[N] overrides the draw),
+    append the step to ``record`` (a ``selfplay.TrajectoryBuffer``: row = its device-side counter),
+    apply it in place as ``env_step`` does, and write the optional outputs for the NEW state."""
+    n = boards.numel()
+    _req(boards, torch.int64, 'boards')
+    _req(step_count, torch.int32, 'step_count', n)
+    _req(done, torch.uint8, 'done', n)
+    _req(total_reward, torch.float32, 'total_reward', n)
+    _opt(policy, torch.float32, 'policy', n * 4)
+    _opt(values, torch.float32, 'values', n)
+    actions = None if actions is None else _u8(actions, 'actions', n)
+    spawns = None if spawns is None else _u8(spawns, 'spawns', n)
+    if policy is None and actions is None:
+        raise ValueError('selfplay_step: give a policy to sample from or explicit actions')
+    _opt(rewards, torch.float32, 'rewards', n)
+    _opt(norm_rewards, torch.float32, 'norm_rewards', n)
+    _opt(obs, torch.float32, 'obs', n * 16)
+    _opt(legal, torch.bool, 'legal', n * 4)
+    _opt(max_tile, torch.int32, 'max_tile', n)
+    _opt(actions_out, torch.uint8, 'actions_out', n)
+    _opt(probs_out, torch.float32, 'probs_out', n * 4)
+    r = record
+    if r is not None and r.n != n:
+        raise ValueError('record: trajectory buffer is for a different number of envs')
+    tr = (lambda name: None) if r is None else (lambda name: _ptr(getattr(r, name)))
+    with torch.cuda.device(boards.device):
+        check(lib().g2048_selfplay_step(
+            _ptr(boards), _ptr(step_count), _ptr(done), _ptr(total_reward), _ptr(policy), _ptr(values),
+            _ptr(actions), _ptr(spawns), float(temperature), seed & (2**64 - 1), env_offset,
+            tr('t_dev'), 0 if r is None else r.capacity, tr('obs'), tr('legal'), tr('actions'), tr('rewards'),
+            tr('policies'), tr('values'), tr('active'), tr('lengths'), _ptr(rewards), _ptr(norm_rewards),
+            _ptr(obs), _ptr(legal), _ptr(max_tile), _ptr(actions_out), _ptr(probs_out), n, _stream()))
 
 
 def legal_flags(boards: torch.Tensor) -> torch.Tensor:

@@ -13,6 +13,7 @@ from __future__ import annotations
 
 from typing import NamedTuple, Optional
 
+import numpy as np  # noqa: F401  (type names in Trajectory)
 import torch
 
 from . import ops
@@ -46,8 +47,11 @@ class BatchedEnv:
         self._obs = torch.empty((n, 16), dtype=torch.float32, device=dev)
         self._legal = torch.empty((n, 4), dtype=torch.bool, device=dev)
         self._max_tile = torch.empty(n, dtype=torch.int32, device=dev)
+        self.policy_in = torch.full((n, 4), 0.25, dtype=torch.float32, device=dev)   # static inputs of step_policy
+        self.values_in = torch.zeros(n, dtype=torch.float32, device=dev)
         self._use_graph = graph
         self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._policy_graphs: dict = {}
         self._episode = 0
 
     @property
@@ -72,6 +76,7 @@ class BatchedEnv:
         bits = torch.tensor([1, 2, 4, 8], dtype=torch.uint8, device=self.device)
         self._legal.copy_((flags.unsqueeze(1) & bits) != 0)
         self._graph = None  # the Philox key changed
+        self._policy_graphs = {}
         return self._result()
 
     def _result(self) -> StepResult:
@@ -81,6 +86,45 @@ class BatchedEnv:
         ops.env_step(self.board, self.step_count, self._done8, self.total_reward, self._actions,
                      self._spawns, seed=self._key, rewards=self._reward, obs=self._obs,
                      max_tile=self._max_tile, legal=self._legal)
+
+    def step_policy(self, policy: torch.Tensor, values: Optional[torch.Tensor] = None, *,
+                    temperature: float = 1.0, record: Optional['TrajectoryBuffer'] = None,
+                    normalize: bool = False) -> StepResult:
+        """One whole self-play iteration as ONE graph launch (``g2048_selfplay_step``): draw an
+        action per env from ``policy`` f32[N,4] (core.py:381 sample_action: legal mask, renormalise,
+        temperature), record the step into ``record`` at its device-side cursor (observation and
+        legal mask of the current state, ``policy``, ``values``, action, reward), apply it, and
+        return the next observation / legal mask / reward / done.  ``policy`` and ``values`` are
+        copied into static buffers (pass ``env.policy_in`` / ``env.values_in`` themselves, filled in
+        place by the network, to skip the copy).  ``normalize``: ``StepResult.reward`` is the
+        reference's log-normalised reward (utils/normalize.py:6)."""
+        if policy.data_ptr() != self.policy_in.data_ptr():
+            self.policy_in.copy_(policy.reshape(self.n, 4), non_blocking=True)
+        if values is not None and values.data_ptr() != self.values_in.data_ptr():
+            self.values_in.copy_(values.reshape(self.n), non_blocking=True)
+        key = (id(record), float(temperature), values is not None, bool(normalize))
+        if record is not None:
+            record.t += 1   # host mirror of the device cursor (for slicing afterwards)
+
+        def launch():
+            ops.selfplay_step(self.board, self.step_count, self._done8, self.total_reward, self.policy_in,
+                              values=self.values_in if values is not None else None,
+                              temperature=temperature, seed=self._key, record=record,
+                              rewards=None if normalize else self._reward,
+                              norm_rewards=self._reward if normalize else None, obs=self._obs,
+                              legal=self._legal, max_tile=self._max_tile, actions_out=self._actions)
+        if not self._use_graph:
+            launch()
+            return self._result()
+        g = self._policy_graphs.get(key)
+        if g is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):   # capture records the launches, it does not run them
+                launch()
+            self._policy_graphs[key] = g
+        g.replay()
+        return self._result()
 
     def step(self, actions: torch.Tensor, spawns: Optional[torch.Tensor] = None) -> StepResult:
         """env.py:211 batched_step + the next observation / legal mask, one launch.  ``spawns``
@@ -108,12 +152,32 @@ class BatchedEnv:
         return self._result()
 
 
+class Trajectory(NamedTuple):
+    """The reference's per-game record (reinforce/training/replay_buffer.py:35-68): same fields, same
+    order, NumPy arrays on the host — what ``ReplayBuffer.add`` takes."""
+
+    observations: 'np.ndarray'   # float32 [T, 16]
+    actions: 'np.ndarray'        # int32   [T]
+    rewards: 'np.ndarray'        # float32 [T]
+    policies: 'np.ndarray'       # float32 [T, 4]
+    values: 'np.ndarray'         # float32 [T]
+    done: bool = True
+    total_reward: float = 0.0
+    max_tile: int = 0
+
+    def __len__(self) -> int:
+        return len(self.observations)
+
+
 class TrajectoryBuffer:
     """Device-side trajectory storage for N parallel games, time-major (the layout
     ``ops.nstep_returns`` reads): replaces the per-step ``np.array(...)`` host copies and the O(N)
-    Python bookkeeping of ``self_play.py:346-368``.  Step t holds the observation and legal mask
-    the policy saw, the action it chose, the reward of that action and whether the game was
-    already over (such steps carry reward 0 and do not count towards ``lengths``)."""
+    Python bookkeeping of ``self_play.py:346-368``.  Step t holds the observation and legal mask the
+    policy saw, the search policy and root value it produced (self_play.py:349-353 ``policies`` /
+    ``values``), the action drawn, the reward of that action and whether the game was still running
+    (finished games carry reward 0 and do not count towards ``lengths``).  ``t_dev`` is the write
+    cursor on the DEVICE: ``g2048_selfplay_step`` records at row ``t_dev`` and advances it, so a
+    recorded iteration needs no host-side index."""
 
     def __init__(self, capacity: int, n: int, device=None):
         dev = torch.device('cuda' if device is None else device)
@@ -122,56 +186,81 @@ class TrajectoryBuffer:
         self.legal = torch.zeros((capacity, n, 4), dtype=torch.bool, device=dev)
         self.actions = torch.zeros((capacity, n), dtype=torch.uint8, device=dev)
         self.rewards = torch.zeros((capacity, n), dtype=torch.float32, device=dev)
-        self.active = torch.zeros((capacity, n), dtype=torch.bool, device=dev)
+        self.policies = torch.zeros((capacity, n, 4), dtype=torch.float32, device=dev)
+        self.values = torch.zeros((capacity, n), dtype=torch.float32, device=dev)
+        self.active = torch.zeros((capacity, n), dtype=torch.uint8, device=dev)
         self.lengths = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.t_dev = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def clear(self) -> None:
         self.t = 0
         self.lengths.zero_()
+        self.t_dev.zero_()
 
-    def returns(self, values: torch.Tensor, discount: float, n_steps: int, td_lambda: float = 0.5) -> torch.Tensor:
+    def returns(self, values: Optional[torch.Tensor], discount: float, n_steps: int, td_lambda: float = 0.5) -> torch.Tensor:
         """n-step TD(lambda) targets float32[t,N] for the recorded steps (self_play.py:524);
-        ``values`` float32[t,N] are the caller's value estimates (search root values)."""
-        return ops.nstep_returns(self.rewards[:self.t], values.contiguous(), discount, n_steps, td_lambda,
+        ``values`` float32[t,N] are the caller's value estimates (default: the recorded root values)."""
+        v = self.values[:self.t] if values is None else values
+        return ops.nstep_returns(self.rewards[:self.t], v.contiguous(), discount, n_steps, td_lambda,
                                  lengths=self.lengths)
 
+    def to_trajectories(self, env: Optional['BatchedEnv'] = None) -> list:
+        """One ``Trajectory`` per game (replay_buffer.py:35-68), cut at each game's length: ONE
+        device-to-host copy per field, then NumPy slicing.  ``env`` supplies done / total_reward /
+        max_tile of the final states (self_play.py:377-386)."""
+        import numpy as np
+        t = self.t
+        obs = self.obs[:t].cpu().numpy()
+        act = self.actions[:t].cpu().numpy().astype(np.int32)
+        rew = self.rewards[:t].cpu().numpy()
+        pol = self.policies[:t].cpu().numpy()
+        val = self.values[:t].cpu().numpy()
+        lengths = self.lengths.cpu().numpy()
+        if env is not None:
+            done = env._done8.cpu().numpy().astype(bool)
+            total = env.total_reward.cpu().numpy()
+            top = env._max_tile.cpu().numpy()
+        out = []
+        for i in range(self.n):
+            k = int(lengths[i])
+            out.append(Trajectory(obs[:k, i].copy(), act[:k, i].copy(), rew[:k, i].copy(), pol[:k, i].copy(),
+                                  val[:k, i].copy(),
+                                  bool(done[i]) if env is not None else True,
+                                  float(total[i]) if env is not None else float(rew[:k, i].sum()),
+                                  int(top[i]) if env is not None else 0))
+        return out
 
-def play_recorded(env: BatchedEnv, policy, buf: TrajectoryBuffer, max_steps: Optional[int] = None) -> int:
-    """Self-play loop without a host copy per step: ``policy(StepResult) -> uint8[N] actions`` runs
-    on the device, every step is appended to ``buf``.  The only host sync is one ``all done``
-    check every 16 steps.  Returns the number of recorded steps."""
+
+def play_recorded(env: BatchedEnv, policy, buf: TrajectoryBuffer, max_steps: Optional[int] = None,
+                  temperature: float = 1.0) -> int:
+    """Self-play loop (self_play.py:314-368) without a host copy per step.  ``policy(StepResult)``
+    runs on the device and returns either ``(probs f32[N,4], values f32[N] | None)`` — the search
+    output; the action is then drawn inside ``g2048_selfplay_step`` — or ``uint8[N]`` actions (legacy
+    callers).  Every iteration is one graph launch that samples, records and steps; the only host
+    sync is one ``all done`` check every 16 steps.  Returns the number of recorded steps."""
     res = env._result()
     limit = buf.capacity if max_steps is None else min(max_steps, buf.capacity)
     buf.clear()
     while buf.t < limit:
-        t = buf.t
-        alive = ~res.done
-        buf.obs[t].copy_(res.observation)
-        buf.legal[t].copy_(res.legal_mask)
-        buf.active[t].copy_(alive)
-        buf.lengths.add_(alive.to(torch.int32))
-        actions = policy(res)
-        buf.actions[t].copy_(actions.reshape(-1))
-        res = env.step(actions)
-        buf.rewards[t].copy_(res.reward)
-        buf.t = t + 1
+        out = policy(res)
+        if isinstance(out, tuple):
+            probs, values = out
+            res = env.step_policy(probs, values, temperature=temperature, record=buf)
+        else:   # explicit actions: recorded as a one-hot policy
+            probs = torch.nn.functional.one_hot(out.reshape(-1).to(torch.int64), 4).to(torch.float32)
+            res = env.step_policy(probs, None, temperature=0.0, record=buf)
         if buf.t % 16 == 0 and bool(res.done.all().item()):
             break
     return buf.t
 
 
 def uniform_legal_policy(seed: int = 0):
-    """Random policy over the legal actions, on the device (the reference's evaluation baseline)."""
-    gen: list = []
-
-    def policy(res: StepResult) -> torch.Tensor:
-        if not gen:
-            g = torch.Generator(device=res.legal_mask.device)
-            g.manual_seed(seed)
-            gen.append(g)
-        w = res.legal_mask.to(torch.float32)
-        w[:, 0] += (w.sum(dim=1) == 0).to(torch.float32)  # finished games: any action (a no-op)
-        return torch.multinomial(w, 1, generator=gen[0]).reshape(-1).to(torch.uint8)
+    """Random policy over the legal actions (the reference's evaluation baseline): returns the legal
+    mask as an unnormalised policy, so the draw happens inside ``g2048_selfplay_step`` (Philox tag 4)
+    and an iteration stays one graph launch.  ``seed`` is kept for callers of the earlier signature;
+    the stream is keyed by the env's own Philox key."""
+    def policy(res: StepResult):
+        return res.legal_mask.to(torch.float32), None
     return policy
 
 
