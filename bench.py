@@ -415,6 +415,7 @@ def run_ours(args):
         if collective:
             total = max_over_ranks(total)
         per = [a.elapsed_time(b) / 1e3 for a, b in ev]
+        timed.last = per
         return total, sum(per) / len(per), min(per)
 
     # ---- primary: injected spawns (the mode that is bit-exact against the reference) ----
@@ -464,7 +465,7 @@ def run_ours(args):
     rollout = {
         'envs_total': n_roll, 'envs_per_gpu': n_roll // world, 'scaling': 'strong', 'seed': ROLL_SEED,
         'env_steps': r_stats.total_steps, 'mean_length': r_stats.total_steps / n_roll,
-        'ms': ro_total / 3 * 1e3, 'best_ms_rank0': ro_best * 1e3,
+        'ms': ro_total / 3 * 1e3, 'best_ms_rank0': ro_best * 1e3, 'per_call_ms_rank0': [round(x * 1e3, 3) for x in timed.last],
         'env_steps_per_sec': r_stats.total_steps * 3 / ro_total, 'unit': UNIT,
         'collective': 'one all_gather_into_tensor of the 24-word statistics vector per rollout (NCCL), '
                       'inside the timed region' if world > 1 else 'none (1 GPU)',

@@ -182,6 +182,10 @@ int g2048_selfplay_step(uint64_t* boards, int32_t* step_count, uint8_t* done, fl
 
 /* Legal mask + done of boards (gamemove.py:45, core.py:275/:305); flags has the LEGAL/DONE bits. */
 int g2048_mask(const uint64_t* boards, uint8_t* flags, size_t n, void* stream);
+/* The same as arrays the reference's callers index directly: legal u8[n*4], one 0/1 byte per action
+ * (core.py:275 legal_actions_mask / env.py:245 batched_get_legal_actions as bool[n,4]) and done u8[n]
+ * (core.py:305 is_done: no legal action).  Either may be NULL. */
+int g2048_legal_actions(const uint64_t* boards, uint8_t* legal, uint8_t* done, size_t n, void* stream);
 
 /*
  * MCTS leaf expansion (gameboard.py:105 latent_state for the four actions, :132

@@ -39,6 +39,7 @@ PROTOTYPES = {
     'g2048_selfplay_step': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_float, _U64, _U64, _P, _U32,
                                       _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     'g2048_mask': (C.c_int, [_P, _P, _SZ, _P]),
+    'g2048_legal_actions': (C.c_int, [_P, _P, _P, _SZ, _P]),
     'g2048_expand': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int, _SZ, _P]),
     'g2048_expand_children': (C.c_int, [_P, _P, _P, _P, C.c_int, _SZ, _P]),
     'g2048_expand_compact': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P, _SZ, _P]),

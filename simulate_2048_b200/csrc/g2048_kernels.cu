@@ -89,6 +89,11 @@ struct DeviceState {
     int sms = 0;
     size_t smem_optin = 0;
     int children_occupancy = 1;  // resident CTAs per SM of expand_children_kernel
+    // Stream-ordered scratch (queue counters, scan aggregates, per-env rollout results) comes from
+    // the library's own pool with an unlimited release threshold: the default pool hands its memory
+    // back to the driver at every synchronisation, which made each call after a host sync pay for
+    // fresh virtual-memory mappings (hundreds of microseconds).
+    cudaMemPool_t pool = nullptr;
 };
 static DeviceState g_dev[64];
 static std::atomic<int> g_impl{G2048_IMPL_AUTO};
@@ -127,6 +132,14 @@ static int current_state(DeviceState** out) {
             CU(cudaDeviceSynchronize());
             int rc = device_occupancy(s);
             if (rc) return rc;
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            CU(cudaMemPoolCreate(&s.pool, &props));
+            unsigned long long keep = ~0ull;
+            CU(cudaMemPoolSetAttribute(s.pool, cudaMemPoolAttrReleaseThreshold, &keep));
             s.ready.store(true, std::memory_order_release);
         }
     }
@@ -986,6 +999,30 @@ extern "C" int g2048_mask(const uint64_t* boards, uint8_t* flags, size_t n, void
     return G2048_OK;
 }
 
+// legal mask as one 0/1 byte per action (a bool[n,4] array: core.py:275, env.py:245) and done bytes
+__global__ void __launch_bounds__(256) legal_bool_kernel(const u64* __restrict__ boards, u32* __restrict__ legal,
+                                                         uint8_t* __restrict__ done, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const u64 b = boards[i];
+        const u32 lo = (u32)b, hi = (u32)(b >> 32);
+        const u32 f = fast::legal_mask(lo, hi, fast::nz8(lo, 1u), fast::nz8(hi, 1u), 1u);
+        if (legal) legal[i] = (f & 1u) | ((f & 2u) << 7) | ((f & 4u) << 14) | ((f & 8u) << 21);
+        if (done) done[i] = f == 0u ? 1 : 0;
+    }
+}
+
+extern "C" int g2048_legal_actions(const uint64_t* boards, uint8_t* legal, uint8_t* done, size_t n, void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!boards || (!legal && !done) || !aligned(legal, 4)) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    legal_bool_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const u64*>(boards), reinterpret_cast<u32*>(legal), done, n);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
 // Warp-cooperative 16-values-per-board writers (observe, unpack).  A warp takes 32 boards = 2 KiB
 // of output; lane l writes the 16-byte chunks l, l + 32, l + 64, l + 96 of it, i.e. row (q & 3) of
 // board (q >> 2) for chunk q, so every store instruction covers 512 contiguous bytes.  (One board
@@ -1819,7 +1856,7 @@ extern "C" int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* re
     u64* after_buf = reinterpret_cast<u64*>(after);
     uint8_t* count_buf = child_count;
     if (!after_buf || !count_buf) {
-        CU(cudaMallocAsync(&scratch, n * 36, st));
+        CU(cudaMallocFromPoolAsync(&scratch, n * 36, s->pool, st));
         if (!after_buf) after_buf = reinterpret_cast<u64*>(scratch);
         if (!count_buf) count_buf = reinterpret_cast<uint8_t*>(scratch) + n * 32;
     }
@@ -1884,7 +1921,7 @@ extern "C" int g2048_expand_compact(const uint64_t* boards, uint64_t* after, int
     if (n < kExpandSmemMinBoards) {
         const size_t tiles = (n + kScanWarps * 32 - 1) / (kScanWarps * 32);
         unsigned long long* scratch = nullptr;
-        CU(cudaMallocAsync(&scratch, (tiles + 2) * sizeof(unsigned long long), st));
+        CU(cudaMallocFromPoolAsync(&scratch, (tiles + 2) * sizeof(unsigned long long), s->pool, st));
         auto launch = [&]() -> int {
             CU(cudaMemsetAsync(scratch, 0, (tiles + 2) * sizeof(unsigned long long), st));
             const ExpandArgs a{reinterpret_cast<const u64*>(boards), reinterpret_cast<u64*>(after), rewards, mask,
@@ -1904,7 +1941,7 @@ extern "C" int g2048_expand_compact(const uint64_t* boards, uint64_t* after, int
     unsigned char* scratch = nullptr;  // [tile sums | afterstates | child counts] as needed
     const size_t sums_bytes = (tiles * 8 + 15) / 16 * 16;
     const size_t need = sums_bytes + (after ? 0 : n * 32) + (child_count ? 0 : n * 4);
-    CU(cudaMallocAsync(&scratch, need, st));
+    CU(cudaMallocFromPoolAsync(&scratch, need, s->pool, st));
     auto launch = [&]() -> int {
         unsigned long long* sums = reinterpret_cast<unsigned long long*>(scratch);
         u64* after_buf = after ? reinterpret_cast<u64*>(after) : reinterpret_cast<u64*>(scratch + sums_bytes);
@@ -2298,7 +2335,7 @@ __device__ __forceinline__ u32 roll_step(RollSlot& s, const RolloutArgs& a, cons
     if (in_hi) { ah += tile; nhi += bit3; } else { al += tile; nlo += bit3; }
     if (kTrace) {
         const u32 step = s.t - 2u;
-        if (playing && step + 1u < a.trace_stride) {
+        if (s.alive && playing && step + 1u < a.trace_stride) {  // (a slot without a game replays env 0: no trace)
             const u32 cell = ((__ffs(bit3) - 1u) >> 2) + (in_hi ? 8u : 0u);
             a.trace[(size_t)(roll_env(s) - a.env_offset) * a.trace_stride + step] =
                 (uint8_t)(0x80u | s.act | (cell << 2) | ((exp - 1u) << 6));
@@ -2444,7 +2481,7 @@ extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint3
     const size_t sz_boards = (post && !boards_io) ? n * 8 : 0, sz_score = (post && !score_out) ? n * 8 : 0;
     const size_t sz_steps = (post && !steps_out) ? (n * 4 + 15) / 16 * 16 : 0, sz_ovf = post ? n : 0;
     unsigned char* scratch = nullptr;
-    CU(cudaMallocAsync(&scratch, counters + sz_boards + sz_score + sz_steps + sz_ovf, st));
+    CU(cudaMallocFromPoolAsync(&scratch, counters + sz_boards + sz_score + sz_steps + sz_ovf, s->pool, st));
     auto launch = [&]() -> int {  // in a helper so that the scratch is released on every path
         unsigned long long* next = reinterpret_cast<unsigned long long*>(scratch);
         unsigned char* p = scratch + counters;
@@ -2800,6 +2837,8 @@ extern "C" int g2048_shutdown(void) {
         cudaFree(s.table);
         cudaFree(s.table_hashed);
         s.table = s.table_hashed = nullptr;
+        if (s.pool) cudaMemPoolDestroy(s.pool);
+        s.pool = nullptr;
         s.ready.store(false, std::memory_order_release);
     }
     if (have_dev) cudaSetDevice(keep);

@@ -73,6 +73,8 @@ def _like(packed: Array, template: Array) -> Array:
 
 
 def _actions(action, n: int, device) -> Array:
+    if isinstance(action, torch.Tensor) and action.dtype == torch.uint8 and action.is_cuda and action.numel() == n:
+        return action.reshape(-1)   # the kernels read only the low two bits (rot90(k) is modulo 4)
     if isinstance(action, int):
         return torch.full((n,), action & 3, dtype=torch.uint8, device=device)
     a = torch.as_tensor(action, device=device).reshape(-1)
@@ -130,10 +132,19 @@ def merge_row(row: Array) -> Tuple[Array, Array]:
 
 # -- core.py:173 fill_cells / :234 next_state / :324 create_initial_board ----------------------
 
+def _need_randomness(name: str, key: Key, spawns) -> None:
+    """The reference requires a PRNG key (core.py:173, :234); a silent default would give every
+    call the same Philox counter (seed 0, env i, step 0), i.e. the same draw for a whole game."""
+    if key is None and spawns is None:
+        raise TypeError(f'{name}: pass key= (an int or a (2,) uint32 key) or spawns= (injected spawn bytes)')
+
+
 def fill_cells(state: Array, key: Key = None, *, spawns: Optional[Array] = None, step: int = 0,
                tag: int = 0) -> Array:
     """core.py:173 — add one tile (2 w.p. 0.9, 4 w.p. 0.1) on a uniformly chosen empty cell; a full
-    board is returned unchanged."""
+    board is returned unchanged.  ``key`` (or ``spawns``) is mandatory, as in the reference; split
+    or advance it between calls (``step=`` advances the counter under one key)."""
+    _need_randomness('fill_cells', key, spawns)
     packed = pack_boards(state).reshape(-1)
     new = ops.spawn(packed, spawns, seed=key_to_seed(key), step=step, tag=tag)
     return _like(new, state)
@@ -142,7 +153,9 @@ def fill_cells(state: Array, key: Key = None, *, spawns: Optional[Array] = None,
 def next_state(state: Array, action, key: Key = None, *, spawns: Optional[Array] = None,
                step: int = 0) -> Tuple[Array, Array]:
     """core.py:234 — full transition: afterstate, then one new tile iff the board changed; the
-    reward is float32 and 0 for an illegal move (core.py:270)."""
+    reward is float32 and 0 for an illegal move (core.py:270).  ``key`` (or ``spawns``) is
+    mandatory, as in the reference."""
+    _need_randomness('next_state', key, spawns)
     packed = pack_boards(state).reshape(-1)
     out = ops.step(packed, _actions(action, packed.numel(), packed.device), spawns,
                    seed=key_to_seed(key), step_base=step)
@@ -161,11 +174,10 @@ def create_initial_board(key: Key = None, *, n: Optional[int] = None,
 # -- core.py:275 legal_actions_mask / :305 is_done ----------------------------------------------
 
 def legal_actions_mask(state: Array) -> Array:
-    """core.py:275 — bool[..., 4] in the order [left, up, right, down]."""
+    """core.py:275 — bool[..., 4] in the order [left, up, right, down] (one launch: the kernel
+    writes the bool array itself)."""
     packed = pack_boards(state).reshape(-1)
-    flags = ops.legal_flags(packed)
-    mask = (flags.unsqueeze(1) & _bits(flags.device)) != 0
-    return mask.reshape(*_lead(state), 4)
+    return ops.legal_actions(packed).reshape(*_lead(state), 4)
 
 
 def is_done(state: Array) -> Array:

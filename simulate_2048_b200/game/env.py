@@ -42,19 +42,29 @@ class GameState(NamedTuple):
 
 
 def _split_keys(keys: Keys, n: int):
-    """-> (seed, env_keys, spawns)"""
+    """-> (seed, env_keys, spawns).  The interpretation follows dtype and shape alone:
+         None / int                      one Philox key for the batch (seed)
+         uint8[n]                        injected spawn bytes
+         int64[n]                        one Philox key per env
+         (u)int32 / int64 [n, 2]         JAX-style per-env keys (two 32-bit words each)
+         anything with 1 or 2 elements   a single key (scalar, or the two words of a JAX key)
+    so an int64[2] tensor with n == 2 is two per-env keys, and a uint32[2] tensor is ONE key."""
     if keys is None:
         return 0, None, None
     if isinstance(keys, int):
         return keys, None, None
     if keys.dtype == torch.uint8:
+        if keys.numel() != n:
+            raise ValueError(f'spawns: expected {n} bytes, got {keys.numel()}')
         return 0, None, keys.reshape(-1)
-    if keys.dtype == torch.int64 and keys.numel() == n and n != 2:
-        return 0, keys.reshape(-1).contiguous(), None
-    if keys.dim() == 2 and keys.shape == (n, 2):  # JAX-style uint32[N, 2] keys
+    if keys.dim() == 2 and keys.shape == (n, 2):
         k = keys.to(torch.int64)
         return 0, ((k[:, 0] & 0xFFFFFFFF) | ((k[:, 1] & 0xFFFFFFFF) << 32)).contiguous(), None
-    return core.key_to_seed(keys), None, None
+    if keys.dtype == torch.int64 and keys.dim() == 1 and keys.numel() == n:
+        return 0, keys.contiguous(), None
+    if keys.numel() in (1, 2):
+        return core.key_to_seed(keys), None, None
+    raise ValueError(f'keys: cannot interpret a {keys.dtype} tensor of shape {tuple(keys.shape)} for {n} envs')
 
 
 def batched_reset(keys: Keys = None, n: Optional[int] = None, *, spawns: Optional[Array] = None,
@@ -84,7 +94,10 @@ def batched_step(states: GameState, actions: Array, keys: Keys = None, *, inplac
     """env.py:211 — one launch for the whole batch.  Returns (states, rewards f32[N],
     dones bool[N], info) with info = {max_tile, step_count, total_reward} (env.py:127-131)."""
     n = states.board.numel()
-    seed, env_keys, spawns = _split_keys(keys, n)
+    if isinstance(keys, int):       # the common call: one seed for the batch
+        seed, env_keys, spawns = keys, None, None
+    else:
+        seed, env_keys, spawns = _split_keys(keys, n)
     if inplace:
         board, sc, tr = states.board, states.step_count, states.total_reward
         done8 = states.done.view(torch.uint8)

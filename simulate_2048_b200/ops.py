@@ -18,14 +18,33 @@ from . import _cabi
 from ._cabi import check, lib
 
 __all__ = [
-    'StepOut', 'ExpandOut', 'RolloutOut', 'step', 'env_step', 'selfplay_step', 'legal_flags', 'expand', 'reset',
-    'observe', 'observe_onehot', 'nstep_returns', 'expect', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'step_host', 'row_table', 'set_impl', 'set_tuning', 'init',
+    'StepOut', 'ExpandOut', 'RolloutOut', 'step', 'env_step', 'selfplay_step', 'legal_flags', 'legal_actions', 'expand', 'reset',
+    'observe', 'observe_onehot', 'nstep_returns', 'expect', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'unpack_into', 'step_host', 'row_table', 'set_impl', 'set_tuning', 'init',
     'pinned_empty', 'host_numa_info', 'step_host_copies', 'shutdown',
 ]
 
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+class _NoSwitch:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
+
+
+_NO_SWITCH = _NoSwitch()
+
+
+def _on(device):
+    """Device guard that costs nothing when ``device`` is already current (``torch.cuda.device`` is
+    ~5 us per call, as much as a small launch)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_SWITCH
+    return torch.cuda.device(device)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -96,7 +115,7 @@ def step(boards: torch.Tensor, actions: torch.Tensor, spawns: Optional[torch.Ten
         _req(out.boards, torch.int64, 'out.boards', n)
         _req(out.rewards, torch.int32, 'out.rewards', n)
         _req(out.flags, torch.uint8, 'out.flags', n)
-    with torch.cuda.device(boards.device):
+    with _on(boards.device):
         check(lib().g2048_step(_ptr(boards), _ptr(actions), _ptr(spawns), seed & (2**64 - 1),
                                env_offset, _ptr(step_ctr), step_base & 0xFFFFFFFF, _ptr(env_keys),
                                _ptr(done_in), _ptr(out.boards), _ptr(out.rewards), _ptr(out.flags),
@@ -125,7 +144,7 @@ def env_step(boards: torch.Tensor, step_count: torch.Tensor, done: torch.Tensor,
     _opt(obs, torch.float32, 'obs', n * 16)
     _opt(max_tile, torch.int32, 'max_tile', n)
     _opt(legal, torch.bool, 'legal', n * 4)
-    with torch.cuda.device(boards.device):
+    with _on(boards.device):
         check(lib().g2048_env_step(_ptr(boards), _ptr(step_count), _ptr(done), _ptr(total_reward),
                                    _ptr(actions), _ptr(spawns), seed & (2**64 - 1), env_offset,
                                    _ptr(env_keys), _ptr(rewards), _ptr(flags), _ptr(obs),
@@ -164,7 +183,7 @@ def selfplay_step(boards: torch.Tensor, step_count: torch.Tensor, done: torch.Te
     if r is not None and r.n != n:
         raise ValueError('record: trajectory buffer is for a different number of envs')
     tr = (lambda name: None) if r is None else (lambda name: _ptr(getattr(r, name)))
-    with torch.cuda.device(boards.device):
+    with _on(boards.device):
         check(lib().g2048_selfplay_step(
             _ptr(boards), _ptr(step_count), _ptr(done), _ptr(total_reward), _ptr(policy), _ptr(values),
             _ptr(actions), _ptr(spawns), float(temperature), seed & (2**64 - 1), env_offset,
@@ -173,11 +192,24 @@ def selfplay_step(boards: torch.Tensor, step_count: torch.Tensor, done: torch.Te
             _ptr(obs), _ptr(legal), _ptr(max_tile), _ptr(actions_out), _ptr(probs_out), n, _stream()))
 
 
+def legal_actions(boards: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bool[N,4] legal-action mask straight from the kernel (g2048_legal_actions; core.py:275)."""
+    _req(boards, torch.int64, 'boards')
+    n = boards.numel()
+    if out is None:
+        out = torch.empty((n, 4), dtype=torch.bool, device=boards.device)
+    else:
+        _req(out, torch.bool, 'out', n * 4)
+    with _on(boards.device):
+        check(lib().g2048_legal_actions(_ptr(boards), _ptr(out), None, n, _stream()))
+    return out
+
+
 def legal_flags(boards: torch.Tensor) -> torch.Tensor:
     """uint8[N]: bits 0-3 legal (L,U,R,D), bit 4 done (g2048_mask; gamemove.py:45, core.py:275)."""
     _req(boards, torch.int64, 'boards')
     flags = torch.empty(boards.numel(), dtype=torch.uint8, device=boards.device)
-    with torch.cuda.device(boards.device):
+    with _on(boards.device):
         check(lib().g2048_mask(_ptr(boards), _ptr(flags), boards.numel(), _stream()))
     return flags
 
@@ -230,7 +262,7 @@ def expand(boards: torch.Tensor, children: str = 'none', zero_fill: bool = True,
     if out is not None:  # reuse a previous result's buffers: no allocation
         if out.after.shape[0] != n or (layout != _cabi.CHILDREN_NONE and out.children is None):
             raise ValueError('out: buffers do not match this call')
-        with torch.cuda.device(dev):
+        with _on(dev):
             if layout == _cabi.CHILDREN_COMPACT and child_offsets is None:
                 total = out.total if out.total is not None else torch.empty(2, dtype=torch.int64, device=dev)
                 _req(out.child_offsets, torch.int64, 'out.child_offsets', n)
@@ -250,7 +282,7 @@ def expand(boards: torch.Tensor, children: str = 'none', zero_fill: bool = True,
     num_empty = torch.empty((n, 4), dtype=torch.uint8, device=dev)
     child_count = torch.empty((n, 4), dtype=torch.uint8, device=dev)
     ch = off = None
-    with torch.cuda.device(dev):
+    with _on(dev):
         if layout == _cabi.CHILDREN_COMPACT:
             off = torch.empty(n, dtype=torch.int64, device=dev)
             total = torch.zeros(2, dtype=torch.int64, device=dev)
@@ -285,7 +317,7 @@ def after_state(boards: torch.Tensor, want_children: bool = True):
     ch = torch.empty((n, 16, 2), dtype=torch.int64, device=dev) if want_children else None  # every slot is written
     ne = torch.empty(n, dtype=torch.uint8, device=dev)
     ec = torch.empty(n, dtype=torch.int16, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         check(lib().g2048_after_state(_ptr(boards), _ptr(ch), _ptr(ne), _ptr(ec), n, _stream()))
     return ch, ne, ec
 
@@ -298,7 +330,7 @@ def reset(n: int, *, seed: int = 0, env_offset: int = 0, env_keys: Optional[torc
     if spawns is not None:
         spawns = _u8(spawns, 'spawns', 2 * n)
     boards = torch.empty(n, dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
+    with _on(dev):
         check(lib().g2048_reset(seed & (2**64 - 1), env_offset, _ptr(env_keys), _ptr(spawns),
                                 _ptr(boards), n, _stream()))
     return boards
@@ -315,7 +347,7 @@ def spawn(boards: torch.Tensor, spawns: Optional[torch.Tensor] = None, *, seed: 
     _opt(env_keys, torch.int64, 'env_keys', n)
     _opt(flags, torch.uint8, 'flags', n)
     out = boards.clone()
-    with torch.cuda.device(boards.device):
+    with _on(boards.device):
         check(lib().g2048_spawn(_ptr(out), _ptr(spawns), seed & (2**64 - 1), env_offset,
                                 _ptr(env_keys), step & 0xFFFFFFFF, tag & 0xFFFFFFFF, _ptr(flags), n,
                                 _stream()))
@@ -328,7 +360,7 @@ def observe(boards: torch.Tensor, want_max: bool = True):
     n = boards.numel()
     obs = torch.empty((n, 16), dtype=torch.float32, device=boards.device)
     mx = torch.empty(n, dtype=torch.uint8, device=boards.device) if want_max else None
-    with torch.cuda.device(boards.device):
+    with _on(boards.device):
         check(lib().g2048_observe(_ptr(boards), _ptr(obs), _ptr(mx), n, _stream()))
     return obs, mx
 
@@ -339,7 +371,7 @@ def observe_onehot(boards: torch.Tensor, width: int = 31) -> torch.Tensor:
     _req(boards, torch.int64, 'boards')
     n = boards.numel()
     out = torch.empty((n, 16, width), dtype=torch.uint8, device=boards.device)
-    with torch.cuda.device(boards.device):
+    with _on(boards.device):
         check(lib().g2048_observe_onehot(_ptr(boards), _ptr(out), int(width), n, _stream()))
     return out
 
@@ -354,7 +386,7 @@ def expect(child_values: torch.Tensor, ex: 'ExpandOut', discount: float = 1.0,
     n = ex.after.shape[0]
     _opt(child_values, torch.float32, 'child_values', ex.children.numel())
     q = torch.empty((n, 4), dtype=torch.float32, device=ex.after.device)
-    with torch.cuda.device(ex.after.device):
+    with _on(ex.after.device):
         check(lib().g2048_expect(_ptr(child_values), _ptr(ex.child_count), _ptr(ex.child_offsets),
                                  _ptr(ex.rewards) if use_rewards else None, float(discount),
                                  float(illegal_value), _ptr(q), n, _stream()))
@@ -377,7 +409,7 @@ def nstep_returns(rewards: torch.Tensor, values: torch.Tensor, discount: float, 
     if out is None:
         out = torch.empty_like(rewards)
     _opt(out, torch.float32, 'out', T * n)
-    with torch.cuda.device(rewards.device):
+    with _on(rewards.device):
         check(lib().g2048_nstep_returns(_ptr(rewards), _ptr(values), _ptr(lengths), float(discount),
                                         int(n_steps), float(td_lambda), _ptr(out), T, n, _stream()))
     return out
@@ -411,7 +443,7 @@ def rollout(n: int, *, seed: int = 0, env_offset: int = 0, max_steps: int = 1 <<
     else:
         _req(stats, torch.int64, 'stats', _cabi.STATS_WORDS)
     trace = torch.zeros((n, trace_stride), dtype=torch.uint8, device=dev) if trace_stride else None
-    with torch.cuda.device(dev):
+    with _on(dev):
         check(lib().g2048_rollout(seed & (2**64 - 1), env_offset, n, max_steps & 0xFFFFFFFF,
                                   1 if from_reset else 0, _ptr(boards), _ptr(score), _ptr(steps),
                                   _ptr(mx), _ptr(stats), _ptr(trace), trace_stride, _stream()))
@@ -426,7 +458,7 @@ def pack(tiles: torch.Tensor) -> torch.Tensor:
     n = tiles.numel() // 16
     boards = torch.empty(n, dtype=torch.int64, device=tiles.device)
     status = torch.zeros(1, dtype=torch.int32, device=tiles.device)
-    with torch.cuda.device(tiles.device):
+    with _on(tiles.device):
         check(lib().g2048_pack(_ptr(tiles), _ptr(boards), _ptr(status), n, _stream()))
     code = int(status.item())
     if code:
@@ -439,12 +471,20 @@ def unpack(boards: torch.Tensor) -> torch.Tensor:
     _req(boards, torch.int64, 'boards')
     n = boards.numel()
     tiles = torch.empty((n, 4, 4), dtype=torch.int32, device=boards.device)
-    with torch.cuda.device(boards.device):
+    with _on(boards.device):
         check(lib().g2048_unpack(_ptr(boards), _ptr(tiles), n, _stream()))
     return tiles
 
 
 _NP_DTYPES = {torch.int64: np.int64, torch.int32: np.int32, torch.uint8: np.uint8, torch.float32: np.float32}
+
+
+def unpack_into(boards: torch.Tensor, tiles: torch.Tensor) -> None:
+    """g2048_unpack into a preallocated int32[N,4,4] tensor."""
+    _req(boards, torch.int64, 'boards')
+    _req(tiles, torch.int32, 'tiles', boards.numel() * 16)
+    with _on(boards.device):
+        check(lib().g2048_unpack(_ptr(boards), _ptr(tiles), boards.numel(), _stream()))
 
 
 def pinned_empty(n: int, dtype, device: Optional[int] = None) -> np.ndarray:

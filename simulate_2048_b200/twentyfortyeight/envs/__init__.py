@@ -2,4 +2,6 @@
 
 from .twentyfortyeight import TwentyFortyEight  # noqa: E402,F401  (manuals_control.py:7 imports it from here)
 
-__all__ = ['TwentyFortyEight']
+from .vector import VectorTwentyFortyEight  # noqa: E402,F401  (N lock-step games, one launch per step)
+
+__all__ = ['TwentyFortyEight', 'VectorTwentyFortyEight']
