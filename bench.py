@@ -680,6 +680,62 @@ def run_ours(args):
         extra['selfplay_4096_fused'] = {'us_per_iteration': dt / 200 * 1e6, 'env_steps_per_sec': 4096 * 200 / dt,
                                         'note': 'BatchedEnv: next observation, legal mask, reward, done from ONE '
                                                 'graph-replayed launch per iteration'}
+        # the whole self-play iteration (sample from a policy, record, step) as ONE graph launch
+        from simulate_2048_b200.selfplay import TrajectoryBuffer
+        tbuf = TrajectoryBuffer(256, 4096, device=dev)
+        benv.reset()
+        pol = torch.rand((4096, 4), device=dev, generator=gen)
+        val = torch.rand(4096, device=dev, generator=gen)
+        benv.policy_in.copy_(pol)
+        benv.values_in.copy_(val)
+        for t in range(3):
+            benv.step_policy(benv.policy_in, benv.values_in, record=tbuf)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in range(200):
+            benv.step_policy(benv.policy_in, benv.values_in, record=tbuf)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        extra['selfplay_4096_policy_recorded'] = {
+            'us_per_iteration': dt / 200 * 1e6, 'env_steps_per_sec': 4096 * 200 / dt,
+            'note': 'BatchedEnv.step_policy: g2048_selfplay_step (sample_action semantics, trajectory record with '
+                    'policies / values, env step, next observation + legal mask) replayed from one CUDA graph'}
+        # BASELINE configs[0] through the drop-in: 1024 random-policy games to game-over, lock-step
+        from simulate_2048_b200.twentyfortyeight.envs import TwentyFortyEight, VectorTwentyFortyEight
+        venv = VectorTwentyFortyEight(1024, seed=0)
+        rng = np.random.default_rng(0)
+        best = None
+        for rep in range(3):
+            venv.reset(seed=rep)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_steps = 0
+            while True:
+                fin = venv.is_finished
+                if fin.all():
+                    break
+                mask = venv.legal_actions_mask
+                acts = (rng.random((1024, 4)) * mask).argmax(axis=1)
+                venv.step(acts)
+                n_steps += int((~fin).sum())
+            dt = time.perf_counter() - t0
+            if best is None or n_steps / dt > best[0]:
+                best = (n_steps / dt, n_steps, dt)
+        single = TwentyFortyEight()
+        single.reset(seed=0)
+        t0 = time.perf_counter()
+        k1 = 0
+        while not single.is_finished and k1 < 200:
+            single.step(int(rng.integers(4)))
+            k1 += 1
+        dt1 = time.perf_counter() - t0
+        extra['config1_through_dropin'] = {
+            'games': 1024, 'env_steps': best[1], 'seconds': best[2], 'env_steps_per_sec': best[0],
+            'api': 'simulate_2048_b200.twentyfortyeight.envs.VectorTwentyFortyEight (lock-step games, host policy '
+                   'over the returned legal masks, one env_step launch + pinned copies per step), best of 3',
+            'single_env_class_steps_per_sec': k1 / dt1,
+            'single_env_note': 'the one-game TwentyFortyEight mirror pays a host/device round trip per call; the '
+                               'vector env is the fast form of the drop-in'}
         # row (f2): batched expectimax (expand + value function on every leaf + probability-weighted backup)
         from simulate_2048_b200 import selfplay
 
@@ -694,6 +750,10 @@ def run_ours(args):
             xm[f'depth{depth}_{n_x}'] = {'ms': t_x * 1e3, 'root_boards_per_sec': n_x / t_x,
                                         'first_level_children': int(ex_x.children.numel())}
             del ex_x
+        _, t_w, _ = timed(lambda: selfplay.expectimax(boards[:4096].contiguous(), leaf_value, depth=2, widen=4), 5, 2,
+                          collective=False)
+        xm['depth2_4096_widen4'] = {'ms': t_w * 1e3, 'root_boards_per_sec': 4096 / t_w,
+                                    'note': 'progressive widening: 4 sampled chance children per afterstate and level'}
         xm['note'] = 'selfplay.expectimax: one g2048_expand per level, leaf values from a torch function, g2048_expect backup'
         extra['expectimax'] = xm
         # row (f4): n-step TD(lambda) targets over device trajectory buffers [T=200, N=4096]

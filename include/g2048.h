@@ -52,7 +52,8 @@
  *     rollout policy: the NEXT action is the hi32(f2 * n_legal)-th legal action of the new board.
  *   Tags: 0 = play step, 1 / 2 = first / second reset tile (step 0; the first rollout action is
  *   digit 3 of the tag-2 word), 3 = first action of a rollout that starts from a given board,
- *   4 = the action draw of g2048_selfplay_step (step = the env's step_count).
+ *   4 = the action draw of g2048_selfplay_step (step = the env's step_count),
+ *   5 = a sampled chance child of g2048_sample_children (step = draw index).
  *
  * Flags byte (per env):
  */
@@ -89,6 +90,7 @@ extern "C" {
 #define G2048_PHILOX_TAG_RESET1 2u
 #define G2048_PHILOX_TAG_START 3u
 #define G2048_PHILOX_TAG_POLICY 4u
+#define G2048_PHILOX_TAG_CHANCE 5u
 
 /* children layout for g2048_expand */
 #define G2048_CHILDREN_NONE 0
@@ -265,6 +267,23 @@ int g2048_observe_onehot(const uint64_t* boards, uint8_t* out, int width, size_t
 int g2048_expect(const float* child_values, const uint8_t* child_count, const int64_t* child_offsets,
                  const int32_t* rewards, float discount, float illegal_value, float* q_out, size_t n,
                  void* stream);
+
+/*
+ * Progressive widening (gameboard.py:174 after_state_lazy + :205 generate_outcome, docs/project.md:49):
+ * instead of all 2 E chance children of an afterstate, k children DRAWN from the spawn distribution
+ * (cell uniform over the empties, tile 2 w.p. 0.9 / 4 w.p. 0.1, with replacement).
+ *   after[n*4], child_count[n*4] as written by g2048_expand (0 = illegal action: its k slots are 0);
+ *   children[(i*4 + a)*k + j] = draw j of (board i, action a), from the Philox word of
+ *   (seed, env_offset + i, draw_base + a*k + j, tag 5), digits 1 and 2 as for a spawn.
+ *   An afterstate without an empty cell is its own child (gameboard.py:158-159).
+ * g2048_expect_sampled is the matching backup:
+ *   q[i*4 + a] = rewards[i*4 + a] + discount * mean_j child_values[(i*4 + a)*k + j]
+ * (an unbiased estimate of g2048_expect's expectation), `illegal_value` for an illegal action.
+ */
+int g2048_sample_children(const uint64_t* after, const uint8_t* child_count, uint32_t k, uint64_t seed,
+                          uint64_t env_offset, uint32_t draw_base, uint64_t* children, size_t n, void* stream);
+int g2048_expect_sampled(const float* child_values, const uint8_t* child_count, const int32_t* rewards,
+                         uint32_t k, float discount, float illegal_value, float* q_out, size_t n, void* stream);
 
 /* n-step TD(lambda) returns over device trajectory buffers (reinforce/training/self_play.py:524
  * compute_n_step_returns, same weighting and normalisation), time-major layout [T][N]:

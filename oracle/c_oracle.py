@@ -78,6 +78,15 @@ def draw_spawn(w: int, n_empty: int):
     return int(rank.value), bool(four.value), int(rem)
 
 
+def sample_children(after, child_count, k, seed=0, env_offset=0, draw_base=0):
+    a = _u64(after).reshape(-1)
+    cc = _u8(child_count).reshape(-1)
+    out = np.zeros(a.size * k, dtype=np.uint64)
+    lib().orc_sample_children(_p(a), _p(cc), C.c_uint32(k), C.c_uint64(seed), C.c_uint64(env_offset),
+                              C.c_uint32(draw_base), _p(out), C.c_size_t(a.size // 4))
+    return out.reshape(-1, 4, k)
+
+
 def latent_state(board: int, action: int):
     after = C.c_uint64(0)
     ovf = C.c_int(0)

@@ -49,6 +49,8 @@ PROTOTYPES = {
     'g2048_observe': (C.c_int, [_P, _P, _P, _SZ, _P]),
     'g2048_observe_onehot': (C.c_int, [_P, _P, C.c_int, _SZ, _P]),
     'g2048_expect': (C.c_int, [_P, _P, _P, _P, C.c_float, C.c_float, _P, _SZ, _P]),
+    'g2048_sample_children': (C.c_int, [_P, _P, _U32, _U64, _U64, _U32, _P, _SZ, _P]),
+    'g2048_expect_sampled': (C.c_int, [_P, _P, _P, _U32, C.c_float, C.c_float, _P, _SZ, _P]),
     'g2048_nstep_returns': (C.c_int, [_P, _P, _P, C.c_double, C.c_int, C.c_double, _P, _SZ, _SZ, _P]),
     'g2048_rollout': (C.c_int, [_U64, _U64, _SZ, _U32, C.c_int, _P, _P, _P, _P, _P, _P, _U32, _P]),
     'g2048_pack': (C.c_int, [_P, _P, _P, _SZ, _P]),

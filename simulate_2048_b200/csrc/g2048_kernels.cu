@@ -2099,6 +2099,74 @@ extern "C" int g2048_expect(const float* child_values, const uint8_t* child_coun
 }
 
 // ---------------------------------------------------------------------------------------------
+// progressive widening (gameboard.py:174 after_state_lazy + :205 generate_outcome): k chance
+// children per legal afterstate DRAWN from the spawn distribution instead of all 2 E of them, and the
+// matching Monte-Carlo backup.  One thread per (board, action, draw).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sample_children_kernel(const u64* __restrict__ after,
+                                                              const uint8_t* __restrict__ child_count, u32 k,
+                                                              u64 seed, u64 env_offset, u32 draw_base,
+                                                              u64* __restrict__ children, size_t n) {
+    const size_t total = n * 4 * (size_t)k;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t ia = t / k;             // board * 4 + action
+        const u32 j = (u32)(t - ia * k);
+        u64 out = 0ull;
+        if (child_count[ia]) {
+            Board b = split(after[ia]);
+            u32 zlo, zhi;
+            empties(b, zlo, zhi);
+            // word of (seed, board, draw index, tag 5): digit 1 = the empty cell, digit 2 = the tile
+            spawn_philox(b, zlo, zhi, philox_word(seed, env_offset + (ia >> 2), draw_base + (u32)(ia & 3) * k + j,
+                                                  G2048_PHILOX_TAG_CHANCE));
+            out = join(b);                   // an afterstate without an empty cell is its own child
+        }
+        children[t] = out;
+    }
+}
+
+extern "C" int g2048_sample_children(const uint64_t* after, const uint8_t* child_count, uint32_t k, uint64_t seed,
+                                     uint64_t env_offset, uint32_t draw_base, uint64_t* children, size_t n,
+                                     void* stream) {
+    if (n == 0 || k == 0) return G2048_OK;
+    if (!after || !child_count || !children) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    sample_children_kernel<<<grid_for(n * 4 * (size_t)k, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const u64*>(after), child_count, k, seed, env_offset, draw_base,
+        reinterpret_cast<u64*>(children), n);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
+__global__ void __launch_bounds__(256) expect_sampled_kernel(const float* __restrict__ v,
+                                                             const uint8_t* __restrict__ child_count,
+                                                             const int32_t* __restrict__ rewards, u32 k, float discount,
+                                                             float illegal_value, float* __restrict__ q, size_t n) {
+    for (size_t ia = blockIdx.x * (size_t)blockDim.x + threadIdx.x; ia < n * 4; ia += (size_t)gridDim.x * blockDim.x) {
+        float acc = 0.0f;
+        for (u32 j = 0; j < k; ++j) acc += v[ia * k + j];
+        const float r = rewards ? (float)rewards[ia] : 0.0f;
+        q[ia] = child_count[ia] ? r + discount * (acc / (float)k) : illegal_value;
+    }
+}
+
+extern "C" int g2048_expect_sampled(const float* child_values, const uint8_t* child_count, const int32_t* rewards,
+                                    uint32_t k, float discount, float illegal_value, float* q_out, size_t n,
+                                    void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!child_values || !child_count || !q_out || k == 0) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    expect_sampled_kernel<<<grid_for(n * 4, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        child_values, child_count, rewards, k, discount, illegal_value, q_out, n);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // n-step TD(lambda) returns (self_play.py:524): one thread per (t, env), time-major buffers so
 // that a warp reads consecutive envs of one time step; the n loop carries the discounted reward
 // sum, the discount power and the lambda power.
@@ -2204,6 +2272,7 @@ struct RollSlot {
     u32 j;          // env & 3: the word of the block this env reads
     u32 ovf;
     u64 score;
+    unsigned long long pre;  // prefetched queue position of the NEXT game (kRollNoId: none)
     bool alive;
 };
 
@@ -2250,25 +2319,34 @@ __device__ __noinline__ bool roll_steal(const RolloutArgs& a, unsigned long long
 // Next game for slot `s`.  The env range is cut into one queue per CTA (a counter each, `per_queue`
 // consecutive ids): a CTA drains its own queue and then steals from the others, so the balance is
 // that of one global queue while no counter is shared between SMs until the very end.
+// The id is PREFETCHED: the atomic for the game after this one is issued now and its result
+// (s.pre) is not touched before the next episode end, ~118 steps later, so the ~1 us round trip
+// of a global atomic never stalls the warp (ncu: long_scoreboard was the third stall reason,
+// 1.6 warps per issue).  Prefetching stops kRollMargin ids before the end of the queue: the last
+// ids are fetched on demand, so no slot sits on a reserved game while others run dry.
 // kFromReset: the game starts on the empty board in phase 0.  Otherwise it starts from boards_io
 // with the first action drawn from the word of tag 3; a board that is already over is emitted here.
+constexpr unsigned long long kRollNoId = ~0ull;
+constexpr unsigned long long kRollMargin = 4096;  // > 2 x slots of a CTA
+
 template <bool kFromReset, bool kTrace>
 __device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, const RollShared& sm,
                                            unsigned long long* next) {
+    const size_t lo = (size_t)blockIdx.x * a.per_queue;
+    const unsigned long long own = lo >= a.n ? 0ull : min((unsigned long long)a.per_queue, (unsigned long long)(a.n - lo));
     for (;;) {
         size_t i;
-        bool got;
-        if (*reinterpret_cast<volatile u32*>(sm.hint) == 0u) {
-            const unsigned long long k = atomicAdd(&next[blockIdx.x], 1ull);
-            i = (size_t)blockIdx.x * a.per_queue + (size_t)k;
-            got = k < a.per_queue && i < a.n;
-            if (!got) {
-                atomicMax(sm.hint, 1u);
-                got = roll_steal(a, next, sm.hint, &i);
-            }
-        } else {
-            got = roll_steal(a, next, sm.hint, &i);
+        unsigned long long k = s.pre;  // reserved at the previous game start (or none)
+        s.pre = kRollNoId;
+        bool got = k < own;
+        if (!got && *reinterpret_cast<volatile u32*>(sm.hint) == 0u) {
+            k = atomicAdd(&next[blockIdx.x], 1ull);  // on demand
+            got = k < own;
+            if (!got) atomicMax(sm.hint, 1u);
         }
+        i = lo + (size_t)k;
+        if (got && k + kRollMargin < own) s.pre = atomicAdd(&next[blockIdx.x], 1ull);  // not read until the next game end
+        if (!got) got = roll_steal(a, next, sm.hint, &i);
         s.lo = s.hi = s.act = s.t = s.ovf = 0u;
         s.score = 0;
         s.alive = got;
@@ -2359,7 +2437,10 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RollSha
                                              unsigned long long* next) {
     RollSlot slot[kRollSlots];
 #pragma unroll
-    for (int k = 0; k < kRollSlots; ++k) roll_fetch<kFromReset, kTrace>(slot[k], a, sm, next);
+    for (int k = 0; k < kRollSlots; ++k) {
+        slot[k].pre = kRollNoId;
+        roll_fetch<kFromReset, kTrace>(slot[k], a, sm, next);
+    }
     for (;;) {
         bool any = false;
 #pragma unroll

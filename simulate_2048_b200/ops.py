@@ -19,7 +19,7 @@ from ._cabi import check, lib
 
 __all__ = [
     'StepOut', 'ExpandOut', 'RolloutOut', 'step', 'env_step', 'selfplay_step', 'legal_flags', 'legal_actions', 'expand', 'reset',
-    'observe', 'observe_onehot', 'nstep_returns', 'expect', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'unpack_into', 'step_host', 'row_table', 'set_impl', 'set_tuning', 'init',
+    'observe', 'observe_onehot', 'nstep_returns', 'expect', 'sample_children', 'expect_sampled', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'unpack_into', 'step_host', 'row_table', 'set_impl', 'set_tuning', 'init',
     'pinned_empty', 'host_numa_info', 'step_host_copies', 'shutdown',
 ]
 
@@ -390,6 +390,31 @@ def expect(child_values: torch.Tensor, ex: 'ExpandOut', discount: float = 1.0,
         check(lib().g2048_expect(_ptr(child_values), _ptr(ex.child_count), _ptr(ex.child_offsets),
                                  _ptr(ex.rewards) if use_rewards else None, float(discount),
                                  float(illegal_value), _ptr(q), n, _stream()))
+    return q
+
+
+def sample_children(ex: 'ExpandOut', k: int, *, seed: int = 0, env_offset: int = 0, draw_base: int = 0) -> torch.Tensor:
+    """int64[N,4,k]: k chance children per legal afterstate DRAWN from the spawn distribution
+    (g2048_sample_children; progressive widening over gameboard.py:174 / :205).  ``ex`` is any
+    ``expand`` result (``children='none'`` is enough); illegal actions give zeros."""
+    n = ex.after.shape[0]
+    out = torch.empty((n, 4, int(k)), dtype=torch.int64, device=ex.after.device)
+    with _on(ex.after.device):
+        check(lib().g2048_sample_children(_ptr(ex.after), _ptr(ex.child_count), int(k), seed & (2**64 - 1),
+                                          env_offset, draw_base & 0xFFFFFFFF, _ptr(out), n, _stream()))
+    return out
+
+
+def expect_sampled(child_values: torch.Tensor, ex: 'ExpandOut', k: int, discount: float = 1.0,
+                   illegal_value: float = float('-inf'), use_rewards: bool = True) -> torch.Tensor:
+    """float32[N,4]: reward + discount * mean of the k sampled child values (g2048_expect_sampled)."""
+    n = ex.after.shape[0]
+    _req(child_values, torch.float32, 'child_values', n * 4 * int(k))
+    q = torch.empty((n, 4), dtype=torch.float32, device=ex.after.device)
+    with _on(ex.after.device):
+        check(lib().g2048_expect_sampled(_ptr(child_values), _ptr(ex.child_count),
+                                         _ptr(ex.rewards) if use_rewards else None, int(k), float(discount),
+                                         float(illegal_value), _ptr(q), n, _stream()))
     return q
 
 

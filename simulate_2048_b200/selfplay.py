@@ -265,24 +265,38 @@ def uniform_legal_policy(seed: int = 0):
 
 
 def expectimax(boards: torch.Tensor, value_fn, depth: int = 1, discount: float = 1.0,
-               terminal_value: float = 0.0):
+               terminal_value: float = 0.0, widen: Optional[int] = None, seed: int = 0, _level: int = 0):
     """Batched depth-``depth`` expectimax on real boards:
-        Q_d(b, a) = r(b, a) + discount * sum_children p * V_{d-1}(child)     (g2048_expect)
+        Q_d(b, a) = r(b, a) + discount * E_children[V_{d-1}(child)]
         V_d(b)    = max over the legal actions of Q_d(b, a), ``terminal_value`` if there is none
         V_0(b)    = value_fn(b)
-    One ``expand`` per level (mask, four afterstates, every chance child), ``value_fn(int64[M]) ->
-    float32[M]`` once on all leaves (e.g. a value network).  The number of boards grows ~60x per
-    level.  Returns (q float32[N,4] with -inf for illegal actions, best action int64[N], ExpandOut)."""
+    ``widen=None``: the exact expectation over all 2 E chance children of every afterstate (one
+    ``expand`` per level + ``g2048_expect``; the number of boards grows ~60x per level).
+    ``widen=k``: progressive widening (gameboard.py:174-244, docs/project.md:49) — k children per
+    afterstate drawn from the spawn distribution (``g2048_sample_children``) and averaged
+    (``g2048_expect_sampled``): an unbiased estimate whose tree grows 4k per level.
+    ``value_fn(int64[M]) -> float32[M]`` runs once on all leaves (e.g. a value network; boards of
+    illegal branches are 0 and their values are ignored).
+    Returns (q float32[N,4] with -inf for illegal actions, best action int64[N], ExpandOut)."""
     if depth < 1:
         raise ValueError('depth must be >= 1')
-    ex = ops.expand(boards, children='compact')
-    if depth == 1:
-        values = value_fn(ex.children).to(torch.float32).contiguous()
-    else:
-        q_child, _, _ = expectimax(ex.children, value_fn, depth - 1, discount, terminal_value)
+    flat = boards.reshape(-1)
+
+    def level_values(children: torch.Tensor) -> torch.Tensor:
+        if depth == 1:
+            return value_fn(children).to(torch.float32).contiguous()
+        q_child, _, _ = expectimax(children, value_fn, depth - 1, discount, terminal_value, widen, seed, _level + 1)
         best = q_child.max(dim=1).values
-        values = torch.where(torch.isinf(best), torch.full_like(best, terminal_value), best).contiguous()
-    q = ops.expect(values, ex, discount=discount)
+        return torch.where(torch.isinf(best), torch.full_like(best, terminal_value), best).contiguous()
+
+    if widen is None:
+        ex = ops.expand(flat, children='compact')
+        q = ops.expect(level_values(ex.children), ex, discount=discount)
+    else:
+        k = int(widen)
+        ex = ops.expand(flat, children='none')
+        kids = ops.sample_children(ex, k, seed=seed, draw_base=_level * 4 * k)
+        q = ops.expect_sampled(level_values(kids.reshape(-1)), ex, k, discount=discount)
     return q, q.argmax(dim=1), ex
 
 

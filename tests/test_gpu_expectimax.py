@@ -82,3 +82,63 @@ def test_expectimax_depth2_reproduces_reference(golden):
     assert np.array_equal(np.isinf(got), np.isinf(want))
     fin = np.isfinite(want)
     np.testing.assert_allclose(got[fin], want[fin], rtol=5e-6, atol=1e-3)
+
+
+def test_sampled_children_vs_oracle(oracle):
+    """g2048_sample_children: bit-exact against the oracle's draws (word of (seed, board, draw, tag 5),
+    digits 1 and 2), every child is a member of the exact child set, illegal actions give zeros."""
+    import torch
+    from simulate_2048_b200 import ops
+    from tests.helpers import synthetic_packed
+    n, k = 3000, 5
+    boards = synthetic_packed(n, seed=41, max_exp=8)
+    d = torch.from_numpy(boards.view(np.int64)).cuda()
+    ex = ops.expand(d, children='compact')
+    kids = ops.sample_children(ex, k, seed=99, env_offset=7, draw_base=40)
+    want = oracle.sample_children(ex.after.cpu().numpy().view(np.uint64), ex.child_count.cpu().numpy(), k,
+                                  seed=99, env_offset=7, draw_base=40)
+    got = kids.cpu().numpy().view(np.uint64)
+    np.testing.assert_array_equal(got, want)
+    cc, offs = ex.child_count.cpu().numpy(), ex.child_offsets.cpu().numpy()
+    allkids = ex.children.cpu().numpy().view(np.uint64)
+    for i in range(0, n, 37):
+        o = int(offs[i])
+        for a in range(4):
+            c = int(cc[i, a])
+            if c == 0:
+                assert (got[i, a] == 0).all()
+            else:
+                assert set(got[i, a].tolist()) <= set(allkids[o:o + c].tolist())
+            o += c
+
+
+def test_progressive_widening_converges_to_exact():
+    """expectimax(widen=k): an unbiased Monte-Carlo estimate of the exact backup — the error against
+    widen=None shrinks like 1/sqrt(k), the greedy action mostly agrees at k = 64, and depth 2 with
+    k = 4 expands 16x fewer boards per level than the exact tree."""
+    import torch
+    from simulate_2048_b200 import ops, selfplay
+    from tests.helpers import synthetic_packed
+    boards = torch.from_numpy(synthetic_packed(4000, seed=3, max_exp=7).view(np.int64)).cuda()
+
+    def value(children):
+        obs, mx = ops.observe(children)
+        return (obs == 0).sum(dim=1).to(torch.float32) * 3.0 + mx.to(torch.float32)
+    exact, best, _ = selfplay.expectimax(boards, value, depth=1)
+    legal = ~torch.isinf(exact)
+    errs = []
+    for k in (4, 16, 64):
+        q, _, _ = selfplay.expectimax(boards, value, depth=1, widen=k, seed=5)
+        assert torch.equal(torch.isinf(q), torch.isinf(exact))
+        errs.append(float((q[legal] - exact[legal]).abs().mean()))
+    assert errs[0] > errs[1] > errs[2] and errs[2] < 0.45 * errs[0]
+    q64, best64, _ = selfplay.expectimax(boards, value, depth=1, widen=64, seed=5)
+    has = legal.any(dim=1)
+    assert float((best64[has] == best[has]).float().mean()) > 0.9
+    bias = float((q64[legal] - exact[legal]).mean())
+    assert abs(bias) < 0.05                                   # unbiased
+    q2, b2, _ = selfplay.expectimax(boards[:512].contiguous(), value, depth=2, widen=4, seed=1)
+    e2, be2, _ = selfplay.expectimax(boards[:512].contiguous(), value, depth=2)
+    ok = ~torch.isinf(e2)
+    assert torch.equal(torch.isinf(q2), torch.isinf(e2))
+    assert float((q2[ok] - e2[ok]).abs().mean()) < 0.25 * float(e2[ok].abs().mean())
