@@ -1661,24 +1661,23 @@ __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned l
     asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Small batches: ONE launch.  A CTA takes a tile of 128 boards by ticket (so a tile only ever waits
-// for tiles that have already started: no dependence on co-residency), runs the four moves
-// (lane = board, hashed table gathered from L2), scans its child totals, publishes the tile
-// aggregate, sums the aggregates of all earlier tiles (every thread polls <= n_tiles / 128 entries,
-// all in flight at once) and then expands its boards from shared memory at prefix + local offset.
-// scratch[0] = ticket counter, scratch[2 + t] = aggregate of tile t | kAggValid (zeroed per call).
+// Small batches: ONE launch.  CTA t takes tile t of 128 boards (thread blocks are dispatched in
+// blockIdx order, so a tile only ever waits for tiles that started before it — the assumption
+// CUB's decoupled look-back makes as well), runs the four moves (lane = board, hashed table
+// gathered from L2), scans its child totals, publishes the tile aggregate, sums the aggregates of
+// all earlier tiles (every thread polls <= n_tiles / 128 entries, all in flight at once) and then
+// expands its boards from shared memory at prefix + local offset.
+// scratch[2 + t] = aggregate of tile t | kAggValid (zeroed per call).
 constexpr int kScanWarps = 4;
 
 __global__ void __launch_bounds__(kScanWarps * 32) expand_compact_fused_kernel(const ExpandArgs a,
                                                                              unsigned long long* scratch,
                                                                              unsigned long long* total_out) {
     __shared__ ChildTile s_tile[kScanWarps];
-    __shared__ u32 s_tile_id, s_warp_tot[kScanWarps];
+    __shared__ u32 s_warp_tot[kScanWarps];
     __shared__ unsigned long long s_red[kScanWarps];
     const u32 FULL = 0xFFFFFFFFu, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_tile_id = (u32)atomicAdd(&scratch[0], 1ull);
-    __syncthreads();
-    const size_t tile = s_tile_id, warp_base = tile * (kScanWarps * 32) + w * 32, mine = warp_base + lane;
+    const size_t tile = blockIdx.x, warp_base = tile * (kScanWarps * 32) + w * 32, mine = warp_base + lane;
     const GlobalLut lut{a.table_hashed};
     uint4 s01 = make_uint4(0u, 0u, 0u, 0u), s23 = s01;
     u32 cc4 = 0u;
@@ -2279,7 +2278,6 @@ struct RollSlot {
 struct RollShared {
     const uint4* orient;  // per-action orientation words
     const uint8_t* pick;  // action pick table
-    u32* hint;            // queues this CTA has found empty (roll_fetch)
 };
 
 __device__ __forceinline__ u64 roll_env(const RollSlot& s) {
@@ -2298,36 +2296,31 @@ __device__ __forceinline__ void roll_emit(const RollSlot& s, const RolloutArgs& 
     if (s.ovf && a.ovf_out) a.ovf_out[i] = 1;  // zero-filled by the host side
 }
 
-// The own queue is empty: steal single ids from the other CTAs' queues, in ring order from the
-// first one this CTA has not yet seen empty (`hint`, shared).  Rare (the end of a launch).
-__device__ __noinline__ bool roll_steal(const RolloutArgs& a, unsigned long long* next, u32* hint, size_t* out) {
-    for (;;) {
-        const u32 h = *reinterpret_cast<volatile u32*>(hint);
-        if (h >= gridDim.x) return false;
-        u32 q = blockIdx.x + h;
-        if (q >= gridDim.x) q -= gridDim.x;
-        const unsigned long long k = atomicAdd(&next[q], 1ull);
-        const size_t i = (size_t)q * a.per_queue + (size_t)k;
-        if (k < a.per_queue && i < a.n) {
-            *out = i;
-            return true;
-        }
-        atomicMax(hint, h + 1u);
-    }
-}
-
-// Next game for slot `s`.  The env range is cut into one queue per CTA (a counter each, `per_queue`
-// consecutive ids): a CTA drains its own queue and then steals from the others, so the balance is
-// that of one global queue while no counter is shared between SMs until the very end.
+// Next game for slot `s`.  The env range is cut into one queue per CTA (`per_queue` consecutive
+// ids and a counter each), so no counter is shared between SMs: ONE counter for the whole grid
+// serialises in L2 (~0.7 G same-address atomics/s capped the round-1 kernel).  The queues hold
+// equal numbers of games; a CTA plays ~14 000 of them, so the work per CTA differs by ~0.4 %
+// (sqrt(14 000) x 55 steps against 14 000 x 118) and stealing between queues is not worth its
+// probes (an earlier version with stealing spent 11 % of its stall samples in the final, empty
+// probe round: ncu, profiles/r02_rollout_ncu_summary.txt).
 // The id is PREFETCHED: the atomic for the game after this one is issued now and its result
-// (s.pre) is not touched before the next episode end, ~118 steps later, so the ~1 us round trip
-// of a global atomic never stalls the warp (ncu: long_scoreboard was the third stall reason,
-// 1.6 warps per issue).  Prefetching stops kRollMargin ids before the end of the queue: the last
-// ids are fetched on demand, so no slot sits on a reserved game while others run dry.
+// (s.pre) is not read before the next episode end, ~118 steps later, so the ~1 us round trip never
+// stalls the warp.  (Inline PTX: the compiler would aggregate atomicAdd over the warp and shuffle
+// the result at once, which waits for it.)  Prefetching stops kRollMargin ids before the end of
+// the queue: the last ids are fetched on demand, so no slot reserves a game others could start.
 // kFromReset: the game starts on the empty board in phase 0.  Otherwise it starts from boards_io
 // with the first action drawn from the word of tag 3; a board that is already over is emitted here.
 constexpr unsigned long long kRollNoId = ~0ull;
 constexpr unsigned long long kRollMargin = 4096;  // > 2 x slots of a CTA
+
+// `lane_zero` is a per-lane value that is always 0 (the slot's overflow flag >> 1): it makes the
+// address look lane-dependent, so ptxas does not aggregate the atomic over the warp — the
+// aggregated form shuffles the result to the lanes at once, i.e. waits for the round trip.
+__device__ __forceinline__ unsigned long long queue_take(unsigned long long* counter, u32 lane_zero) {
+    unsigned long long k;
+    asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(k) : "l"(counter + lane_zero) : "memory");
+    return k;
+}
 
 template <bool kFromReset, bool kTrace>
 __device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, const RollShared& sm,
@@ -2335,18 +2328,12 @@ __device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, co
     const size_t lo = (size_t)blockIdx.x * a.per_queue;
     const unsigned long long own = lo >= a.n ? 0ull : min((unsigned long long)a.per_queue, (unsigned long long)(a.n - lo));
     for (;;) {
-        size_t i;
         unsigned long long k = s.pre;  // reserved at the previous game start (or none)
         s.pre = kRollNoId;
-        bool got = k < own;
-        if (!got && *reinterpret_cast<volatile u32*>(sm.hint) == 0u) {
-            k = atomicAdd(&next[blockIdx.x], 1ull);  // on demand
-            got = k < own;
-            if (!got) atomicMax(sm.hint, 1u);
-        }
-        i = lo + (size_t)k;
-        if (got && k + kRollMargin < own) s.pre = atomicAdd(&next[blockIdx.x], 1ull);  // not read until the next game end
-        if (!got) got = roll_steal(a, next, sm.hint, &i);
+        const u32 lane_zero = s.ovf >> 1;  // ovf is 0 or 1
+        if (k == kRollNoId) k = queue_take(&next[blockIdx.x], lane_zero);  // on demand
+        const bool got = k < own;
+        if (got && k + kRollMargin < own) s.pre = queue_take(&next[blockIdx.x], lane_zero);  // not read until the next game end
         s.lo = s.hi = s.act = s.t = s.ovf = 0u;
         s.score = 0;
         s.alive = got;
@@ -2354,12 +2341,12 @@ __device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, co
             s.qlo = s.qhi = s.j = 0u;
             return;
         }
-        const u64 env = a.env_offset + i;
+        const u64 env = a.env_offset + lo + (size_t)k;
         s.qlo = (u32)(env >> 2);
         s.qhi = (u32)(env >> 34);
         s.j = (u32)env & 3u;
         if (kFromReset) return;
-        const Board b = split(a.boards_io[i]);
+        const Board b = split(a.boards_io[lo + (size_t)k]);
         s.lo = b.lo;
         s.hi = b.hi;
         s.t = 2u;
@@ -2439,6 +2426,7 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RollSha
 #pragma unroll
     for (int k = 0; k < kRollSlots; ++k) {
         slot[k].pre = kRollNoId;
+        slot[k].ovf = 0u;
         roll_fetch<kFromReset, kTrace>(slot[k], a, sm, next);
     }
     for (;;) {
@@ -2464,15 +2452,13 @@ template <bool kSmem, bool kFromReset, bool kTrace, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutArgs a, unsigned long long* next) {
     __shared__ __align__(16) uint4 sh_orient[8];
     __shared__ uint8_t sh_pick[64];
-    __shared__ u32 sh_hint;
     u64* bar = reinterpret_cast<u64*>(smem_words + kSmemRows);
     if (kSmem) table_stage_begin(smem_words, bar, a.table_hashed);
-    if (threadIdx.x == 0) sh_hint = 0u;
     if (threadIdx.x < 32) reinterpret_cast<u32*>(sh_orient)[threadIdx.x] = reinterpret_cast<const u32*>(c_orient)[threadIdx.x];
     if (threadIdx.x < 64) sh_pick[threadIdx.x] = c_pick[threadIdx.x];
     if (kSmem) table_stage_wait(bar); else __syncthreads();
 
-    const RollShared sm{sh_orient, sh_pick, &sh_hint};
+    const RollShared sm{sh_orient, sh_pick};
     if (kSmem) rollout_loop<kFromReset, kTrace>(a, sm, SmemLut{}, next);
     else rollout_loop<kFromReset, kTrace>(a, sm, GlobalLut{a.table_hashed}, next);
 }
