@@ -2270,8 +2270,9 @@ struct RollSlot {
     u32 qlo, qhi;   // Philox counter words 0, 1 = quad of the global env id
     u32 j;          // env & 3: the word of the block this env reads
     u32 ovf;
+    u32 k;          // position of this game in the CTA's queue (env = queue base + k)
+    u32 pre;        // prefetched queue position of the NEXT game (kRollNoId: none)
     u64 score;
-    unsigned long long pre;  // prefetched queue position of the NEXT game (kRollNoId: none)
     bool alive;
 };
 
@@ -2280,20 +2281,41 @@ struct RollShared {
     const uint8_t* pick;  // action pick table
 };
 
-__device__ __forceinline__ u64 roll_env(const RollSlot& s) {
-    return ((u64)s.qhi << 34) | ((u64)s.qlo << 2) | s.j;
+// per-thread constants of the CTA's queue: its first env (local index), its length, and the output
+// pointers moved to that base (the host side always provides boards / score / steps buffers)
+struct RollQueue {
+    size_t lo;
+    u32 own;
+    u64* boards;
+    int64_t* score;
+    int32_t* steps;
+    uint8_t* ovf;
+    uint8_t* trace;
+    unsigned int* counter;
+};
+
+__device__ __forceinline__ RollQueue roll_queue(const RolloutArgs& a, unsigned int* next) {
+    RollQueue q;
+    q.lo = (size_t)blockIdx.x * a.per_queue;
+    q.own = q.lo >= a.n ? 0u : (u32)min((size_t)a.per_queue, a.n - q.lo);
+    q.boards = a.boards_io + q.lo;
+    q.score = a.score_out + q.lo;
+    q.steps = a.steps_out + q.lo;
+    q.ovf = a.ovf_out ? a.ovf_out + q.lo : nullptr;
+    q.trace = a.trace ? a.trace + q.lo * a.trace_stride : nullptr;
+    q.counter = next + blockIdx.x;
+    return q;
 }
 
 // the episode of slot `s` is over: its per-env results (rollout_stats_kernel does the rest)
 template <bool kTrace>
-__device__ __forceinline__ void roll_emit(const RollSlot& s, const RolloutArgs& a) {
-    const size_t i = (size_t)(roll_env(s) - a.env_offset);
+__device__ __forceinline__ void roll_emit(const RollSlot& s, const RolloutArgs& a, const RollQueue& q) {
     const u32 step = s.t - 2u;
-    if (kTrace) a.trace[i * a.trace_stride + min(step, a.trace_stride - 1u)] = 0;
-    if (a.boards_io) a.boards_io[i] = ((u64)s.hi << 32) | s.lo;
-    if (a.score_out) a.score_out[i] = (int64_t)s.score;
-    if (a.steps_out) a.steps_out[i] = (int32_t)step;
-    if (s.ovf && a.ovf_out) a.ovf_out[i] = 1;  // zero-filled by the host side
+    if (kTrace) q.trace[(size_t)s.k * a.trace_stride + min(step, a.trace_stride - 1u)] = 0;
+    q.boards[s.k] = ((u64)s.hi << 32) | s.lo;
+    q.score[s.k] = (int64_t)s.score;
+    q.steps[s.k] = (int32_t)step;
+    if (s.ovf && q.ovf) q.ovf[s.k] = 1;  // zero-filled by the host side
 }
 
 // Next game for slot `s`.  The env range is cut into one queue per CTA (`per_queue` consecutive
@@ -2310,43 +2332,42 @@ __device__ __forceinline__ void roll_emit(const RollSlot& s, const RolloutArgs& 
 // the queue: the last ids are fetched on demand, so no slot reserves a game others could start.
 // kFromReset: the game starts on the empty board in phase 0.  Otherwise it starts from boards_io
 // with the first action drawn from the word of tag 3; a board that is already over is emitted here.
-constexpr unsigned long long kRollNoId = ~0ull;
-constexpr unsigned long long kRollMargin = 4096;  // > 2 x slots of a CTA
+constexpr u32 kRollNoId = ~0u;
+constexpr u32 kRollMargin = 4096;  // > 2 x slots of a CTA
 
 // `lane_zero` is a per-lane value that is always 0 (the slot's overflow flag >> 1): it makes the
 // address look lane-dependent, so ptxas does not aggregate the atomic over the warp — the
 // aggregated form shuffles the result to the lanes at once, i.e. waits for the round trip.
-__device__ __forceinline__ unsigned long long queue_take(unsigned long long* counter, u32 lane_zero) {
-    unsigned long long k;
-    asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(k) : "l"(counter + lane_zero) : "memory");
+__device__ __forceinline__ u32 queue_take(unsigned int* counter, u32 lane_zero) {
+    u32 k;
+    asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(k) : "l"(counter + lane_zero) : "memory");
     return k;
 }
 
 template <bool kFromReset, bool kTrace>
 __device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, const RollShared& sm,
-                                           unsigned long long* next) {
-    const size_t lo = (size_t)blockIdx.x * a.per_queue;
-    const unsigned long long own = lo >= a.n ? 0ull : min((unsigned long long)a.per_queue, (unsigned long long)(a.n - lo));
+                                           const RollQueue& q) {
     for (;;) {
-        unsigned long long k = s.pre;  // reserved at the previous game start (or none)
-        s.pre = kRollNoId;
+        u32 k = s.pre;  // reserved at the previous game start (or none)
         const u32 lane_zero = s.ovf >> 1;  // ovf is 0 or 1
-        if (k == kRollNoId) k = queue_take(&next[blockIdx.x], lane_zero);  // on demand
-        const bool got = k < own;
-        if (got && k + kRollMargin < own) s.pre = queue_take(&next[blockIdx.x], lane_zero);  // not read until the next game end
+        if (k == kRollNoId) k = queue_take(q.counter, lane_zero);  // on demand
+        const bool got = k < q.own;
+        s.pre = kRollNoId;
+        if (got && k + kRollMargin < q.own) s.pre = queue_take(q.counter, lane_zero);  // not read until the next game end
         s.lo = s.hi = s.act = s.t = s.ovf = 0u;
         s.score = 0;
+        s.k = k;
         s.alive = got;
         if (!got) {
             s.qlo = s.qhi = s.j = 0u;
             return;
         }
-        const u64 env = a.env_offset + lo + (size_t)k;
+        const u64 env = a.env_offset + q.lo + k;
         s.qlo = (u32)(env >> 2);
         s.qhi = (u32)(env >> 34);
         s.j = (u32)env & 3u;
         if (kFromReset) return;
-        const Board b = split(a.boards_io[lo + (size_t)k]);
+        const Board b = split(q.boards[k]);
         s.lo = b.lo;
         s.hi = b.hi;
         s.t = 2u;
@@ -2354,14 +2375,14 @@ __device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, co
         const u32 w = philox_word(a.keys, env, 0u, G2048_PHILOX_TAG_START);
         s.act = sm.pick[mask * 4u + __umulhi(w, (u32)__popc(mask))];
         if (mask != 0u && a.max_steps != 0u) return;
-        roll_emit<kTrace>(s, a);  // nothing to play
+        roll_emit<kTrace>(s, a, q);  // nothing to play
     }
 }
 
 // one step (or reset phase) of slot `s`; returns the legal mask of the new board
 template <bool kTrace, class Lut>
 __device__ __forceinline__ u32 roll_step(RollSlot& s, const RolloutArgs& a, const RollShared& sm,
-                                         const Lut& lut) {
+                                         const RollQueue& q, const Lut& lut) {
     const u32 one = a.one;
     const bool playing = s.t >= 2u;
     const Philox4 p = philox4x32_10(s.qlo, s.qhi, playing ? s.t - 2u : 0u,
@@ -2402,7 +2423,7 @@ __device__ __forceinline__ u32 roll_step(RollSlot& s, const RolloutArgs& a, cons
         const u32 step = s.t - 2u;
         if (s.alive && playing && step + 1u < a.trace_stride) {  // (a slot without a game replays env 0: no trace)
             const u32 cell = ((__ffs(bit3) - 1u) >> 2) + (in_hi ? 8u : 0u);
-            a.trace[(size_t)(roll_env(s) - a.env_offset) * a.trace_stride + step] =
+            q.trace[(size_t)s.k * a.trace_stride + step] =
                 (uint8_t)(0x80u | s.act | (cell << 2) | ((exp - 1u) << 6));
         }
     }
@@ -2421,13 +2442,14 @@ __device__ __forceinline__ u32 roll_step(RollSlot& s, const RolloutArgs& a, cons
 
 template <bool kFromReset, bool kTrace, class Lut>
 __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RollShared& sm, const Lut& lut,
-                                             unsigned long long* next) {
+                                             unsigned int* next) {
+    const RollQueue q = roll_queue(a, next);
     RollSlot slot[kRollSlots];
 #pragma unroll
     for (int k = 0; k < kRollSlots; ++k) {
         slot[k].pre = kRollNoId;
         slot[k].ovf = 0u;
-        roll_fetch<kFromReset, kTrace>(slot[k], a, sm, next);
+        roll_fetch<kFromReset, kTrace>(slot[k], a, sm, q);
     }
     for (;;) {
         bool any = false;
@@ -2436,20 +2458,20 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RollSha
         if (!any) break;
         u32 mask[kRollSlots];
 #pragma unroll
-        for (int k = 0; k < kRollSlots; ++k) mask[k] = roll_step<kTrace>(slot[k], a, sm, lut);
+        for (int k = 0; k < kRollSlots; ++k) mask[k] = roll_step<kTrace>(slot[k], a, sm, q, lut);
 #pragma unroll
         for (int k = 0; k < kRollSlots; ++k) {
             RollSlot& s = slot[k];
             if (s.alive && s.t >= 2u && (mask[k] == 0u || s.t - 2u >= a.max_steps)) {
-                roll_emit<kTrace>(s, a);
-                roll_fetch<kFromReset, kTrace>(s, a, sm, next);
+                roll_emit<kTrace>(s, a, q);
+                roll_fetch<kFromReset, kTrace>(s, a, sm, q);
             }
         }
     }
 }
 
 template <bool kSmem, bool kFromReset, bool kTrace, int kThreads>
-__global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutArgs a, unsigned long long* next) {
+__global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutArgs a, unsigned int* next) {
     __shared__ __align__(16) uint4 sh_orient[8];
     __shared__ uint8_t sh_pick[64];
     u64* bar = reinterpret_cast<u64*>(smem_words + kSmemRows);
@@ -2541,27 +2563,29 @@ extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint3
     const int bytes = smem ? (int)kSmemTableBytes + 64 : 0;
     const int threads = smem ? g_roll_threads : kRollSmallThreads;
     const int grid = smem ? s->sms : grid_for((n + kRollSlots - 1) / kRollSlots, kRollSmallThreads, s->sms, 8);
-    // scratch (stream-ordered): the queue counters, and the per-env arrays the statistics pass reads
-    // when the caller does not ask for them
+    // scratch (stream-ordered): the queue counters, and the per-env result arrays the caller does not
+    // ask for (the kernel always writes boards / score / steps; the statistics pass reads them)
     const bool post = stats_out || maxexp_out;
-    const size_t counters = ((size_t)grid * 8 + 15) / 16 * 16;
-    const size_t sz_boards = (post && !boards_io) ? n * 8 : 0, sz_score = (post && !score_out) ? n * 8 : 0;
-    const size_t sz_steps = (post && !steps_out) ? (n * 4 + 15) / 16 * 16 : 0, sz_ovf = post ? n : 0;
+    const size_t per_queue = (n + (size_t)grid - 1) / (size_t)grid;
+    if (per_queue >= ((size_t)1 << 31)) return G2048_EINVAL;
+    const size_t counters = ((size_t)grid * 4 + 15) / 16 * 16;
+    const size_t sz_boards = boards_io ? 0 : n * 8, sz_score = score_out ? 0 : n * 8;
+    const size_t sz_steps = steps_out ? 0 : (n * 4 + 15) / 16 * 16, sz_ovf = post ? n : 0;
     unsigned char* scratch = nullptr;
     CU(cudaMallocFromPoolAsync(&scratch, counters + sz_boards + sz_score + sz_steps + sz_ovf, s->pool, st));
     auto launch = [&]() -> int {  // in a helper so that the scratch is released on every path
-        unsigned long long* next = reinterpret_cast<unsigned long long*>(scratch);
+        unsigned int* next = reinterpret_cast<unsigned int*>(scratch);
         unsigned char* p = scratch + counters;
-        u64* boards_buf = boards_io ? reinterpret_cast<u64*>(boards_io) : (sz_boards ? reinterpret_cast<u64*>(p) : nullptr);
+        u64* boards_buf = boards_io ? reinterpret_cast<u64*>(boards_io) : reinterpret_cast<u64*>(p);
         p += sz_boards;
-        int64_t* score_buf = score_out ? score_out : (sz_score ? reinterpret_cast<int64_t*>(p) : nullptr);
+        int64_t* score_buf = score_out ? score_out : reinterpret_cast<int64_t*>(p);
         p += sz_score;
-        int32_t* steps_buf = steps_out ? steps_out : (sz_steps ? reinterpret_cast<int32_t*>(p) : nullptr);
+        int32_t* steps_buf = steps_out ? steps_out : reinterpret_cast<int32_t*>(p);
         p += sz_steps;
         uint8_t* ovf_buf = sz_ovf ? p : nullptr;
-        CU(cudaMemsetAsync(next, 0, (size_t)grid * sizeof(unsigned long long), st));
+        CU(cudaMemsetAsync(next, 0, (size_t)grid * sizeof(unsigned int), st));
         if (ovf_buf) CU(cudaMemsetAsync(ovf_buf, 0, n, st));
-        const RolloutArgs a{seed, env_offset, n, (n + (size_t)grid - 1) / (size_t)grid, max_steps, boards_buf,
+        const RolloutArgs a{seed, env_offset, n, per_queue, max_steps, boards_buf,
                             score_buf, steps_buf, ovf_buf, trace, trace_stride, s->table, s->table_hashed, 1u,
                             philox_key_schedule(seed)};
 #define G2048_LAUNCH_ROLL(SM, FR, TR, TH)                                                                  \
