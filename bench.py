@@ -757,8 +757,8 @@ def run_ours(args):
             xm[f'depth{depth}_{n_x}'] = {'ms': t_x * 1e3, 'root_boards_per_sec': n_x / t_x,
                                         'first_level_children': int(ex_x.children.numel())}
             del ex_x
-        _, t_w, _ = timed(lambda: selfplay.expectimax(boards[:4096].contiguous(), leaf_value, depth=2, widen=4), 5, 2,
-                          collective=False)
+        wide_fn = lambda: selfplay.expectimax(boards[:4096].contiguous(), leaf_value, depth=2, widen=4)  # noqa: E731
+        _, t_w, _ = timed(wide_fn, 5, 2, collective=False)
         xm['depth2_4096_widen4'] = {'ms': t_w * 1e3, 'root_boards_per_sec': 4096 / t_w,
                                     'note': 'progressive widening: 4 sampled chance children per afterstate and level'}
         xm['note'] = 'selfplay.expectimax: one g2048_expand per level, leaf values from a torch function, g2048_expect backup'

@@ -116,13 +116,20 @@ def batched_step(states: GameState, actions: Array, keys: Keys = None, *, inplac
 
 
 def batched_get_observation(states: GameState) -> Array:
-    """env.py:228 — float32[N, 16]."""
-    return core.encode_observation(states.board)
+    """env.py:228 — float32[N, 16].  (A GameState board is packed int64[N]: straight to the kernel,
+    without the representation checks and reshapes of the generic core function.)"""
+    b = states.board
+    if b.dim() == 1 and b.dtype == torch.int64:
+        return ops.observe(b, want_max=False)[0]
+    return core.encode_observation(b)
 
 
 def batched_get_legal_actions(states: GameState) -> Array:
     """env.py:245 — bool[N, 4]."""
-    return core.legal_actions_mask(states.board)
+    b = states.board
+    if b.dim() == 1 and b.dtype == torch.int64:
+        return ops.legal_actions(b)
+    return core.legal_actions_mask(b)
 
 
 # -- single-env forms (env.py:55, :79, :136, :154): a batch of one -----------------------------
