@@ -100,6 +100,8 @@ static std::atomic<int> g_impl{G2048_IMPL_AUTO};
 static std::atomic<int> g_step_threads{0};  // 0 = automatic: 640 with injected spawns (5 warps per scheduler at 96 registers: +1 %), 512 with Philox
 // programmatic dependent launch of the step kernel (environment G2048_PDL=0 turns it off)
 static const int g_pdl = [] { const char* e = getenv("G2048_PDL"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
+// environment G2048_EXPAND_OLD=1: small-batch expansion through the first-generation lane = board kernels (A/B)
+static const int g_expand_old = [] { const char* e = getenv("G2048_EXPAND_OLD"); return e && atoi(e) != 0 ? 1 : 0; }();
 static std::atomic<int> g_step_groups{1};   // groups of 4 envs per thread (1 or 2)  // tuning knob (g2048_set_tuning)
 
 static int device_occupancy(DeviceState& s);  // defined next to the kernels it measures
@@ -1479,8 +1481,8 @@ __device__ __forceinline__ void expand_record(ChildTile& t, u32 lane, uint4 s01,
 // A lane serves a FIXED (action, rank) pair — action = lane / 8, rank = lane % 8 (+ 8 in the
 // second pass) — so no per-child search for the segment is needed and the record is read once
 // per board.
-template <int kLayout>
-__device__ __forceinline__ void expand_children_tile(const ExpandArgs& a, const ChildTile& t, u32 n_here,
+template <int kLayout, class Tile>
+__device__ __forceinline__ void expand_children_tile(const ExpandArgs& a, const Tile& t, u32 n_here,
                                                      u32 lane) {
     const u32 act = lane >> 3, r0 = lane & 7u, byte_sel = 0x4440u + act;
     for (u32 k = 0; k < n_here; ++k) {
@@ -1742,6 +1744,143 @@ __global__ void __launch_bounds__(kScanWarps * 32) expand_compact_fused_kernel(c
         expand_children_tile<G2048_CHILDREN_COMPACT>(a, s_tile[w], (u32)min((size_t)32, a.n - warp_base), lane);
 }
 
+// Small batches, second generation: lane = (board, ACTION).  The lane = board kernels above keep
+// only ~3.5 warps per scheduler busy at 65 536 boards (2048 warps on 592 schedulers) and every lane
+// walks four dependent table gathers: ncu showed 26-32 % issue activity and 18-23 us per launch,
+// all of it latency (profiles/r02_expand_fused_before_ncu_summary.txt).  With one (board, action)
+// per lane there are four times as many warps, each with a quarter of the chain: a warp owns 8
+// boards, computes their 32 moves at once (per-lane orientation words from shared memory, as the
+// step kernel), combines the four lanes of a board with two shuffles, and expands the 8 boards
+// from shared memory.  kScan adds the device-side offsets of g2048_expand_compact: CTA t owns tile
+// t of 64 boards, publishes its child total as ONE relaxed 64-bit word (value | valid bit) and
+// sums the words of all earlier tiles (thread blocks are dispatched in blockIdx order, so a tile
+// only waits for tiles that started before it — the assumption CUB's look-back makes as well).
+constexpr int kQuadWarps = 8, kQuadBoards = 8 * kQuadWarps;  // 8 boards per warp, 64 per CTA
+
+struct QuadTile {
+    uint4 rec[8][4];  // {after.lo, after.hi, n_lo, n_hi} per board and action
+    uint4 meta[8];    // {counts, first pair of each action, offset lo, offset hi}
+};
+
+template <int kLayout, bool kScan>
+__global__ void __launch_bounds__(kQuadWarps * 32) expand_quad_kernel(const ExpandArgs a, unsigned long long* agg,
+                                                                    unsigned long long* total_out) {
+    __shared__ QuadTile s_tile[kQuadWarps];
+    __shared__ __align__(16) uint4 s_orient[8];
+    __shared__ u32 s_warp_tot[kQuadWarps];
+    __shared__ unsigned long long s_red[kQuadWarps];
+    const u32 FULL = 0xFFFFFFFFu, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const u32 b = lane >> 2, act = lane & 3u;
+    if (threadIdx.x < 32) reinterpret_cast<u32*>(s_orient)[threadIdx.x] = reinterpret_cast<const u32*>(c_orient)[threadIdx.x];
+    __syncthreads();
+    const GlobalLut lut{a.table_hashed};
+    for (size_t tile = blockIdx.x; tile * kQuadBoards < a.n; tile += gridDim.x) {  // kScan: one tile per CTA
+        const size_t warp_base = tile * kQuadBoards + w * 8, mine = warp_base + b, ia = mine * 4 + act;
+        const bool have = mine < a.n;
+        u32 al = 0u, ah = 0u, cc = 0u, flags = 0u;  // flags: bit act = moved, bit 8 = overflow
+        if (have) {
+            const u64 packed = a.boards[mine];
+            const u32 lo = (u32)packed, hi = (u32)(packed >> 32);
+            u32 ne;
+            int reward;
+            if (!fast::has_big_tile(lo, hi)) {
+                const uint4 o0 = s_orient[2u * act];
+                fast::Orient o;
+                o.mask = o0.x; o.mul_hi = o0.y; o.mul_lo = o0.z; o.sel_lo = o0.w;
+                o.sel_hi = s_orient[2u * act + 1u].x;
+                bool moved;
+                reward = (int)fast::move_fast(lo, hi, o, lut, a.one, al, ah, moved);
+                ne = 16u - __popc(fast::nz8(al, a.one)) - __popc(fast::nz8(ah, a.one));
+                cc = moved ? 2u * ne : 0u;  // a move always leaves an empty cell
+                flags = moved ? 1u << act : 0u;
+            } else {  // exact path: a tile >= 16384 on the board
+                const MoveResult r = move_action(Board{lo, hi}, act, GlobalTable{a.table});
+                al = r.after.lo;
+                ah = r.after.hi;
+                const bool moved = (al != lo) | (ah != hi);
+                reward = (int)r.score;
+                ne = 16u - __popc(nz8(al)) - __popc(nz8(ah));
+                cc = moved ? (ne ? 2u * ne : 1u) : 0u;
+                flags = (moved ? 1u << act : 0u) | (r.overflow ? 0x100u : 0u);
+            }
+            if (a.after) a.after[ia] = ((u64)ah << 32) | al;
+            if (a.rewards) a.rewards[ia] = reward;
+            if (a.num_empty) a.num_empty[ia] = (uint8_t)ne;
+            if (a.child_count) a.child_count[ia] = (uint8_t)cc;
+        }
+        // the four lanes of a board: counts packed one byte per action, flags or-ed
+        u32 cc4 = cc << (8u * act);
+        cc4 += __shfl_xor_sync(FULL, cc4, 1);
+        cc4 += __shfl_xor_sync(FULL, cc4, 2);
+        flags |= __shfl_xor_sync(FULL, flags, 1);
+        flags |= __shfl_xor_sync(FULL, flags, 2);
+        if (have && act == 0u && a.mask)
+            a.mask[mine] = (uint8_t)(board_flags(flags & 0xFu) | ((flags & 0x100u) ? G2048_FLAG_OVERFLOW : 0u));
+        const u32 tot = sum_bytes4(cc4);
+        unsigned long long off;
+        if (kScan) {
+            u32 inc = act == 0u ? tot : 0u;  // inclusive scan over the warp; one entry per board
+#pragma unroll
+            for (u32 d = 1; d < 32u; d <<= 1) {
+                const u32 v = __shfl_up_sync(FULL, inc, d);
+                if (lane >= d) inc += v;
+            }
+            const u32 excl = __shfl_sync(FULL, inc, lane & ~3u) - tot;  // of my board, inside the warp
+            if (lane == 31u) s_warp_tot[w] = inc;
+            __syncthreads();
+            u32 warp_off = 0u, cta_tot = 0u;
+#pragma unroll
+            for (u32 k = 0; k < (u32)kQuadWarps; ++k) {
+                warp_off += k < w ? s_warp_tot[k] : 0u;
+                cta_tot += s_warp_tot[k];
+            }
+            if (threadIdx.x == 0) st_relaxed_u64(&agg[tile], kAggValid | cta_tot);
+            // every thread polls the words j = tid, tid + 256, ... of the earlier tiles; the loads of
+            // a round of four are all in flight before the first one is tested
+            unsigned long long part = 0ull;
+            constexpr size_t kStride = (size_t)kQuadWarps * 32;
+            for (size_t j0 = threadIdx.x; j0 < tile; j0 += 4 * kStride) {
+                unsigned long long v[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) v[r] = j0 + r * kStride < tile ? ld_relaxed_u64(&agg[j0 + r * kStride]) : kAggValid;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    while (!(v[r] & kAggValid)) v[r] = ld_relaxed_u64(&agg[j0 + r * kStride]);
+                    part += v[r] & ~kAggValid;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+            if (lane == 0u) s_red[w] = part;
+            __syncthreads();
+            unsigned long long prefix = 0ull;
+#pragma unroll
+            for (u32 k = 0; k < (u32)kQuadWarps; ++k) prefix += s_red[k];
+            off = prefix + warp_off + excl;
+            if (have && act == 0u && a.offsets_out) a.offsets_out[mine] = (int64_t)off;
+            if (threadIdx.x == 0 && (tile + 1) * (size_t)kQuadBoards >= a.n && total_out) {  // the last tile
+                total_out[0] = prefix + cta_tot;
+                total_out[1] = (a.capacity != 0 && prefix + cta_tot > a.capacity) ? 1ull : 0ull;
+            }
+            if (a.capacity != 0 && off + tot > a.capacity) cc4 = 0u;  // does not fit: nothing is written
+        } else {
+            off = !have ? 0ull
+                        : (kLayout == G2048_CHILDREN_COMPACT ? (unsigned long long)a.child_offsets[mine]
+                                                             : (unsigned long long)mine * 128ull);
+        }
+        QuadTile& t = s_tile[w];
+        t.rec[b][act] = make_uint4(al, ah, fast::nz8(al, 1u), fast::nz8(ah, 1u));
+        if (act == 0u) {
+            const u32 h = (cc4 >> 1) & 0x7F7F7F7Fu;  // pairs (= empty cells) in front of each action's segment
+            t.meta[b] = make_uint4(cc4, (h << 8) + (h << 16) + (h << 24), (u32)off, (u32)(off >> 32));
+        }
+        __syncwarp();
+        if (warp_base < a.n)
+            expand_children_tile<kLayout>(a, t, (u32)min((size_t)8, a.n - warp_base), lane);
+        __syncwarp();
+    }
+}
+
 // Large batches: moves kernel (writes child_count), then a three-kernel scan of the per-board
 // totals (tile sums, scan of the tile sums by one CTA, per-tile apply), then the children kernel.
 constexpr int kScanThreads = 256, kScanPerThread = 4, kScanTileBoards = kScanThreads * kScanPerThread;
@@ -1852,11 +1991,20 @@ extern "C" int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* re
         const ExpandArgs a{reinterpret_cast<const u64*>(boards), reinterpret_cast<u64*>(after), rewards, mask,
                            num_empty, child_count, reinterpret_cast<u64*>(children), child_offsets,
                            child_layout, n, s->table, s->table_hashed, 1u};
-        const int grid = grid_for(n, kFusedWarps * 32, s->sms, 32 / kFusedWarps);
-        if (child_layout == G2048_CHILDREN_COMPACT)
-            expand_fused_kernel<G2048_CHILDREN_COMPACT><<<grid, kFusedWarps * 32, 0, st>>>(a);
-        else
-            expand_fused_kernel<G2048_CHILDREN_DENSE><<<grid, kFusedWarps * 32, 0, st>>>(a);
+        if (g_expand_old) {  // first-generation fused kernel (lane = board), kept for the A/B measurement
+            const int grid = grid_for(n, kFusedWarps * 32, s->sms, 32 / kFusedWarps);
+            if (child_layout == G2048_CHILDREN_COMPACT)
+                expand_fused_kernel<G2048_CHILDREN_COMPACT><<<grid, kFusedWarps * 32, 0, st>>>(a);
+            else
+                expand_fused_kernel<G2048_CHILDREN_DENSE><<<grid, kFusedWarps * 32, 0, st>>>(a);
+        } else {
+            const size_t tiles = (n + kQuadBoards - 1) / kQuadBoards;
+            const int grid = (int)(tiles < (size_t)s->sms * 8 ? tiles : (size_t)s->sms * 8);
+            if (child_layout == G2048_CHILDREN_COMPACT)
+                expand_quad_kernel<G2048_CHILDREN_COMPACT, false><<<grid, kQuadWarps * 32, 0, st>>>(a, nullptr, nullptr);
+            else
+                expand_quad_kernel<G2048_CHILDREN_DENSE, false><<<grid, kQuadWarps * 32, 0, st>>>(a, nullptr, nullptr);
+        }
         CU(cudaGetLastError());
         return G2048_OK;
     }
@@ -1929,7 +2077,7 @@ extern "C" int g2048_expand_compact(const uint64_t* boards, uint64_t* after, int
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long* tot = reinterpret_cast<unsigned long long*>(total_out);
     if (n < kExpandSmemMinBoards) {
-        const size_t tiles = (n + kScanWarps * 32 - 1) / (kScanWarps * 32);
+        const size_t tiles = g_expand_old ? (n + kScanWarps * 32 - 1) / (kScanWarps * 32) : (n + kQuadBoards - 1) / kQuadBoards;
         unsigned long long* scratch = nullptr;
         CU(cudaMallocFromPoolAsync(&scratch, (tiles + 2) * sizeof(unsigned long long), s->pool, st));
         auto launch = [&]() -> int {
@@ -1937,7 +2085,10 @@ extern "C" int g2048_expand_compact(const uint64_t* boards, uint64_t* after, int
             const ExpandArgs a{reinterpret_cast<const u64*>(boards), reinterpret_cast<u64*>(after), rewards, mask,
                                num_empty, child_count, reinterpret_cast<u64*>(children), nullptr,
                                G2048_CHILDREN_COMPACT, n, s->table, s->table_hashed, 1u, child_offsets, capacity};
-            expand_compact_fused_kernel<<<(unsigned)tiles, kScanWarps * 32, 0, st>>>(a, scratch, tot);
+            if (g_expand_old)
+                expand_compact_fused_kernel<<<(unsigned)tiles, kScanWarps * 32, 0, st>>>(a, scratch, tot);
+            else
+                expand_quad_kernel<G2048_CHILDREN_COMPACT, true><<<(unsigned)tiles, kQuadWarps * 32, 0, st>>>(a, scratch + 2, tot);
             CU(cudaGetLastError());
             return G2048_OK;
         };

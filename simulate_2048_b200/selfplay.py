@@ -116,14 +116,16 @@ class BatchedEnv:
         if not self._use_graph:
             launch()
             return self._result()
-        g = self._policy_graphs.get(key)
-        if g is None:
+        entry = self._policy_graphs.get(key)
+        if entry is None:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):   # capture records the launches, it does not run them
                 launch()
-            self._policy_graphs[key] = g
-        g.replay()
+            # the entry keeps `record` alive: the graph holds its device pointers, and a freed
+            # buffer's id() could be handed to a different object
+            entry = self._policy_graphs[key] = (g, record)
+        entry[0].replay()
         return self._result()
 
     def step(self, actions: torch.Tensor, spawns: Optional[torch.Tensor] = None) -> StepResult:
