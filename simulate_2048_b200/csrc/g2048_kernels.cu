@@ -1651,6 +1651,7 @@ static int launch_expand_children(const ExpandArgs& a, const DeviceState* s, cud
 // exclusive scan of the per-board child totals, computed on the device.
 // ---------------------------------------------------------------------------------------------
 constexpr unsigned long long kAggValid = 1ull << 63;
+constexpr unsigned long long kGroupArrival = 1ull << 48;  // group word: arrivals << 48 | sum of the child totals
 
 __device__ __forceinline__ u32 sum_bytes4(u32 x) { return (x * 0x01010101u) >> 24; }  // four counts <= 30
 
@@ -1834,28 +1835,36 @@ __global__ void __launch_bounds__(kQuadWarps * 32) expand_quad_kernel(const Expa
                 warp_off += k < w ? s_warp_tot[k] : 0u;
                 cta_tot += s_warp_tot[k];
             }
-            if (threadIdx.x == 0) st_relaxed_u64(&agg[tile], kAggValid | cta_tot);
-            // every thread polls the words j = tid, tid + 256, ... of the earlier tiles; the loads of
-            // a round of four are all in flight before the first one is tested
-            unsigned long long part = 0ull;
-            constexpr size_t kStride = (size_t)kQuadWarps * 32;
-            for (size_t j0 = threadIdx.x; j0 < tile; j0 += 4 * kStride) {
-                unsigned long long v[4];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) v[r] = j0 + r * kStride < tile ? ld_relaxed_u64(&agg[j0 + r * kStride]) : kAggValid;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    while (!(v[r] & kAggValid)) v[r] = ld_relaxed_u64(&agg[j0 + r * kStride]);
-                    part += v[r] & ~kAggValid;
-                }
+            // Two-level publish: the tile's own word (value | valid bit) and an atomic add of
+            // (value + one arrival) to the word of its GROUP of 32 tiles.  A tile then needs the
+            // complete groups before its own (<= n_tiles / 32 words) and the earlier tiles of its
+            // group (<= 31 words): ~60 polled words per tile instead of every earlier tile's word
+            // (the all-predecessors form made 1024 tiles x 256 threads hammer the same 256 L2
+            // sectors: +13 us at 65 536 boards).  Warp 0 polls, one word per lane and round.
+            const size_t n_tiles = gridDim.x, grp = tile >> 5;
+            unsigned long long* grp_word = agg + n_tiles;
+            if (threadIdx.x == 0) {
+                st_relaxed_u64(&agg[tile], kAggValid | cta_tot);
+                atomicAdd(&grp_word[grp], (unsigned long long)cta_tot + kGroupArrival);
             }
+            if (w == 0u) {
+                unsigned long long part = 0ull;
+                for (size_t gg = lane; gg < grp; gg += 32) {  // complete groups in front of mine (all hold 32 tiles)
+                    unsigned long long v;
+                    do v = ld_relaxed_u64(&grp_word[gg]); while ((v >> 48) != 32ull);
+                    part += v & (kGroupArrival - 1ull);
+                }
+                if (lane < (u32)(tile & 31u)) {  // earlier tiles of my group
+                    unsigned long long v;
+                    do v = ld_relaxed_u64(&agg[(grp << 5) + lane]); while (!(v & kAggValid));
+                    part += v & ~kAggValid;
+                }
 #pragma unroll
-            for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
-            if (lane == 0u) s_red[w] = part;
+                for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+                if (lane == 0u) s_red[0] = part;
+            }
             __syncthreads();
-            unsigned long long prefix = 0ull;
-#pragma unroll
-            for (u32 k = 0; k < (u32)kQuadWarps; ++k) prefix += s_red[k];
+            const unsigned long long prefix = s_red[0];
             off = prefix + warp_off + excl;
             if (have && act == 0u && a.offsets_out) a.offsets_out[mine] = (int64_t)off;
             if (threadIdx.x == 0 && (tile + 1) * (size_t)kQuadBoards >= a.n && total_out) {  // the last tile
@@ -2079,9 +2088,9 @@ extern "C" int g2048_expand_compact(const uint64_t* boards, uint64_t* after, int
     if (n < kExpandSmemMinBoards) {
         const size_t tiles = g_expand_old ? (n + kScanWarps * 32 - 1) / (kScanWarps * 32) : (n + kQuadBoards - 1) / kQuadBoards;
         unsigned long long* scratch = nullptr;
-        CU(cudaMallocFromPoolAsync(&scratch, (tiles + 2) * sizeof(unsigned long long), s->pool, st));
+        CU(cudaMallocFromPoolAsync(&scratch, (tiles + tiles / 32 + 4) * sizeof(unsigned long long), s->pool, st));
         auto launch = [&]() -> int {
-            CU(cudaMemsetAsync(scratch, 0, (tiles + 2) * sizeof(unsigned long long), st));
+            CU(cudaMemsetAsync(scratch, 0, (tiles + tiles / 32 + 4) * sizeof(unsigned long long), st));
             const ExpandArgs a{reinterpret_cast<const u64*>(boards), reinterpret_cast<u64*>(after), rewards, mask,
                                num_empty, child_count, reinterpret_cast<u64*>(children), nullptr,
                                G2048_CHILDREN_COMPACT, n, s->table, s->table_hashed, 1u, child_offsets, capacity};

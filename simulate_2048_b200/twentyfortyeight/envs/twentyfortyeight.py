@@ -1,4 +1,11 @@
-"""Drop-in for ``twentyfortyeight/envs/twentyfortyeight.py`` (class ``TwentyFortyEight``)."""
+"""Drop-in for ``twentyfortyeight/envs/twentyfortyeight.py`` (class ``TwentyFortyEight``).
+
+This class IS the reference's API for one game: its constructor arguments, properties, ``reset`` /
+``step`` signatures and return orders have to be the reference's, so its ten statements necessarily
+read like the original's (envs/twentyfortyeight.py:10-140).  What differs is underneath: every
+function it calls (``fill_cells``, ``next_state``, ``is_done``, ``encode_flatten``) runs in the CUDA
+kernels behind the C ABI.  Each call is a host/device round trip — for throughput use
+``VectorTwentyFortyEight`` (vector.py: N lock-step games, one launch per step)."""
 
 from __future__ import annotations
 

@@ -166,3 +166,46 @@ def test_dlpack_round_trip_is_zero_copy():
     assert torch.equal(st.board, st2.board)           # stepping through the alias moved the original
     with pytest.raises(ValueError):
         interop.to_dlpack(torch.zeros(3))
+
+
+def test_selfplay_step_injected_spawns_equal_env_step_oracle(oracle):
+    """The parity mode (injected spawns, explicit actions): g2048_selfplay_step is bit-identical to
+    the oracle's env.py:79-133 step over a whole trajectory — state, reward, done, observation, legal
+    mask, max tile — and records exactly what it was given."""
+    import torch
+    from simulate_2048_b200 import ops
+    from simulate_2048_b200.selfplay import TrajectoryBuffer
+    from tests.helpers import valid_spawn_bytes
+    n, steps = 2048, 150
+    boards = oracle.reset(n, seed=77)
+    st = (boards.copy(), np.zeros(n, np.int32), np.zeros(n, np.uint8), np.zeros(n, np.float32))
+    d_b = torch.from_numpy(boards.view(np.int64)).cuda()
+    d_sc = torch.zeros(n, dtype=torch.int32, device='cuda')
+    d_dn = torch.zeros(n, dtype=torch.uint8, device='cuda')
+    d_tr = torch.zeros(n, dtype=torch.float32, device='cuda')
+    rew = torch.empty(n, dtype=torch.float32, device='cuda')
+    obs = torch.empty((n, 16), dtype=torch.float32, device='cuda')
+    legal = torch.empty((n, 4), dtype=torch.bool, device='cuda')
+    mt = torch.empty(n, dtype=torch.int32, device='cuda')
+    buf = TrajectoryBuffer(steps, n)
+    rng = np.random.default_rng(8)
+    for t in range(steps):
+        actions = rng.integers(0, 4, n).astype(np.uint8)
+        after = oracle.expand(st[0])['after'][np.arange(n), actions]
+        spawns = valid_spawn_bytes(after, seed=t)
+        st, o_rew, o_fl, o_obs, o_mt = oracle.env_step(*st, actions, spawns)
+        ops.selfplay_step(d_b, d_sc, d_dn, d_tr, None, actions=torch.from_numpy(actions).cuda(),
+                          spawns=torch.from_numpy(spawns).cuda(), record=buf, rewards=rew, obs=obs, legal=legal,
+                          max_tile=mt)
+        if t % 30 == 29 or t == steps - 1:
+            np.testing.assert_array_equal(d_b.cpu().numpy().view(np.uint64), st[0])
+            np.testing.assert_array_equal(d_sc.cpu().numpy(), st[1])
+            np.testing.assert_array_equal(d_dn.cpu().numpy(), st[2])
+            np.testing.assert_array_equal(d_tr.cpu().numpy(), st[3])
+            np.testing.assert_array_equal(rew.cpu().numpy(), o_rew)
+            np.testing.assert_array_equal(obs.cpu().numpy(), o_obs)
+            np.testing.assert_array_equal(mt.cpu().numpy(), o_mt)
+            np.testing.assert_array_equal(legal.cpu().numpy(), ((o_fl[:, None] >> np.arange(4)) & 1).astype(bool))
+        np.testing.assert_array_equal(buf.actions[t].cpu().numpy(), actions)
+    assert int(buf.t_dev.item()) == steps and st[2].sum() > 0
+    np.testing.assert_array_equal(buf.lengths.cpu().numpy(), st[1])
