@@ -100,8 +100,6 @@ static std::atomic<int> g_impl{G2048_IMPL_AUTO};
 static std::atomic<int> g_step_threads{0};  // 0 = automatic: 640 with injected spawns (5 warps per scheduler at 96 registers: +1 %), 512 with Philox
 // programmatic dependent launch of the step kernel (environment G2048_PDL=0 turns it off)
 static const int g_pdl = [] { const char* e = getenv("G2048_PDL"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
-// environment G2048_EXPAND_OLD=1: small-batch expansion through the first-generation lane = board kernels (A/B)
-static const int g_expand_old = [] { const char* e = getenv("G2048_EXPAND_OLD"); return e && atoi(e) != 0 ? 1 : 0; }();
 static std::atomic<int> g_step_groups{1};   // groups of 4 envs per thread (1 or 2)  // tuning knob (g2048_set_tuning)
 
 static int device_occupancy(DeviceState& s);  // defined next to the kernels it measures
@@ -1592,40 +1590,6 @@ __global__ void __launch_bounds__(kChildWarps * 32) expand_children_kernel(const
     }
 }
 
-// Small batches: moves and children in ONE kernel (lane = board for the four moves through the
-// L2-resident hashed table, then the warp expands its 32 boards from shared memory).  Saves the
-// second launch and the trip of the records through global memory; large batches keep the two
-// kernels, because there the persistent moves kernel with the staged table is the faster half.
-constexpr int kFusedWarps = 2;  // small CTAs spread the 2048 warp-tiles of a 65536-board batch evenly over 148 SMs (1, 2, 4, 8 warps measure alike)
-
-template <int kLayout>
-__global__ void __launch_bounds__(kFusedWarps * 32) expand_fused_kernel(const ExpandArgs a) {
-    __shared__ ChildTile s_tile[kFusedWarps];
-    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
-    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    const GlobalLut lut{a.table_hashed};
-    for (size_t tile = warp * 32; tile < a.n; tile += n_warps * 32) {
-        const size_t mine = tile + lane;
-        uint4 s01 = make_uint4(0u, 0u, 0u, 0u), s23 = s01;
-        u32 cc4 = 0u;
-        unsigned long long off = 0ull;
-        if (mine < a.n) {
-            const MovesOut r = expand_moves_compute(a, a.boards[mine], lut);
-            expand_moves_store(a, mine, r);
-            s01 = make_uint4(r.after4[0].x, r.after4[0].y, r.after4[1].x, r.after4[1].y);
-            s23 = make_uint4(r.after4[2].x, r.after4[2].y, r.after4[3].x, r.after4[3].y);
-            cc4 = r.cc4;
-            off = (kLayout == G2048_CHILDREN_COMPACT) ? (unsigned long long)a.child_offsets[mine]
-                                                      : (unsigned long long)mine * 128ull;
-        }
-        expand_record(s_tile[w], lane, s01, s23, cc4, off);
-        __syncwarp();
-        expand_children_tile<kLayout>(a, s_tile[w], (u32)min((size_t)32, a.n - tile), lane);
-        __syncwarp();
-    }
-}
-
 // the second kernel of the expansion: one wave, as many blocks as are resident at once (a partial
 // second wave costs ~14 %)
 static int device_occupancy(DeviceState& s) {
@@ -1667,89 +1631,13 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Small batches: ONE launch.  CTA t takes tile t of 128 boards (thread blocks are dispatched in
-// blockIdx order, so a tile only ever waits for tiles that started before it — the assumption
-// CUB's decoupled look-back makes as well), runs the four moves (lane = board, hashed table
-// gathered from L2), scans its child totals, publishes the tile aggregate, sums the aggregates of
-// all earlier tiles (every thread polls <= n_tiles / 128 entries, all in flight at once) and then
-// expands its boards from shared memory at prefix + local offset.
-// scratch[2 + t] = aggregate of tile t | kAggValid (zeroed per call).
-constexpr int kScanWarps = 4;
-
-__global__ void __launch_bounds__(kScanWarps * 32) expand_compact_fused_kernel(const ExpandArgs a,
-                                                                             unsigned long long* scratch,
-                                                                             unsigned long long* total_out) {
-    __shared__ ChildTile s_tile[kScanWarps];
-    __shared__ u32 s_warp_tot[kScanWarps];
-    __shared__ unsigned long long s_red[kScanWarps];
-    const u32 FULL = 0xFFFFFFFFu, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-    const size_t tile = blockIdx.x, warp_base = tile * (kScanWarps * 32) + w * 32, mine = warp_base + lane;
-    const GlobalLut lut{a.table_hashed};
-    uint4 s01 = make_uint4(0u, 0u, 0u, 0u), s23 = s01;
-    u32 cc4 = 0u;
-    if (mine < a.n) {
-        const MovesOut r = expand_moves_compute(a, a.boards[mine], lut);
-        expand_moves_store(a, mine, r);
-        s01 = make_uint4(r.after4[0].x, r.after4[0].y, r.after4[1].x, r.after4[1].y);
-        s23 = make_uint4(r.after4[2].x, r.after4[2].y, r.after4[3].x, r.after4[3].y);
-        cc4 = r.cc4;
-    }
-    const u32 tot = sum_bytes4(cc4);
-    u32 inc = tot;  // inclusive scan over the warp
-#pragma unroll
-    for (u32 d = 1; d < 32u; d <<= 1) {
-        const u32 v = __shfl_up_sync(FULL, inc, d);
-        if (lane >= d) inc += v;
-    }
-    if (lane == 31u) s_warp_tot[w] = inc;
-    __syncthreads();
-    u32 warp_off = 0u, cta_tot = 0u;
-#pragma unroll
-    for (u32 k = 0; k < (u32)kScanWarps; ++k) {
-        warp_off += k < w ? s_warp_tot[k] : 0u;
-        cta_tot += s_warp_tot[k];
-    }
-    unsigned long long* agg = scratch + 2;
-    if (threadIdx.x == 0) st_relaxed_u64(&agg[tile], kAggValid | cta_tot);
-    // every thread polls the aggregates j = tid, tid + 128, ... of the earlier tiles; the loads of a
-    // round of four are all in flight before the first one is tested
-    unsigned long long part = 0ull;
-    constexpr size_t kStride = (size_t)kScanWarps * 32;
-    for (size_t j0 = threadIdx.x; j0 < tile; j0 += 4 * kStride) {
-        unsigned long long v[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) v[r] = j0 + r * kStride < tile ? ld_relaxed_u64(&agg[j0 + r * kStride]) : kAggValid;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            while (!(v[r] & kAggValid)) v[r] = ld_relaxed_u64(&agg[j0 + r * kStride]);
-            part += v[r] & ~kAggValid;
-        }
-    }
-#pragma unroll
-    for (int off = 16; off; off >>= 1) part += __shfl_xor_sync(FULL, part, off);
-    if (lane == 0u) s_red[w] = part;
-    __syncthreads();
-    unsigned long long prefix = 0ull;
-#pragma unroll
-    for (u32 k = 0; k < (u32)kScanWarps; ++k) prefix += s_red[k];
-    const unsigned long long off = prefix + warp_off + (inc - tot);
-    if (mine < a.n && a.offsets_out) a.offsets_out[mine] = (int64_t)off;
-    if (threadIdx.x == 0 && (tile + 1) * (size_t)(kScanWarps * 32) >= a.n && total_out) {  // the last tile
-        total_out[0] = prefix + cta_tot;
-        total_out[1] = (a.capacity != 0 && prefix + cta_tot > a.capacity) ? 1ull : 0ull;
-    }
-    if (a.capacity != 0 && off + tot > a.capacity) cc4 = 0u;
-    expand_record(s_tile[w], lane, s01, s23, cc4, off);
-    __syncwarp();
-    if (warp_base < a.n)
-        expand_children_tile<G2048_CHILDREN_COMPACT>(a, s_tile[w], (u32)min((size_t)32, a.n - warp_base), lane);
-}
-
-// Small batches, second generation: lane = (board, ACTION).  The lane = board kernels above keep
-// only ~3.5 warps per scheduler busy at 65 536 boards (2048 warps on 592 schedulers) and every lane
-// walks four dependent table gathers: ncu showed 26-32 % issue activity and 18-23 us per launch,
-// all of it latency (profiles/r02_expand_fused_before_ncu_summary.txt).  With one (board, action)
-// per lane there are four times as many warps, each with a quarter of the chain: a warp owns 8
+// Small batches (n < 2^17): moves and children in ONE kernel, lane = (board, ACTION).  The first
+// generation (lane = board, removed) kept only ~3.5 warps per scheduler busy at 65 536 boards (2048
+// warps on 592 schedulers) and every lane walked four dependent table gathers: ncu showed 26-32 %
+// issue activity and 18-23 us per launch, all of it latency
+// (profiles/r02_expand_fused_before_ncu_summary.txt).  With one (board, action) per lane there are
+// four times as many warps, each with a quarter of the chain (4096 boards: 7.4 -> 4.1 us, 16 384:
+// 8.4 -> 5.2, 65 536: 11.2 -> 10.5 with given offsets): a warp owns 8
 // boards, computes their 32 moves at once (per-lane orientation words from shared memory, as the
 // step kernel), combines the four lanes of a board with two shuffles, and expands the 8 boards
 // from shared memory.  kScan adds the device-side offsets of g2048_expand_compact: CTA t owns tile
@@ -2000,20 +1888,12 @@ extern "C" int g2048_expand(const uint64_t* boards, uint64_t* after, int32_t* re
         const ExpandArgs a{reinterpret_cast<const u64*>(boards), reinterpret_cast<u64*>(after), rewards, mask,
                            num_empty, child_count, reinterpret_cast<u64*>(children), child_offsets,
                            child_layout, n, s->table, s->table_hashed, 1u};
-        if (g_expand_old) {  // first-generation fused kernel (lane = board), kept for the A/B measurement
-            const int grid = grid_for(n, kFusedWarps * 32, s->sms, 32 / kFusedWarps);
-            if (child_layout == G2048_CHILDREN_COMPACT)
-                expand_fused_kernel<G2048_CHILDREN_COMPACT><<<grid, kFusedWarps * 32, 0, st>>>(a);
-            else
-                expand_fused_kernel<G2048_CHILDREN_DENSE><<<grid, kFusedWarps * 32, 0, st>>>(a);
-        } else {
-            const size_t tiles = (n + kQuadBoards - 1) / kQuadBoards;
-            const int grid = (int)(tiles < (size_t)s->sms * 8 ? tiles : (size_t)s->sms * 8);
-            if (child_layout == G2048_CHILDREN_COMPACT)
-                expand_quad_kernel<G2048_CHILDREN_COMPACT, false><<<grid, kQuadWarps * 32, 0, st>>>(a, nullptr, nullptr);
-            else
-                expand_quad_kernel<G2048_CHILDREN_DENSE, false><<<grid, kQuadWarps * 32, 0, st>>>(a, nullptr, nullptr);
-        }
+        const size_t tiles = (n + kQuadBoards - 1) / kQuadBoards;
+        const int grid = (int)(tiles < (size_t)s->sms * 8 ? tiles : (size_t)s->sms * 8);
+        if (child_layout == G2048_CHILDREN_COMPACT)
+            expand_quad_kernel<G2048_CHILDREN_COMPACT, false><<<grid, kQuadWarps * 32, 0, st>>>(a, nullptr, nullptr);
+        else
+            expand_quad_kernel<G2048_CHILDREN_DENSE, false><<<grid, kQuadWarps * 32, 0, st>>>(a, nullptr, nullptr);
         CU(cudaGetLastError());
         return G2048_OK;
     }
@@ -2086,7 +1966,7 @@ extern "C" int g2048_expand_compact(const uint64_t* boards, uint64_t* after, int
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long* tot = reinterpret_cast<unsigned long long*>(total_out);
     if (n < kExpandSmemMinBoards) {
-        const size_t tiles = g_expand_old ? (n + kScanWarps * 32 - 1) / (kScanWarps * 32) : (n + kQuadBoards - 1) / kQuadBoards;
+        const size_t tiles = (n + kQuadBoards - 1) / kQuadBoards;
         unsigned long long* scratch = nullptr;
         CU(cudaMallocFromPoolAsync(&scratch, (tiles + tiles / 32 + 4) * sizeof(unsigned long long), s->pool, st));
         auto launch = [&]() -> int {
@@ -2094,10 +1974,7 @@ extern "C" int g2048_expand_compact(const uint64_t* boards, uint64_t* after, int
             const ExpandArgs a{reinterpret_cast<const u64*>(boards), reinterpret_cast<u64*>(after), rewards, mask,
                                num_empty, child_count, reinterpret_cast<u64*>(children), nullptr,
                                G2048_CHILDREN_COMPACT, n, s->table, s->table_hashed, 1u, child_offsets, capacity};
-            if (g_expand_old)
-                expand_compact_fused_kernel<<<(unsigned)tiles, kScanWarps * 32, 0, st>>>(a, scratch, tot);
-            else
-                expand_quad_kernel<G2048_CHILDREN_COMPACT, true><<<(unsigned)tiles, kQuadWarps * 32, 0, st>>>(a, scratch + 2, tot);
+            expand_quad_kernel<G2048_CHILDREN_COMPACT, true><<<(unsigned)tiles, kQuadWarps * 32, 0, st>>>(a, scratch + 2, tot);
             CU(cudaGetLastError());
             return G2048_OK;
         };
