@@ -320,3 +320,26 @@ def test_rollout_statistics_sanity(T, ops):
     s = EpisodeStats.from_vector(out.stats.cpu()).summary()
     assert 105 < s['mean_length'] < 130 and 950 < s['mean_reward'] < 1250
     assert s['max_tile'] <= 2048 and s['reached_2048'] < 20
+
+
+def test_rollout_persistent_kernel_variants(T, ops, oracle):
+    """The shared-memory-table rollout kernel (n >= 148 * 512 envs) in its other template variants:
+    games that start from given boards (incl. boards that are already over and a step cap), and
+    trace mode with a stride shorter than the games (truncated traces keep their terminator)."""
+    n = 148 * 512 + 77
+    start = synthetic_packed(n, seed=21, max_exp=6)
+    start[::1000] = 0x1212212112122121                      # no legal move: emitted at once
+    got = ops.rollout(n, seed=9, env_offset=5, boards=dev(T, start), max_steps=300)
+    want = oracle.rollout(n, seed=9, env_offset=5, from_reset=False, boards=start, max_steps=300)
+    np.testing.assert_array_equal(host(got.boards), want['boards'])
+    np.testing.assert_array_equal(got.score.cpu().numpy(), want['score'])
+    np.testing.assert_array_equal(got.steps.cpu().numpy(), want['steps'])
+    np.testing.assert_array_equal(got.maxexp.cpu().numpy(), want['maxexp'])
+    np.testing.assert_array_equal(got.stats.cpu().numpy().view(np.uint64), want['stats'])
+    assert (got.steps.cpu().numpy()[::1000] == 0).all()
+    stride = 48
+    tr = ops.rollout(n, seed=4, trace_stride=stride, max_steps=200)
+    wt = oracle.rollout(n, seed=4, trace_stride=stride, max_steps=200)
+    np.testing.assert_array_equal(tr.trace.cpu().numpy(), wt['trace'])
+    np.testing.assert_array_equal(tr.steps.cpu().numpy(), wt['steps'])
+    np.testing.assert_array_equal(tr.stats.cpu().numpy().view(np.uint64), wt['stats'])

@@ -48,3 +48,59 @@ def test_bench_rank_local_block_has_no_collective():
     assert 'barrier(' not in block and 'max_over_ranks(' not in block and 'dist.' not in block
     calls = re.findall(r'timed\(.*', block)
     assert calls and all('collective=False' in c for c in calls), calls
+
+
+def test_split_keys_follows_dtype_and_shape():
+    """game/env.py _split_keys: the interpretation of a `keys` argument depends on dtype and shape
+    alone — an int64[2] tensor with two envs is two per-env keys, a uint32-style [2] tensor of any
+    other length is ONE key (the ADVICE finding of round 1: `n != 2` special case)."""
+    import torch
+    from simulate_2048_b200.game.env import _split_keys
+    assert _split_keys(None, 5) == (0, None, None)
+    assert _split_keys(17, 5) == (17, None, None)
+    seed, keys, spawns = _split_keys(torch.tensor([3, 4], dtype=torch.int64), 2)
+    assert seed == 0 and spawns is None and keys.tolist() == [3, 4]            # per-env keys, also for n == 2
+    seed, keys, spawns = _split_keys(torch.tensor([3, 4], dtype=torch.int32), 7)
+    assert keys is None and spawns is None and seed == 3 | (4 << 32)           # one JAX-style key
+    seed, keys, spawns = _split_keys(torch.tensor([[1, 2], [3, 4], [5, 6]], dtype=torch.int32), 3)
+    assert keys.tolist() == [1 | (2 << 32), 3 | (4 << 32), 5 | (6 << 32)]      # uint32[N,2] per-env keys
+    seed, keys, spawns = _split_keys(torch.zeros(4, dtype=torch.uint8), 4)
+    assert spawns is not None and keys is None
+    import pytest
+    with pytest.raises(ValueError):
+        _split_keys(torch.zeros(3, dtype=torch.uint8), 4)                      # wrong number of spawn bytes
+    with pytest.raises(ValueError):
+        _split_keys(torch.zeros(5, dtype=torch.int64), 4)                      # neither per-env nor a single key
+
+
+def test_single_board_transitions_require_randomness():
+    """core.next_state / fill_cells: a key (or injected spawns) is mandatory, as in the reference
+    (core.py:173, :234) — no silent seed 0."""
+    import pytest
+    import torch
+    from simulate_2048_b200.game import core
+    board = torch.zeros((4, 4), dtype=torch.int32)
+    with pytest.raises(TypeError):
+        core.next_state(board, 0)
+    with pytest.raises(TypeError):
+        core.fill_cells(board)
+
+
+def test_staged_reference_is_a_verbatim_copy():
+    """oracle/_ref (what bench.py's CPU legs and the live differential tests run) is byte-identical
+    to the mounted reference package; the manifest lists every file with its SHA-256."""
+    import hashlib
+    import json
+    import os
+    import pytest
+    from oracle import make_ref
+    if not os.path.isdir(make_ref.SRC):
+        pytest.skip('reference not mounted')
+    assert make_ref.stage() == make_ref.DST
+    manifest = json.load(open(make_ref.MANIFEST))['files']
+    assert 'twentyfortyeight/core/gameboard.py' in manifest and len(manifest) >= 9
+    for rel, digest in manifest.items():
+        src = os.path.join(make_ref.REF_ROOT, rel)
+        assert hashlib.sha256(open(src, 'rb').read()).hexdigest() == digest, rel
+    gb, gm, Env = make_ref.load()
+    assert os.path.abspath(gb.__file__).startswith(make_ref.DST_ROOT) and Env.ACTIONS == {'left': 0, 'up': 1, 'right': 2, 'down': 3}
