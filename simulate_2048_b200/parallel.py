@@ -89,9 +89,11 @@ class EpisodeStats:
 
 def sharded_rollout(n_total: int, *, seed: int = 0, max_steps: int = 1 << 20,
                     rank: Optional[int] = None, world: Optional[int] = None,
-                    per_env: bool = False, group: Optional[dist.ProcessGroup] = None, device=None):
+                    per_env: bool = False, group: Optional[dist.ProcessGroup] = None, device=None,
+                    to_host: bool = True):
     """Random rollouts of envs [0, n_total) split over the ranks.  Returns (local RolloutOut,
-    global EpisodeStats)."""
+    global EpisodeStats); with ``to_host=False`` the second value is the reduced 24-word vector as
+    a DEVICE tensor (no host synchronisation: decode it later with ``EpisodeStats.from_vector``)."""
     from . import ops  # CUDA only
 
     if rank is None or world is None:
@@ -101,4 +103,5 @@ def sharded_rollout(n_total: int, *, seed: int = 0, max_steps: int = 1 << 20,
     lo, hi = shard_range(n_total, rank, world)
     out = ops.rollout(hi - lo, seed=seed, env_offset=lo, max_steps=max_steps, per_env=per_env,
                       device=device)
-    return out, EpisodeStats.from_vector(reduce_stats(out.stats, group).cpu())
+    reduced = reduce_stats(out.stats, group)
+    return out, (EpisodeStats.from_vector(reduced.cpu()) if to_host else reduced)

@@ -19,7 +19,8 @@ BASE_KEYS = {'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_ste
              'scaling', 'vs_baseline', 'dtype', 'data', 'config', 'e2e', 'gpu_launches'}
 
 
-@pytest.mark.parametrize('name,n', [('r02_bench_final.json', 1), ('r02_bench_2gpu.json', 2), ('r01_bench_8gpu.json', 8)])
+@pytest.mark.parametrize('name,n', [('r02_bench_final.json', 1), ('r02_bench_2gpu.json', 2), ('r02_bench_8gpu.json', 8),
+                                    ('r01_bench_8gpu.json', 8)])
 def test_our_arm_line(name, n):
     d = _load(name)
     assert BASE_KEYS <= set(d) and {'roofline', 'clocks'} <= set(d)
@@ -44,7 +45,7 @@ def test_our_arm_line(name, n):
         assert b['kind'] in ('reference', 'port') and b['cores'] >= 1 and b['value'] > 0 and 'sample' in b
 
 
-@pytest.mark.parametrize('name,n', [('r02_bench_final.json', 1), ('r02_bench_2gpu.json', 2)])
+@pytest.mark.parametrize('name,n', [('r02_bench_final.json', 1), ('r02_bench_2gpu.json', 2), ('r02_bench_8gpu.json', 8)])
 def test_round2_keys(name, n):
     """Philox-mode step and the sharded config-4 rollout live inside `roofline` (a key the driver's
     parse keeps); e2e carries the copy ceiling; the CPU baseline is the real reference engine."""
