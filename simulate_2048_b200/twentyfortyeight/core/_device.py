@@ -37,6 +37,28 @@ def to_numpy(packed: torch.Tensor, like: np.ndarray) -> np.ndarray:
     return tiles.reshape(like.shape).astype(like.dtype if like.dtype.kind in 'iu' else np.int64)
 
 
+def pack_host(state: np.ndarray):
+    """One [4,4] board of tile values -> its packed 64-bit word, on the host (a change of
+    representation, not a game rule).  Returns None when some value is not 0 or a power of two in
+    [2, 32768] — the caller then takes the device pack path, which reports the error."""
+    word = 0
+    for i, v in enumerate(np.asarray(state).reshape(-1).tolist()):
+        v = int(v)
+        if v:
+            e = v.bit_length() - 1
+            if v < 2 or v > 32768 or (1 << e) != v:
+                return None
+            word |= e << (4 * i)
+    return word
+
+
+def unpack_host(word: int, dtype=np.int64) -> np.ndarray:
+    """Packed word -> [4,4] tile values (host)."""
+    word = int(word)
+    return np.array([(1 << ((word >> (4 * i)) & 0xF)) if (word >> (4 * i)) & 0xF else 0 for i in range(16)],
+                    dtype=dtype).reshape(4, 4)
+
+
 class SpawnStream:
     """Stand-in for the module-level ``_GENERATOR`` (gameboard.py:20): a Philox key plus a draw
     counter.  Unseeded at import, like the reference."""
