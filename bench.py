@@ -443,7 +443,7 @@ def run_ours(args):
     philox = {'value': world * B * max(args.steps // 2, 5) / p_total, 'unit': UNIT,
               'bytes_per_env_step': BYTES_PHILOX, 'achieved_gbs': BYTES_PHILOX * B / p_mean / 1e9,
               'frac': BYTES_PHILOX * B / p_mean / 1e9 / peak, 'mean_launch_ms': p_mean * 1e3,
-              'kernel': 'step_lut_kernel<true, 512, 1>',
+              'kernel': 'step_lut_kernel<true, 640, 1>',
               'stream': 'Philox4x32-10, one block per env quad (include/g2048.h "Philox mode")'}
 
     # ---- BASELINE configs[3]: fused rollouts to termination, 2^24 envs in total sharded over ALL

@@ -115,9 +115,9 @@ int g2048_init(int device);
 int g2048_shutdown(void);
 /* Select the row-move implementation used by g2048_step (process-wide measurement knob). */
 int g2048_set_impl(int impl);
-/* Tuning knobs of the smem-table step kernel: threads per CTA (0 = automatic — 640 with injected
- * spawns, 512 with Philox — or 512, 640, 768, 1024; one CTA per SM) and consecutive envs per
- * thread (4, or 8 with 512 / 768 / 1024 threads). */
+/* Tuning knobs of the smem-table step kernel: threads per CTA (0 = automatic = 640, or 512, 640,
+ * 768, 1024; one CTA per SM) and consecutive envs per thread (4, or 8 with 512 / 768 / 1024
+ * threads).  Process-wide measurement knob, like g2048_set_impl. */
 int g2048_set_tuning(int step_threads, int envs_per_thread);
 
 /*

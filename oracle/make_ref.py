@@ -27,6 +27,8 @@ SRC = os.path.join(REF_ROOT, 'twentyfortyeight')
 DST_ROOT = os.path.join(HERE, '_ref')
 DST = os.path.join(DST_ROOT, 'twentyfortyeight')
 MANIFEST = os.path.join(DST_ROOT, 'MANIFEST.json')
+REFERENCE_TESTS = ('test_board.py', 'test_move.py', 'test_environment.py')   # the NumPy engine's own tests
+TESTS_DST = os.path.join(DST_ROOT, 'reference_tests')
 
 
 def _sha(path: str) -> str:
@@ -37,12 +39,22 @@ def _sha(path: str) -> str:
 def stage(force: bool = False) -> Optional[str]:
     """Copy the reference package if it is mounted; return the staged path (None if neither the
     reference nor an earlier copy exists)."""
-    if os.path.isdir(SRC) and (force or not os.path.exists(MANIFEST)):
+    if os.path.isdir(SRC) and (force or not os.path.exists(MANIFEST) or not os.path.isdir(TESTS_DST)):
         if os.path.isdir(DST):
             shutil.rmtree(DST)
         shutil.copytree(SRC, DST, ignore=shutil.ignore_patterns('__pycache__', '*.pyc'))
+        # the reference's own tests of this path (run against the device-backed mirror by
+        # tests/test_gpu_reference_suite.py)
+        tests_dst = os.path.join(DST_ROOT, 'reference_tests')
+        if os.path.isdir(tests_dst):
+            shutil.rmtree(tests_dst)
+        os.makedirs(tests_dst)
+        for name in REFERENCE_TESTS:
+            src = os.path.join(REF_ROOT, 'tests', name)
+            if os.path.exists(src):
+                shutil.copy(src, os.path.join(tests_dst, name))
         files = {}
-        for root, _, names in os.walk(DST):
+        for root, _, names in list(os.walk(DST)) + list(os.walk(tests_dst)):
             for name in sorted(names):
                 p = os.path.join(root, name)
                 files[os.path.relpath(p, DST_ROOT)] = _sha(p)

@@ -97,7 +97,7 @@ struct DeviceState {
 };
 static DeviceState g_dev[64];
 static std::atomic<int> g_impl{G2048_IMPL_AUTO};
-static std::atomic<int> g_step_threads{0};  // 0 = automatic: 640 with injected spawns (5 warps per scheduler at 96 registers: +1 %), 512 with Philox
+static std::atomic<int> g_step_threads{0};  // 0 = automatic: 640 (5 warps per scheduler at 96 registers: +1 % over 512 in both spawn modes)
 // programmatic dependent launch of the step kernel (environment G2048_PDL=0 turns it off)
 static const int g_pdl = [] { const char* e = getenv("G2048_PDL"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
 static std::atomic<int> g_step_groups{1};   // groups of 4 envs per thread (1 or 2)  // tuning knob (g2048_set_tuning)
@@ -635,7 +635,7 @@ extern "C" int g2048_step(const uint64_t* boards_in, const uint8_t* actions, con
 
     if (use_lut) {
         const int smem = (int)kStepSmemBytes;
-        const int threads = tune_threads ? tune_threads : (spawns ? 640 : 512), groups = tune_groups;
+        const int threads = tune_threads ? tune_threads : 640, groups = tune_groups;  // 5 warps per scheduler at 96 registers
         // one CTA per SM as soon as there is a warp-tile for each (the kernel splits in warp-tiles)
         const size_t wunits = n / ((size_t)128 * groups);
         const int grid = (int)(wunits < (size_t)s->sms ? (wunits ? wunits : 1) : (size_t)s->sms);
