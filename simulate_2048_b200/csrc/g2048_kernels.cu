@@ -2488,9 +2488,28 @@ __device__ __forceinline__ u32 roll_step(RollSlot& s, const RolloutArgs& a, cons
     return mask;
 }
 
+// end-of-episode handling of one slot: results out, next game in
+template <bool kFromReset, bool kTrace>
+__device__ __forceinline__ void roll_finish(RollSlot& s, u32 mask, const RolloutArgs& a, const RollShared& sm,
+                                            const RollQueue& q) {
+    if (s.alive && s.t >= 2u && (mask == 0u || s.t - 2u >= a.max_steps)) {
+        roll_emit<kTrace>(s, a, q);
+        roll_fetch<kFromReset, kTrace>(s, a, sm, q);
+    }
+}
+
+// The drain.  Once the queue is empty a lane is left with its last two games, and a warp stays in
+// the loop until the longest of its 64 last games ends (~300 iterations) while its lanes fall idle.
+// Two measures halve what that costs: a lane whose slot 0 runs dry takes over its own slot-1 game
+// (so live games sit in slot 0), and the warp votes once per iteration whether ANY lane still has a
+// slot-1 game — if not, it runs the one-slot loop body (half the instructions).  All lanes stay in
+// the loop until the warp is done (a lane without games steps a dummy game that is never emitted),
+// so the votes are full-warp.  The two-slot body keeps both steps in one basic block: ptxas
+// interleaves the two dependent chains (ILP 2).
 template <bool kFromReset, bool kTrace, class Lut>
 __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RollShared& sm, const Lut& lut,
                                              unsigned int* next) {
+    const u32 FULL = 0xFFFFFFFFu;
     const RollQueue q = roll_queue(a, next);
     RollSlot slot[kRollSlots];
 #pragma unroll
@@ -2500,20 +2519,19 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RollSha
         roll_fetch<kFromReset, kTrace>(slot[k], a, sm, q);
     }
     for (;;) {
-        bool any = false;
-#pragma unroll
-        for (int k = 0; k < kRollSlots; ++k) any |= slot[k].alive;
-        if (!any) break;
-        u32 mask[kRollSlots];
-#pragma unroll
-        for (int k = 0; k < kRollSlots; ++k) mask[k] = roll_step<kTrace>(slot[k], a, sm, q, lut);
-#pragma unroll
-        for (int k = 0; k < kRollSlots; ++k) {
-            RollSlot& s = slot[k];
-            if (s.alive && s.t >= 2u && (mask[k] == 0u || s.t - 2u >= a.max_steps)) {
-                roll_emit<kTrace>(s, a, q);
-                roll_fetch<kFromReset, kTrace>(s, a, sm, q);
+        if (__any_sync(FULL, slot[1].alive)) {
+            const u32 m0 = roll_step<kTrace>(slot[0], a, sm, q, lut);
+            const u32 m1 = roll_step<kTrace>(slot[1], a, sm, q, lut);
+            roll_finish<kFromReset, kTrace>(slot[0], m0, a, sm, q);
+            roll_finish<kFromReset, kTrace>(slot[1], m1, a, sm, q);
+            if (!slot[0].alive && slot[1].alive) {  // the queue is empty: keep the lane's last game in slot 0
+                slot[0] = slot[1];
+                slot[1].alive = false;
             }
+        } else {
+            if (!__any_sync(FULL, slot[0].alive)) break;
+            const u32 m0 = roll_step<kTrace>(slot[0], a, sm, q, lut);
+            roll_finish<kFromReset, kTrace>(slot[0], m0, a, sm, q);
         }
     }
 }
