@@ -34,8 +34,8 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
 def combine_stats(stack: torch.Tensor) -> torch.Tensor:
     """[W, 24] per-rank statistics -> [24] global (sum, except the two max words)."""
     out = stack.sum(dim=0)
-    for w in _MAX_WORDS:
-        out[w] = stack[:, w].max()
+    lo, hi = _MAX_WORDS[0], _MAX_WORDS[-1] + 1          # the two max words are adjacent
+    out[lo:hi] = stack[:, lo:hi].amax(dim=0)
     return out
 
 
