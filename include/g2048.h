@@ -154,6 +154,19 @@ int g2048_env_step(uint64_t* boards, int32_t* step_count, uint8_t* done, float* 
                    void* stream);
 
 /*
+ * core.py:381 sample_action for a batch: the distribution built from `policy` f32[n*4] and
+ * `legal` u8[n*4] (0/1 bytes, a bool[n,4] array) exactly as core.py:401-421 (mask, renormalise, uniform
+ * over the legal actions below 1e-8 of mass, softmax(log(p + 1e-8) / temperature), argmax below
+ * temperature 0.01; f32, tolerance 1e-6 against a NumPy evaluation), and one draw per env: the
+ * inverse CDF at the top 24 bits of the Philox word of (seed, env_offset + i, step, tag 4), with
+ * step = step_ctr[i] (i32[n], e.g. the GameState step_count) or step_base.  actions_out u8[n] and
+ * probs_out f32[n*4] are each optional.  An action of probability 0 is never returned.
+ */
+int g2048_sample_action(const float* policy, const uint8_t* legal, float temperature, uint64_t seed,
+                        uint64_t env_offset, const int32_t* step_ctr, uint32_t step_base,
+                        uint8_t* actions_out, float* probs_out, size_t n, void* stream);
+
+/*
  * One self-play iteration in ONE call (self_play.py:314-368: observation, legal mask, sample_action,
  * batched_step and the per-step trajectory appends), in place on a GameState:
  *   1. action: drawn from `policy` f32[n*4] exactly as core.py:381-424 sample_action builds its

@@ -36,6 +36,7 @@ PROTOTYPES = {
     'g2048_set_tuning': (C.c_int, [C.c_int, C.c_int]),
     'g2048_step': (C.c_int, [_P, _P, _P, _U64, _U64, _P, _U32, _P, _P, _P, _P, _P, _SZ, _P]),
     'g2048_env_step': (C.c_int, [_P, _P, _P, _P, _P, _P, _U64, _U64, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    'g2048_sample_action': (C.c_int, [_P, _P, C.c_float, _U64, _U64, _P, _U32, _P, _P, _SZ, _P]),
     'g2048_selfplay_step': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_float, _U64, _U64, _P, _U32,
                                       _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     'g2048_mask': (C.c_int, [_P, _P, _SZ, _P]),

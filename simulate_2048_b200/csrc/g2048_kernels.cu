@@ -869,6 +869,41 @@ __device__ __forceinline__ u32 sample_from(const float q[4], u32 w) {
     return last;
 }
 
+// core.py:381 sample_action on its own: policy f32[n*4] + legal u8[n*4] -> action u8[n] (and the
+// distribution); the draw of env i is the word of (seed, env_offset + i, step, tag 4), as inside
+// g2048_selfplay_step.
+__global__ void __launch_bounds__(256) sample_action_kernel(const float* __restrict__ policy,
+                                                            const uint8_t* __restrict__ legal, float temperature,
+                                                            u64 seed, u64 env_offset, const int32_t* __restrict__ step_ctr,
+                                                            u32 step_base, uint8_t* __restrict__ actions,
+                                                            float* __restrict__ probs, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const u32 l4 = reinterpret_cast<const u32*>(legal)[i];
+        const u32 mask = ((l4 & 0xFFu) ? 1u : 0u) | ((l4 & 0xFF00u) ? 2u : 0u) | ((l4 & 0xFF0000u) ? 4u : 0u) |
+                         ((l4 & 0xFF000000u) ? 8u : 0u);
+        float q[4];
+        action_distribution(*reinterpret_cast<const float4*>(policy + i * 4), mask, temperature, q);
+        const u32 step = step_ctr ? (u32)step_ctr[i] : step_base;
+        if (actions) actions[i] = (uint8_t)sample_from(q, philox_word(seed, env_offset + i, step, G2048_PHILOX_TAG_POLICY));
+        if (probs) *reinterpret_cast<float4*>(probs + i * 4) = make_float4(q[0], q[1], q[2], q[3]);
+    }
+}
+
+extern "C" int g2048_sample_action(const float* policy, const uint8_t* legal, float temperature, uint64_t seed,
+                                   uint64_t env_offset, const int32_t* step_ctr, uint32_t step_base,
+                                   uint8_t* actions_out, float* probs_out, size_t n, void* stream) {
+    if (n == 0) return G2048_OK;
+    if (!policy || !legal || (!actions_out && !probs_out)) return G2048_EINVAL;
+    if (!aligned(policy, 16) || !aligned(legal, 4) || !aligned(probs_out, 16)) return G2048_EINVAL;
+    DeviceState* s;
+    int rc = current_state(&s);
+    if (rc) return rc;
+    sample_action_kernel<<<grid_for(n, 256, s->sms, 8), 256, 0, (cudaStream_t)stream>>>(
+        policy, legal, temperature, seed, env_offset, step_ctr, step_base, actions_out, probs_out, n);
+    CU(cudaGetLastError());
+    return G2048_OK;
+}
+
 template <bool kPhilox>
 __global__ void __launch_bounds__(256) selfplay_step_kernel(const SelfplayArgs a) {
     const GlobalTable T{a.table};

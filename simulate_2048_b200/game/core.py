@@ -198,31 +198,31 @@ def encode_observation(board: Array) -> Array:
 
 # -- core.py:381 sample_action ------------------------------------------------------------------
 
+def _policy_batch(policy: Array, legal_mask: Array):
+    pol = policy.to(torch.float32).reshape(-1, NUM_ACTIONS).contiguous()
+    legal = legal_mask.to(torch.bool).reshape(-1, NUM_ACTIONS).contiguous()
+    if pol.shape != legal.shape:
+        raise ValueError('policy and legal_mask must have the same shape [..., 4]')
+    return pol, legal
+
+
 def action_distribution(temperature: float, policy: Array, legal_mask: Array) -> Array:
     """The distribution core.py:401-421 samples from: illegal actions masked, renormalised (uniform
     over the legal actions when the mass is below 1e-8), then softmax(log(p + 1e-8) / temperature),
-    or a one-hot of the argmax when temperature < 0.01.  float32[..., 4]."""
-    legal = legal_mask.to(torch.bool)
-    pol = policy.to(torch.float32)
-    masked = torch.where(legal, pol, torch.zeros_like(pol))
-    total = masked.sum(dim=-1, keepdim=True)
-    legal_f = legal.to(torch.float32)
-    uniform = legal_f / legal_f.sum(dim=-1, keepdim=True).clamp(min=1.0)
-    masked = torch.where(total < 1e-8, uniform, masked / total)
-    if temperature < 0.01:
-        return torch.nn.functional.one_hot(masked.argmax(dim=-1), NUM_ACTIONS).to(torch.float32)
-    return torch.softmax(torch.log(masked + 1e-8) / temperature, dim=-1)
+    or a one-hot of the argmax when temperature < 0.01.  float32[..., 4] (g2048_sample_action)."""
+    pol, legal = _policy_batch(policy, legal_mask)
+    _, probs = ops.sample_action(pol, legal, temperature, want_probs=True)
+    return probs.reshape(policy.shape)
 
 
 def sample_action(key: Key, temperature: float, policy: Array, legal_mask: Array) -> Array:
     """core.py:381 — an action drawn from ``action_distribution`` (int64[...]; a scalar tensor for a
-    single policy).  The JAX key becomes the seed of a device generator: the threefry draw itself
-    cannot be reproduced, the distribution is the reference's."""
-    dist = action_distribution(temperature, policy, legal_mask)
-    gen = torch.Generator(device=dist.device)
-    gen.manual_seed(key_to_seed(key) & (2 ** 63 - 1))
-    picks = torch.multinomial(dist.reshape(-1, NUM_ACTIONS), 1, generator=gen)
-    return picks.reshape(dist.shape[:-1])
+    single policy), one kernel launch for the whole batch.  The JAX key becomes the Philox key of the
+    draw (word of (key, row index, 0, tag 4)): the threefry draw itself cannot be reproduced, the
+    distribution is the reference's."""
+    pol, legal = _policy_batch(policy, legal_mask)
+    picks = ops.sample_action(pol, legal, temperature, seed=key_to_seed(key))
+    return picks.to(torch.int64).reshape(policy.shape[:-1])
 
 
 def max_tile(board: Array) -> Array:

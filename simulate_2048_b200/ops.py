@@ -18,7 +18,7 @@ from . import _cabi
 from ._cabi import check, lib
 
 __all__ = [
-    'StepOut', 'ExpandOut', 'RolloutOut', 'step', 'env_step', 'selfplay_step', 'legal_flags', 'legal_actions', 'expand', 'reset',
+    'StepOut', 'ExpandOut', 'RolloutOut', 'step', 'env_step', 'selfplay_step', 'sample_action', 'legal_flags', 'legal_actions', 'expand', 'reset',
     'observe', 'observe_onehot', 'nstep_returns', 'expect', 'sample_children', 'expect_sampled', 'spawn', 'after_state', 'rollout', 'pack', 'unpack', 'unpack_into', 'step_host', 'row_table', 'set_impl', 'set_tuning', 'init',
     'pinned_empty', 'host_numa_info', 'step_host_copies', 'shutdown',
 ]
@@ -157,6 +157,24 @@ def env_step(boards: torch.Tensor, step_count: torch.Tensor, done: torch.Tensor,
                                    _ptr(actions), _ptr(spawns), seed & (2**64 - 1), env_offset,
                                    _ptr(env_keys), _ptr(rewards), _ptr(flags), _ptr(obs),
                                    _ptr(max_tile), _ptr(legal), n, _stream()))
+
+
+def sample_action(policy: torch.Tensor, legal: torch.Tensor, temperature: float = 1.0, *, seed: int = 0,
+                  env_offset: int = 0, step_ctr: Optional[torch.Tensor] = None, step_base: int = 0,
+                  want_probs: bool = False):
+    """core.py:381 sample_action for a batch (g2048_sample_action): uint8[N] actions drawn from
+    ``policy`` f32[N,4] under ``legal`` bool[N,4]; with ``want_probs`` also the f32[N,4] distribution."""
+    n = policy.numel() // 4
+    _req(policy, torch.float32, 'policy', n * 4)
+    _req(legal, torch.bool, 'legal', n * 4)
+    _opt(step_ctr, torch.int32, 'step_ctr', n)
+    actions = torch.empty(n, dtype=torch.uint8, device=policy.device)
+    probs = torch.empty((n, 4), dtype=torch.float32, device=policy.device) if want_probs else None
+    with _on(policy.device):
+        check(lib().g2048_sample_action(_ptr(policy), _ptr(legal), float(temperature), seed & (2**64 - 1),
+                                        env_offset, _ptr(step_ctr), step_base & 0xFFFFFFFF, _ptr(actions),
+                                        _ptr(probs), n, _stream()))
+    return (actions, probs) if want_probs else actions
 
 
 def selfplay_step(boards: torch.Tensor, step_count: torch.Tensor, done: torch.Tensor,

@@ -103,8 +103,8 @@ class BatchedEnv:
         if values is not None and values.data_ptr() != self.values_in.data_ptr():
             self.values_in.copy_(values.reshape(self.n), non_blocking=True)
         key = (id(record), float(temperature), values is not None, bool(normalize))
-        if record is not None:
-            record.t += 1   # host mirror of the device cursor (for slicing afterwards)
+        if record is not None:   # host mirror of the device cursor (rows beyond the capacity are not recorded)
+            record.t = min(record.t + 1, record.capacity)
 
         def launch():
             ops.selfplay_step(self.board, self.step_count, self._done8, self.total_reward, self.policy_in,
