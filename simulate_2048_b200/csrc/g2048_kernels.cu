@@ -2596,7 +2596,9 @@ __global__ void __launch_bounds__(256) rollout_stats_kernel(const u64* __restric
                                                             uint8_t* __restrict__ maxexp_out,
                                                             u64* __restrict__ stats, size_t n) {
     __shared__ u64 sh[G2048_STATS_WORDS];
+    __shared__ u32 sh_hist[16];  // 32-bit shared atomics are native; the 64-bit form is a CAS loop
     if (threadIdx.x < G2048_STATS_WORDS) sh[threadIdx.x] = 0;
+    if (threadIdx.x < 16) sh_hist[threadIdx.x] = 0;
     __syncthreads();
     u64 t_steps = 0, t_score = 0, t_maxscore = 0;
     u32 t_eps = 0, t_maxsteps = 0, t_capped = 0, t_ovf = 0;
@@ -2607,7 +2609,7 @@ __global__ void __launch_bounds__(256) rollout_stats_kernel(const u64* __restric
         if (!stats) continue;
         const u64 sc = (u64)score[i];
         const u32 st = (u32)steps[i];
-        atomicAdd(&sh[8 + mx], 1ull);
+        atomicAdd(&sh_hist[mx], 1u);  // < 2^32 episodes per CTA: the grid-stride loop gives a CTA n / grid of them
         t_eps += 1u;
         t_steps += st;
         t_score += sc;
@@ -2638,7 +2640,7 @@ __global__ void __launch_bounds__(256) rollout_stats_kernel(const u64* __restric
     }
     __syncthreads();
     if (threadIdx.x < G2048_STATS_WORDS) {
-        const u64 v = sh[threadIdx.x];
+        const u64 v = threadIdx.x >= 8 ? (u64)sh_hist[threadIdx.x - 8] : sh[threadIdx.x];
         if (threadIdx.x == 3 || threadIdx.x == 4) atomicMax(&stats[threadIdx.x], v);
         else if (v) atomicAdd(&stats[threadIdx.x], v);
     }
