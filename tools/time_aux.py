@@ -47,3 +47,18 @@ dn = torch.zeros(n, dtype=torch.uint8, device='cuda')
 tr = torch.zeros(n, dtype=torch.float32, device='cuda')
 bb = b.clone()
 timed('env_step (state only)', lambda: ops.env_step(bb, st, dn, tr, acts, None, seed=1), 2 * (8 + 4 + 1 + 4) + 1)
+# round 2 kernels
+timed('legal_actions (bool[N,4])', lambda: ops.legal_actions(b), 8 + 4)
+pol = torch.rand((n, 4), device='cuda')
+legal = ops.legal_actions(b)
+timed('sample_action', lambda: ops.sample_action(pol, legal, 1.0, seed=3), 16 + 4 + 1)
+obs = torch.empty((n, 16), dtype=torch.float32, device='cuda')
+lg = torch.empty((n, 4), dtype=torch.bool, device='cuda')
+rw = torch.empty(n, dtype=torch.float32, device='cuda')
+timed('selfplay_step (no record)', lambda: ops.selfplay_step(bb, st, dn, tr, pol, temperature=1.0, seed=1, rewards=rw, obs=obs, legal=lg),
+      2 * (8 + 4 + 1 + 4) + 16 + 4 + 64 + 4)
+m = n // 16
+ex = ops.expand(b[:m].contiguous(), children='none')
+timed('sample_children k=4', lambda: ops.sample_children(ex, 4, seed=1), (32 + 4 + 16 * 8) / 16)
+vals = torch.rand(m * 16, device='cuda')
+timed('expect_sampled k=4', lambda: ops.expect_sampled(vals, ex, 4), (64 + 4 + 16 + 16) / 16)
