@@ -168,3 +168,37 @@ def test_environment_wrapper_and_initial_board(T, oracle):
     np.testing.assert_array_equal(env2.board.cpu().numpy(), first)
     env2.reset_env()
     assert int(env2.state.step_count) == 0 and not env2.done
+
+
+def test_empty_batches_everywhere(T, ops):
+    """n = 0 through every tensor-level entry point: no launch, no error, empty outputs."""
+    from simulate_2048_b200 import _cabi
+    e64 = T.empty(0, dtype=T.int64, device='cuda')
+    e8 = T.empty(0, dtype=T.uint8, device='cuda')
+    out = ops.step(e64, e8, None, seed=1)
+    assert out.boards.numel() == 0 and out.rewards.numel() == 0 and out.flags.numel() == 0
+    assert ops.step(e64, e8, e8).boards.numel() == 0
+    assert ops.legal_flags(e64).numel() == 0 and tuple(ops.legal_actions(e64).shape) == (0, 4)
+    for layout in ('none', 'dense', 'compact'):
+        ex = ops.expand(e64, children=layout)
+        assert ex.after.shape[0] == 0 and (ex.children is None or ex.children.numel() == 0)
+    assert ops.expand(e64, children='compact').total.tolist() == [0, 0]
+    ch, ne, ec = ops.after_state(e64)
+    assert ch.numel() == 0 and ne.numel() == 0
+    assert ops.reset(0, seed=1).numel() == 0 and ops.spawn(e64, None, seed=1).numel() == 0
+    obs, mx = ops.observe(e64)
+    assert tuple(obs.shape) == (0, 16) and ops.observe_onehot(e64).numel() == 0
+    assert ops.unpack(e64).numel() == 0 and ops.pack(T.empty((0, 4, 4), dtype=T.int32, device='cuda')).numel() == 0
+    r = ops.rollout(0, seed=1)
+    assert r.score.numel() == 0 and int(r.stats.sum()) == 0
+    ops.env_step(e64, T.empty(0, dtype=T.int32, device='cuda'), e8, T.empty(0, dtype=T.float32, device='cuda'), e8, None, seed=1)
+    ops.selfplay_step(e64, T.empty(0, dtype=T.int32, device='cuda'), e8, T.empty(0, dtype=T.float32, device='cuda'),
+                      T.empty((0, 4), dtype=T.float32, device='cuda'), seed=1)
+    assert ops.sample_action(T.empty((0, 4), dtype=T.float32, device='cuda'), T.empty((0, 4), dtype=T.bool, device='cuda')).numel() == 0
+    hb, hr, hf = ops.step_host(np.empty(0, np.uint64), np.empty(0, np.uint8), None, seed=1)
+    assert hb.size == 0 and hr.size == 0 and hf.size == 0
+    # bad arguments come back as error codes, not crashes
+    lib = ops.lib()
+    assert lib.g2048_step(None, None, None, 0, 0, None, 0, None, None, None, None, None, 16, None) == _cabi.EINVAL
+    assert lib.g2048_expand_compact(None, None, None, None, None, None, None, None, 0, None, 4, None) == _cabi.EINVAL
+    assert lib.g2048_observe_onehot(e64.data_ptr(), e8.data_ptr(), 7, 1, None) == _cabi.EINVAL
