@@ -132,3 +132,32 @@ def test_game_through_mirror_equals_reference_env(T, ref):
             assert mirror.is_done(state) == done
             steps += 1
         assert env.is_finished
+
+
+def test_rollout_traces_replay_through_the_reference_engine(T, ops, oracle, ref):
+    """SURVEY.md §8d config 4 parity: the fused rollout kernel emits (action, spawn cell, tile) per
+    step; replayed through the REAL reference engine — ``latent_state`` for the move, the spawned
+    tile written where the trace says, ``legal_actions`` to confirm the action was legal and
+    ``is_done`` at the end — every game ends on the kernel's final board with the kernel's score."""
+    gb, gm, _ = ref
+    n, stride = 96, 2048
+    out = ops.rollout(n, seed=2024, env_offset=17, trace_stride=stride)
+    trace = out.trace.cpu().numpy()
+    start = ops.unpack(ops.reset(n, seed=2024, env_offset=17)).cpu().numpy().astype(np.int64)
+    final = ops.unpack(out.boards).cpu().numpy()
+    scores, steps = out.score.cpu().numpy(), out.steps.cpu().numpy()
+    for i in range(n):
+        board, score, t = start[i].copy(), 0, 0
+        while trace[i, t]:
+            byte = int(trace[i, t])
+            action, cell, four = byte & 3, (byte >> 2) & 0xF, (byte >> 6) & 1
+            assert action in gm.legal_actions(board)
+            after, reward = gb.latent_state(board, action)
+            board = np.array(after)
+            assert board[cell // 4, cell % 4] == 0
+            board[cell // 4, cell % 4] = 4 if four else 2
+            score += int(reward)
+            t += 1
+        assert t == steps[i] and score == scores[i]
+        np.testing.assert_array_equal(board, final[i])
+        assert gb.is_done(board) and not gm.legal_actions(board)
