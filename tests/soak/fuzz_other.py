@@ -28,7 +28,8 @@ def main():
     c_oracle.build()
     rng = np.random.default_rng(777)
     kinds = ['synthetic', 'dense_low', 'big', 'sparse', 'midgame']
-    tot = {'expand_boards': 0, 'expand_children': 0, 'env_steps': 0, 'rollout_games': 0, 'rollout_steps': 0}
+    tot = {'expand_boards': 0, 'expand_children': 0, 'env_steps': 0, 'rollout_games': 0, 'rollout_steps': 0,
+           'selfplay_steps': 0, 'sampled_children': 0}
     bad = 0
     t0 = time.time()
     for rnd in range(rounds):
@@ -88,9 +89,61 @@ def main():
             print(f'MISMATCH rollout round {rnd}', flush=True)
         tot['rollout_games'] += n
         tot['rollout_steps'] += int(out.steps.sum().item())
+        # ---- rollout from given boards (mid-game positions, a step cap) against the oracle
+        n = int(rng.integers(5000, 90000))
+        start = gen_boards('midgame' if rnd % 2 else 'dense_low', n, rng, dev)
+        seed = int(rng.integers(1 << 62)); cap = int(rng.integers(20, 400))
+        out = ops.rollout(n, seed=seed, boards=torch.from_numpy(start.view(np.int64).copy()).to(dev), max_steps=cap)
+        want = c_oracle.rollout(n, seed=seed, from_reset=False, boards=start, max_steps=cap)
+        ok = (np.array_equal(host(out.boards), want['boards']) and np.array_equal(out.score.cpu().numpy(), want['score']) and
+              np.array_equal(out.steps.cpu().numpy(), want['steps']) and np.array_equal(out.maxexp.cpu().numpy(), want['maxexp']) and
+              np.array_equal(out.stats.cpu().numpy().view(np.uint64), want['stats']))
+        if not ok:
+            bad += 1
+            print(f'MISMATCH rollout-from-boards round {rnd}', flush=True)
+        tot['rollout_games'] += n
+        tot['rollout_steps'] += int(out.steps.sum().item())
+        # ---- selfplay_step: sampled actions (= the standalone sampler's), recorded trajectory, state vs oracle
+        n = int(rng.integers(3000, 40000))
+        seed = int(rng.integers(1 << 62))
+        b = c_oracle.reset(n, seed=seed)
+        sc = np.zeros(n, np.int32); dn = np.zeros(n, np.uint8); tr = np.zeros(n, np.float32)
+        db = torch.from_numpy(b.view(np.int64).copy()).to(dev)
+        dsc = torch.zeros(n, dtype=torch.int32, device=dev); ddn = torch.zeros(n, dtype=torch.uint8, device=dev)
+        dtr = torch.zeros(n, dtype=torch.float32, device=dev)
+        dact = torch.empty(n, dtype=torch.uint8, device=dev)
+        drew = torch.empty(n, dtype=torch.float32, device=dev)
+        for t in range(30):
+            pol = torch.rand((n, 4), device=dev) + 0.01
+            legal = ops.legal_actions(db)
+            alone = ops.sample_action(pol, legal, 0.7, seed=seed, step_ctr=dsc)
+            ops.selfplay_step(db, dsc, ddn, dtr, pol, temperature=0.7, seed=seed, rewards=drew, actions_out=dact)
+            acts = dact.cpu().numpy()
+            (b, sc, dn, tr), rew, fl, obs, mt = c_oracle.env_step(b, sc, dn, tr, acts, None, seed=seed)
+            lg = legal.cpu().numpy()
+            ok = (np.array_equal(host(db), b) and np.array_equal(dsc.cpu().numpy(), sc) and
+                  np.array_equal(ddn.cpu().numpy(), dn) and np.array_equal(dtr.cpu().numpy(), tr) and
+                  np.array_equal(drew.cpu().numpy(), rew) and np.array_equal(alone.cpu().numpy(), acts) and
+                  bool(lg[lg.any(axis=1), acts[lg.any(axis=1)]].all()))
+            if not ok:
+                bad += 1
+                print(f'MISMATCH selfplay_step round {rnd} t={t}', flush=True)
+                break
+            tot['selfplay_steps'] += n
+        # ---- sampled chance children against the oracle
+        n = int(rng.integers(2000, 50000)); k = int(rng.integers(1, 9))
+        boards = gen_boards(kind, n, rng, dev)
+        ex = ops.expand(torch.from_numpy(boards.view(np.int64)).to(dev), children='none')
+        seed = int(rng.integers(1 << 62))
+        kids = ops.sample_children(ex, k, seed=seed, env_offset=rnd, draw_base=3 * rnd)
+        want = c_oracle.sample_children(host(ex.after), ex.child_count.cpu().numpy(), k, seed=seed, env_offset=rnd, draw_base=3 * rnd)
+        if not np.array_equal(host(kids), want):
+            bad += 1
+            print(f'MISMATCH sample_children round {rnd}', flush=True)
+        tot['sampled_children'] += n * 4 * k
         print(f'round {rnd} {kind}: ok so far, mismatching checks: {bad}', flush=True)
     line = dict(tot, mismatching_checks=bad, rounds=rounds, seconds=round(time.time() - t0, 1),
-                oracle='oracle/g2048_oracle.c (orc_expand, orc_env_step, orc_rollout)')
+                oracle='oracle/g2048_oracle.c (orc_expand, orc_env_step, orc_rollout, orc_sample_children)')
     print(json.dumps(line))
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
     with open(os.path.join(ROOT, 'gpurun_out', 'fuzz_other.json'), 'w') as f:
