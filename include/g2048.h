@@ -50,10 +50,24 @@
  *     rank  = hi32(w  * n_empty)   spawn cell among the empties,   f1 = lo32(w  * n_empty)
  *     tile 4 iff hi32(f1 * 10) == 0 (p = 0.1),                      f2 = lo32(f1 * 10)
  *     rollout policy: the NEXT action is the hi32(f2 * n_legal)-th legal action of the new board.
- *   Tags: 0 = play step, 1 / 2 = first / second reset tile (step 0; the first rollout action is
- *   digit 3 of the tag-2 word), 3 = first action of a rollout that starts from a given board,
+ *   Tags: 0 = play step, 3 = first action of a rollout that starts from a given board,
  *   4 = the action draw of g2048_selfplay_step (step = the env's step_count),
- *   5 = a sampled chance child of g2048_sample_children (step = draw index).
+ *   5 = a sampled chance child of g2048_sample_children (step = draw index),
+ *   1 / 2 = free for callers of g2048_spawn.
+ *
+ * Game stream (g2048_reset and g2048_rollout), stream layout v3: the draws of ONE game are
+ *   consecutive words of that env's own blocks — block b = Philox4x32-10 of counter
+ *   (env_lo, env_hi, b, tag 6) under the same key, and word p of the stream is word p & 3 of block
+ *   p >> 2 (env = GLOBAL env id).  Four consecutive draws of a game cost one block: a rollout lane,
+ *   whose games are all at different steps, cannot share the quad layout's block with anyone.
+ *     p = 0, 1 : first / second reset tile (digits 1, 2 as above); the first action of a rollout
+ *                from reset is digit 3 of word 1;
+ *     rollout from reset: play step k reads word k + 2;  rollout from given boards: word k
+ *     (its first action is digit 3 of the quad-layout word of (env, step 0, tag 3)).
+ *   The lock-step entry points (g2048_step, g2048_env_step, g2048_selfplay_step, g2048_spawn) use
+ *   the quad layout; a rollout is therefore NOT the Philox-mode g2048_step sequence of the same
+ *   seed — its trace (action, spawn cell, tile per step) replays through g2048_step with injected
+ *   spawns and through the reference engine.
  *
  * Flags byte (per env):
  */
@@ -67,7 +81,7 @@
 extern "C" {
 #endif
 
-#define G2048_ABI_VERSION 2
+#define G2048_ABI_VERSION 3
 
 #define G2048_FLAG_LEFT 0x01u     /* legal-action mask of the NEW board, bit a = action a */
 #define G2048_FLAG_UP 0x02u
@@ -86,11 +100,10 @@ extern "C" {
 #define G2048_ERANGE (-4)   /* tile value not representable (pack) */
 
 #define G2048_PHILOX_TAG_STEP 0u
-#define G2048_PHILOX_TAG_RESET0 1u
-#define G2048_PHILOX_TAG_RESET1 2u
 #define G2048_PHILOX_TAG_START 3u
 #define G2048_PHILOX_TAG_POLICY 4u
 #define G2048_PHILOX_TAG_CHANCE 5u
+#define G2048_PHILOX_TAG_GAME 6u    /* the game stream: counter (env_lo, env_hi, block, 6) */
 
 /* children layout for g2048_expand */
 #define G2048_CHILDREN_NONE 0
@@ -249,7 +262,7 @@ int g2048_after_state(const uint64_t* boards, uint64_t* children, uint8_t* num_e
                       uint16_t* empty_cells, size_t n, void* stream);
 
 /* New games: two spawns on the empty board (core.py:324 create_initial_board,
- * twentyfortyeight.py:84 reset).  spawns[n*2] injected or NULL for Philox tags 1, 2. */
+ * twentyfortyeight.py:84 reset).  spawns[n*2] injected or NULL for words 0, 1 of the env's game stream. */
 int g2048_reset(uint64_t seed, uint64_t env_offset, const uint64_t* env_keys,
                 const uint8_t* spawns, uint64_t* boards_out, size_t n, void* stream);
 
@@ -312,11 +325,11 @@ int g2048_nstep_returns(const float* rewards, const float* values, const int32_t
 
 /*
  * Fused random-policy rollout to termination, boards in registers:
- *   policy = uniform over the legal actions (digit 3 of the previous step's word, see "Philox
- *   mode"), spawns from digits 1 / 2 of the word of (env, step): the boards of a rollout are those
- *   of g2048_step in Philox mode fed with the same actions.
+ *   policy = uniform over the legal actions (digit 3 of the previous step's word), spawns from
+ *   digits 1 / 2 of the env's game-stream word of that step (see "Game stream"): results depend on
+ *   (seed, global env id) only — not on the grid, the GPU count or which lane played the game.
  *   boards_io[n]: start boards if `from_reset` == 0 (updated to the final boards), else
- *   output only (games start from g2048_reset's Philox boards).
+ *   output only (games start from g2048_reset's Philox boards of the same seed).
  *   score_out i64[n] (sum of rewards), steps_out i32[n], maxexp_out u8[n] — any may be NULL.
  *   stats_out u64[G2048_STATS_WORDS] (device, accumulated atomically; zero it first):
  *     [0] episodes, [1] total steps, [2] total score, [3] max score, [4] max steps,

@@ -42,6 +42,7 @@ def lib() -> C.CDLL:
         _lib.orc_legal_mask_values.restype = C.c_uint
         _lib.orc_rollout.restype = C.c_uint64
         _lib.orc_philox_word.restype = C.c_uint32
+        _lib.orc_game_word.restype = C.c_uint32
         _lib.orc_draw_spawn.restype = C.c_uint32
     return _lib
 
@@ -69,6 +70,11 @@ def philox4x32_10(ctr, key):
 def philox_word(key: int, env: int, step: int, tag: int) -> int:
     """The 32-bit word env reads at (step, tag): word env & 3 of the block of quad env >> 2."""
     return int(lib().orc_philox_word(C.c_uint64(key), C.c_uint64(env), C.c_uint32(step), C.c_uint32(tag)))
+
+
+def game_word(key: int, env: int, p: int) -> int:
+    """Word p of env's game stream (g2048_reset, g2048_rollout): word p & 3 of the env's block p >> 2."""
+    return int(lib().orc_game_word(C.c_uint64(key), C.c_uint64(env), C.c_uint32(p)))
 
 
 def draw_spawn(w: int, n_empty: int):

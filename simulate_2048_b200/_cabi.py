@@ -90,7 +90,7 @@ def lib() -> C.CDLL:
             fn = getattr(handle, name)  # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        if handle.g2048_abi_version() != 2:
+        if handle.g2048_abi_version() != 3:
             raise ImportError('libg2048.so ABI version mismatch; rebuild it')
         _lib = handle
     return _lib

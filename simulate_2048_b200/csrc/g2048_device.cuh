@@ -380,6 +380,18 @@ __device__ __forceinline__ u32 philox_word(const PhiloxKeys& ks, u64 env, u32 st
     return philox_pick(philox_quad(ks, env, step, tag), (u32)env & 3u);
 }
 
+// The GAME stream of one env (include/g2048.h "Game stream"; g2048_reset and g2048_rollout): block b =
+// Philox4x32-10 of counter (env_lo, env_hi, b, tag 6), and word p of the stream is word p & 3 of
+// block p >> 2 — four consecutive draws of ONE game cost one block.  (The quad layout above gives
+// four envs at the SAME step one block: the right shape for the lock-step kernels, the wrong one
+// for a rollout lane whose games are at different steps.)
+__device__ __forceinline__ Philox4 philox_game_block(const PhiloxKeys& ks, u32 env_lo, u32 env_hi, u32 b) {
+    return philox4x32_10(env_lo, env_hi, b, G2048_PHILOX_TAG_GAME, ks);
+}
+__device__ __forceinline__ Philox4 philox_game_block(u64 key, u64 env, u32 b) {
+    return philox4x32_10((u32)env, (u32)(env >> 32), b, G2048_PHILOX_TAG_GAME, (u32)key, (u32)(key >> 32));
+}
+
 // digits 1 and 2 of a word: spawn rank in [0, n) and the spawned exponent (2 for a tile 4, p = 0.1);
 // returns the remainder f2 (the next digit is the rollout policy's action)
 __device__ __forceinline__ u32 draw_spawn(u32 w, u32 n, u32& rank, u32& exp) {

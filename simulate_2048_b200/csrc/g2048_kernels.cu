@@ -1264,8 +1264,11 @@ extern "C" int g2048_unpack(const uint64_t* boards, int32_t* tiles, size_t n, vo
 }
 
 // two sequential spawns on the empty board (core.py:338-342)
+// (Philox: words 0 and 1 of the env's game stream, include/g2048.h "Game stream")
 __device__ __forceinline__ Board reset_board(u64 key, u64 env, const uint8_t* spawn2) {
     Board b{0u, 0u};
+    Philox4 p{0u, 0u, 0u, 0u};
+    if (!spawn2) p = philox_game_block(key, env, 0u);
 #pragma unroll
     for (u32 t = 0; t < 2; ++t) {
         u32 zlo, zhi;
@@ -1273,7 +1276,7 @@ __device__ __forceinline__ Board reset_board(u64 key, u64 env, const uint8_t* sp
         if (spawn2) {
             spawn_byte(b, zlo, zhi, spawn2[t]);
         } else {
-            spawn_philox(b, zlo, zhi, philox_word(key, env, 0u, G2048_PHILOX_TAG_RESET0 + t));
+            spawn_philox(b, zlo, zhi, t == 0u ? p.x : p.y);
         }
     }
     return b;
@@ -2330,33 +2333,42 @@ __device__ __noinline__ uint4 rollout_move_slow(u32 lo, u32 hi, u32 action) {
 }
 
 // Every lane plays kRollSlots games at once, one step of each per loop iteration: the two
-// dependent chains interleave (ILP 2 with 6 warps per scheduler instead of ILP 1 with 8), and a
-// game that ends is replaced at once from the queues inside the (divergent) episode branch — no
-// vote and no idle iteration on the common path.  That branch is taken by a warp in about every
-// fourth slot-step (32 lanes x 1 / 118 steps), so it is kept to three stores and one atomic: the
-// per-episode results go to per-env arrays (the caller's or scratch) and a second, HBM-bound
-// kernel (rollout_stats_kernel) derives the max tile, the capped flag and the 24 statistics words
-// from them.  Results are keyed by the global env id and step, so they do not depend on which
-// lane or slot played a game.
+// dependent chains interleave (ILP 2 with 6 warps per scheduler instead of ILP 1 with 8).
+//
+// Random numbers: a game draws from its env's own GAME stream (include/g2048.h "Game stream"):
+// word p of the stream is word p & 3 of block p >> 2, so ONE Philox4x32-10 block feeds four
+// consecutive steps of a game.  To make that pay in SIMT, the loop runs in QUADS of four
+// iterations: games only start at a quad boundary, so every lane of the warp is at word
+// (iteration & 3) of its current block — the two blocks of a lane (one per slot) are computed
+// once per quad by the whole warp, and inside the unrolled quad the word is a fixed register.
+// (Round-2 first version: the quad-layout block of (env >> 2, step) per lane and step, three of
+// its four words unused — 43 of 222 instructions per step.)  A game that ends inside a quad is
+// frozen (`ended`: no move, no spawn, no step count) until the boundary, where its results are
+// written and the next game is fetched: a lane idles 1.5 iterations per ~120-step game, and the
+// divergent episode branch runs once per quad instead of once per iteration.  That branch is kept
+// to three stores and one atomic: the per-episode results go to per-env arrays (the caller's or
+// scratch) and a second, HBM-bound kernel (rollout_stats_kernel) derives the max tile, the capped
+// flag and the 24 statistics words from them.  Results are keyed by the global env id and the
+// position in the game, so they do not depend on which lane or slot played a game, or when.
 //
 // One step (roll_step) = the fast transition of g2048_fast.cuh with the action drawn one step
-// ahead: the word of (env, step) places the tile (digits 1, 2) and, once the mask of the new board
+// ahead: the word of the step places the tile (digits 1, 2) and, once the mask of the new board
 // is known, picks the NEXT action (digit 3) — so the policy costs one IMAD.HI and one LDS.  The two
-// reset tiles run through the same code as phases t = 0, 1 (Philox tags 1, 2, no move): a new game
-// costs two ordinary iterations instead of a divergent reset path.
+// reset tiles run through the same code as phases t = 0, 1 (stream words 0, 1, no move): a new
+// game costs two ordinary iterations instead of a divergent reset path.
 constexpr int kRollSlots = 2;
 
 struct RollSlot {
     u32 lo, hi;     // board
     u32 act;        // action of the next step (already drawn)
     u32 t;          // 0, 1: reset tiles still to place; t >= 2: playing step t - 2
-    u32 qlo, qhi;   // Philox counter words 0, 1 = quad of the global env id
-    u32 j;          // env & 3: the word of the block this env reads
+    u32 elo, ehi;   // global env id (Philox counter words 0, 1 of the game stream)
     u32 ovf;
     u32 k;          // position of this game in the CTA's queue (env = queue base + k)
     u32 pre;        // prefetched queue position of the NEXT game (kRollNoId: none)
     u64 score;
-    bool alive;
+    bool alive;     // the slot holds a game whose results have not been written yet
+    bool ended;     // that game is over (or there is none): frozen until the next quad boundary
 };
 
 struct RollShared {
@@ -2441,14 +2453,14 @@ __device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, co
         s.score = 0;
         s.k = k;
         s.alive = got;
+        s.ended = !got;
         if (!got) {
-            s.qlo = s.qhi = s.j = 0u;
+            s.elo = s.ehi = 0u;
             return;
         }
         const u64 env = a.env_offset + q.lo + k;
-        s.qlo = (u32)(env >> 2);
-        s.qhi = (u32)(env >> 34);
-        s.j = (u32)env & 3u;
+        s.elo = (u32)env;
+        s.ehi = (u32)(env >> 32);
         if (kFromReset) return;
         const Board b = split(q.boards[k]);
         s.lo = b.lo;
@@ -2462,15 +2474,19 @@ __device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, co
     }
 }
 
-// one step (or reset phase) of slot `s`; returns the legal mask of the new board
+// the block that holds the next four words of the slot's game: stream position = t from reset
+// (words 0, 1 are the reset tiles), t - 2 from given boards; a multiple of 4 at every quad boundary
+template <bool kFromReset>
+__device__ __forceinline__ Philox4 roll_block(const RollSlot& s, const RolloutArgs& a) {
+    return philox_game_block(a.keys, s.elo, s.ehi, (kFromReset ? s.t : s.t - 2u) >> 2);
+}
+
+// one step (or reset phase) of slot `s` with the stream word `w`
 template <bool kTrace, class Lut>
-__device__ __forceinline__ u32 roll_step(RollSlot& s, const RolloutArgs& a, const RollShared& sm,
-                                         const RollQueue& q, const Lut& lut) {
+__device__ __forceinline__ void roll_step(RollSlot& s, u32 w, const RolloutArgs& a, const RollShared& sm,
+                                          const RollQueue& q, const Lut& lut) {
     const u32 one = a.one;
-    const bool playing = s.t >= 2u;
-    const Philox4 p = philox4x32_10(s.qlo, s.qhi, playing ? s.t - 2u : 0u,
-                                    playing ? G2048_PHILOX_TAG_STEP : s.t + 1u, a.keys);
-    const u32 w = philox_pick(p, s.j);
+    const bool playing = s.t >= 2u && !s.ended;
     u32 al, ah, reward;
     // The fast move runs unconditionally — on the empty board when some tile is >= 16384 (such a
     // row lies outside the staged table window) — and the exact out-of-line move then replaces
@@ -2485,12 +2501,12 @@ __device__ __forceinline__ u32 roll_step(RollSlot& s, const RolloutArgs& a, cons
         bool moved;
         reward = fast::move_fast(big ? 0u : s.lo, big ? 0u : s.hi, o, lut, one, al, ah, moved);
     }
-    if (big) {
+    if (big && playing) {
         const uint4 r = rollout_move_slow(s.lo, s.hi, s.act);
         al = r.x; ah = r.y; reward = r.z;
-        s.ovf |= playing ? r.w : 0u;
+        s.ovf |= r.w;
     }
-    if (!playing) { al = s.lo; ah = s.hi; reward = 0u; }  // reset phases only spawn
+    if (!playing) { al = s.lo; ah = s.hi; reward = 0u; }  // reset phases only spawn; a frozen slot does nothing
     s.score += reward;
     u32 nlo = fast::nz8(al, one), nhi = fast::nz8(ah, one);
     const u32 tiles_lo = fast::popc(nlo), ne = 16u - (tiles_lo + fast::popc(nhi));
@@ -2498,13 +2514,14 @@ __device__ __forceinline__ u32 roll_step(RollSlot& s, const RolloutArgs& a, cons
     fast::mul_wide(w, ne, rank, f1);      // digit 1: spawn rank
     fast::mul_wide(f1, 10u, tenth, f2);   // digit 2: 0 -> tile 4
     bool in_hi;
-    const u32 bit3 = fast::spawn_marker(nlo, nhi, tiles_lo, rank, one, in_hi);
+    u32 bit3 = fast::spawn_marker(nlo, nhi, tiles_lo, rank, one, in_hi);
+    if (s.ended) bit3 = 0u;
     const u32 exp = 2u - fast::nonzero01(tenth);
     const u32 tile = fast::shr<3>(bit3) * exp;
     if (in_hi) { ah += tile; nhi += bit3; } else { al += tile; nlo += bit3; }
     if (kTrace) {
         const u32 step = s.t - 2u;
-        if (s.alive && playing && step + 1u < a.trace_stride) {  // (a slot without a game replays env 0: no trace)
+        if (playing && step + 1u < a.trace_stride) {
             const u32 cell = ((__ffs(bit3) - 1u) >> 2) + (in_hi ? 8u : 0u);
             q.trace[(size_t)s.k * a.trace_stride + step] =
                 (uint8_t)(0x80u | s.act | (cell << 2) | ((exp - 1u) << 6));
@@ -2513,33 +2530,34 @@ __device__ __forceinline__ u32 roll_step(RollSlot& s, const RolloutArgs& a, cons
     const u32 mask = fast::legal_mask(al, ah, nlo, nhi, one);
     // digit 3: the next action, the k-th legal one of the new board
     const u32 act = sm.pick[mask * 4u + fast::mulhi(f2, fast::popc(mask))];
-    // A slot without a game (the queues are empty) keeps stepping a dummy game that is never
-    // emitted: once that board is stuck, the no-op move leaves no empty cell, the spawn marker is 0
-    // and nothing changes any more — cheaper than freezing the slot with three selects per step.
     s.lo = al;
     s.hi = ah;
-    s.t += 1u;
     s.act = act;
-    return mask;
+    if (!s.ended) {
+        s.t += 1u;
+        s.ended = s.t >= 2u && (mask == 0u || s.t - 2u >= a.max_steps);
+    }
 }
 
-// end-of-episode handling of one slot: results out, next game in
+// quad boundary: results of a finished game out, next game in
 template <bool kFromReset, bool kTrace>
-__device__ __forceinline__ void roll_finish(RollSlot& s, u32 mask, const RolloutArgs& a, const RollShared& sm,
+__device__ __forceinline__ void roll_finish(RollSlot& s, const RolloutArgs& a, const RollShared& sm,
                                             const RollQueue& q) {
-    if (s.alive && s.t >= 2u && (mask == 0u || s.t - 2u >= a.max_steps)) {
+    if (s.alive && s.ended) {
         roll_emit<kTrace>(s, a, q);
         roll_fetch<kFromReset, kTrace>(s, a, sm, q);
     }
 }
 
+#define G2048_ROLL_WORD(p, u) ((u) == 0 ? (p).x : (u) == 1 ? (p).y : (u) == 2 ? (p).z : (p).w)
+
 // The drain.  Once the queue is empty a lane is left with its last two games, and a warp stays in
 // the loop until the longest of its 64 last games ends (~300 iterations) while its lanes fall idle.
 // Two measures halve what that costs: a lane whose slot 0 runs dry takes over its own slot-1 game
-// (so live games sit in slot 0), and the warp votes once per iteration whether ANY lane still has a
-// slot-1 game — if not, it runs the one-slot loop body (half the instructions).  All lanes stay in
-// the loop until the warp is done (a lane without games steps a dummy game that is never emitted),
-// so the votes are full-warp.  The two-slot body keeps both steps in one basic block: ptxas
+// (so live games sit in slot 0), and the warp votes once per quad whether ANY lane still has a
+// slot-1 game — if not, it runs the one-slot quad (half the instructions).  All lanes stay in the
+// loop until the warp is done (a lane without games holds frozen slots), so the votes are
+// full-warp.  The two-slot quad keeps both steps of an iteration in one basic block: ptxas
 // interleaves the two dependent chains (ILP 2).
 template <bool kFromReset, bool kTrace, class Lut>
 __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RollShared& sm, const Lut& lut,
@@ -2555,21 +2573,29 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RollSha
     }
     for (;;) {
         if (__any_sync(FULL, slot[1].alive)) {
-            const u32 m0 = roll_step<kTrace>(slot[0], a, sm, q, lut);
-            const u32 m1 = roll_step<kTrace>(slot[1], a, sm, q, lut);
-            roll_finish<kFromReset, kTrace>(slot[0], m0, a, sm, q);
-            roll_finish<kFromReset, kTrace>(slot[1], m1, a, sm, q);
+            const Philox4 p0 = roll_block<kFromReset>(slot[0], a), p1 = roll_block<kFromReset>(slot[1], a);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                roll_step<kTrace>(slot[0], G2048_ROLL_WORD(p0, u), a, sm, q, lut);
+                roll_step<kTrace>(slot[1], G2048_ROLL_WORD(p1, u), a, sm, q, lut);
+            }
+            roll_finish<kFromReset, kTrace>(slot[0], a, sm, q);
+            roll_finish<kFromReset, kTrace>(slot[1], a, sm, q);
             if (!slot[0].alive && slot[1].alive) {  // the queue is empty: keep the lane's last game in slot 0
                 slot[0] = slot[1];
                 slot[1].alive = false;
+                slot[1].ended = true;
             }
         } else {
             if (!__any_sync(FULL, slot[0].alive)) break;
-            const u32 m0 = roll_step<kTrace>(slot[0], a, sm, q, lut);
-            roll_finish<kFromReset, kTrace>(slot[0], m0, a, sm, q);
+            const Philox4 p0 = roll_block<kFromReset>(slot[0], a);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) roll_step<kTrace>(slot[0], G2048_ROLL_WORD(p0, u), a, sm, q, lut);
+            roll_finish<kFromReset, kTrace>(slot[0], a, sm, q);
         }
     }
 }
+#undef G2048_ROLL_WORD
 
 template <bool kSmem, bool kFromReset, bool kTrace, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutArgs a, unsigned int* next) {

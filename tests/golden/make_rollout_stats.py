@@ -21,7 +21,7 @@ from oracle import c_oracle  # noqa: E402
 SEED = 2048
 lib = c_oracle.lib()
 lib.orc_set_num_threads(len(os.sched_getaffinity(0)))
-out = {'seed': SEED, 'max_steps': 1 << 20, 'from_reset': True, 'philox_stream': 'v2 (quad block, mixed-radix digits)',
+out = {'seed': SEED, 'max_steps': 1 << 20, 'from_reset': True, 'philox_stream': 'v3 game stream (block per env and four draws, mixed-radix digits)',
        'stats': {}}
 for lg in (16, 20, 21, 24):
     stats = np.zeros(24, dtype=np.uint64)

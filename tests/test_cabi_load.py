@@ -35,7 +35,7 @@ def test_header_symbols_are_exported(cabi):
 
 def test_abi_version_and_error_strings(cabi):
     lib = cabi.lib()
-    assert lib.g2048_abi_version() == 2  # v2: quad-block Philox stream layout
+    assert lib.g2048_abi_version() == 3  # v3: quad-block Philox layout + per-env game stream (reset, rollout)
     for code in (0, -1, -2, -3, -4):
         assert lib.g2048_error_string(code)
     assert lib.g2048_set_impl(99) == cabi.EINVAL

@@ -102,6 +102,38 @@ def test_philox_stream_layout_v2(oracle):
     assert oracle.philox_word(2048, 5, 7, 0) == _philox_py([1, 0, 7, 0], [2048, 0])[1]
 
 
+def test_game_stream_layout_v3(oracle):
+    """include/g2048.h "Game stream" (g2048_reset, g2048_rollout): word p of env e = word p & 3 of
+    the block of counter (e_lo, e_hi, p >> 2, tag 6) — checked against the independent generator; the
+    reset tiles are words 0 and 1, and a from-reset rollout reads word step + 2."""
+    rng = np.random.default_rng(6)
+    for _ in range(200):
+        key = int(rng.integers(0, 2**63)) * 2 + int(rng.integers(0, 2))
+        env = int(rng.integers(0, 2**40))
+        p = int(rng.integers(0, 2**20))
+        block = _philox_py([env & 0xFFFFFFFF, env >> 32, p >> 2, 6], [key & 0xFFFFFFFF, key >> 32])
+        assert oracle.game_word(key, env, p) == block[p & 3]
+    assert [oracle.game_word(0, 0, p) for p in range(4)] == _philox_py([0, 0, 0, 6], [0, 0])
+    # reset = two spawns from words 0, 1 (rank base 16, then base 15; tile 4 iff digit 2 == 0)
+    for env in (0, 1, 5, 10**12 + 3):
+        tiles = [0] * 16
+        for t in range(2):
+            empties = [c for c in range(16) if tiles[c] == 0]
+            rank, four, _ = oracle.draw_spawn(oracle.game_word(77, env, t), len(empties))
+            tiles[empties[rank]] = 4 if four else 2
+        got = oracle.unpack(oracle.reset(1, seed=77, env_offset=env)).reshape(-1).tolist()
+        assert got == tiles
+    # a from-reset rollout's first spawn is word 2: replay one step by hand
+    out = oracle.rollout(4, seed=9, trace_stride=64)
+    for i in range(4):
+        byte = int(out['trace'][i, 0])
+        b0 = oracle.reset(1, seed=9, env_offset=i)
+        after = oracle.latent_state(int(b0[0]), byte & 3)[0]
+        empties = [c for c in range(16) if (after >> (4 * c)) & 0xF == 0]
+        rank, four, _ = oracle.draw_spawn(oracle.game_word(9, i, 2), len(empties))
+        assert empties[rank] == (byte >> 2) & 0xF and bool(four) == bool(byte & 0x40)
+
+
 def test_philox_digits_are_uniform(oracle):
     """Digit 2 (p = 0.1) and digit 3 are independent of digit 1: chi-square-free sanity bounds."""
     n = 200_000
