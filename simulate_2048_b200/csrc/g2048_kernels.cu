@@ -2308,6 +2308,7 @@ struct RolloutArgs {
     size_t n;
     size_t per_queue;  // env ids per CTA queue (roll_fetch)
     u32 max_steps;
+    u32 t_end;  // max_steps + 2 (saturated): a slot's `t` at which a game is stopped
     u64* boards_io;
     int64_t* score_out;
     int32_t* steps_out;
@@ -2366,10 +2367,19 @@ struct RollSlot {
     u32 ovf;
     u32 k;          // position of this game in the CTA's queue (env = queue base + k)
     u32 pre;        // prefetched queue position of the NEXT game (kRollNoId: none)
-    u64 score;
+    u32 score;      // < 2^32: even a game that builds a 65536 tile scores ~1.8 M
     bool alive;     // the slot holds a game whose results have not been written yet
     bool ended;     // that game is over (or there is none): frozen until the next quad boundary
+    bool big;       // the board MAY hold a tile >= 16384 (rows outside the staged table window): set
+                    // when a move scores >= 16384 — no smaller move can build such a tile — and
+                    // re-evaluated exactly on the out-of-line path the flag sends the next move to
 };
+
+// some tile >= 16384 (nibble >= 14).  Plain C: the lop3 asm of fast::has_big_tile crashes ptxas 12.9
+// (SIGSEGV) once two slots are unrolled in the rollout kernel.
+__device__ __forceinline__ bool roll_has_big(u32 lo, u32 hi) {
+    return ((((lo << 1) & (lo << 2) & lo) | ((hi << 1) & (hi << 2) & hi)) & 0x88888888u) != 0u;
+}
 
 struct RollShared {
     const uint4* orient;  // per-action orientation words
@@ -2454,6 +2464,7 @@ __device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, co
         s.k = k;
         s.alive = got;
         s.ended = !got;
+        s.big = false;
         if (!got) {
             s.elo = s.ehi = 0u;
             return;
@@ -2466,6 +2477,7 @@ __device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, co
         s.lo = b.lo;
         s.hi = b.hi;
         s.t = 2u;
+        s.big = roll_has_big(b.lo, b.hi);
         const u32 mask = fast::legal_mask(b.lo, b.hi, fast::nz8(b.lo, a.one), fast::nz8(b.hi, a.one), a.one);
         const u32 w = philox_word(a.keys, env, 0u, G2048_PHILOX_TAG_START);
         s.act = sm.pick[mask * 4u + __umulhi(w, (u32)__popc(mask))];
@@ -2486,27 +2498,32 @@ template <bool kTrace, class Lut>
 __device__ __forceinline__ void roll_step(RollSlot& s, u32 w, const RolloutArgs& a, const RollShared& sm,
                                           const RollQueue& q, const Lut& lut) {
     const u32 one = a.one;
-    const bool playing = s.t >= 2u && !s.ended;
+    const bool run = !s.ended;
+    const bool playing = run & (s.t >= 2u);
+    // The fast move runs unconditionally — on the EMPTY board in a reset phase, in a frozen slot and
+    // when the board may hold a tile >= 16384 (such a row lies outside the staged table window): the
+    // move of the empty board is the empty board with score 0, so OR-ing the withheld board back in
+    // restores it (one LOP3 per half, no selects on the results).
+    const bool fast_ok = playing & !s.big;
+    const u32 xl = fast_ok ? s.lo : 0u, xh = fast_ok ? s.hi : 0u;
     u32 al, ah, reward;
-    // The fast move runs unconditionally — on the empty board when some tile is >= 16384 (such a
-    // row lies outside the staged table window) — and the exact out-of-line move then replaces
-    // its result.  The test is plain C: the lop3 asm of fast::has_big_tile crashes ptxas 12.9
-    // (SIGSEGV) once two slots are unrolled in this kernel.
-    const bool big = ((((s.lo << 1) & (s.lo << 2) & s.lo) | ((s.hi << 1) & (s.hi << 2) & s.hi)) & 0x88888888u) != 0u;
     {
         const uint4 o0 = sm.orient[2u * s.act];
         fast::Orient o;
         o.mask = o0.x; o.mul_hi = o0.y; o.mul_lo = o0.z; o.sel_lo = o0.w;
         o.sel_hi = sm.orient[2u * s.act + 1u].x;
         bool moved;
-        reward = fast::move_fast(big ? 0u : s.lo, big ? 0u : s.hi, o, lut, one, al, ah, moved);
+        reward = fast::move_fast(xl, xh, o, lut, one, al, ah, moved);
     }
-    if (big && playing) {
+    al |= s.lo ^ xl;
+    ah |= s.hi ^ xh;
+    if (s.big & playing) {  // never in random play: the exact out-of-line move
         const uint4 r = rollout_move_slow(s.lo, s.hi, s.act);
         al = r.x; ah = r.y; reward = r.z;
         s.ovf |= r.w;
+        s.big = roll_has_big(al, ah);
     }
-    if (!playing) { al = s.lo; ah = s.hi; reward = 0u; }  // reset phases only spawn; a frozen slot does nothing
+    s.big |= reward >= 16384u;
     s.score += reward;
     u32 nlo = fast::nz8(al, one), nhi = fast::nz8(ah, one);
     const u32 tiles_lo = fast::popc(nlo), ne = 16u - (tiles_lo + fast::popc(nhi));
@@ -2515,7 +2532,7 @@ __device__ __forceinline__ void roll_step(RollSlot& s, u32 w, const RolloutArgs&
     fast::mul_wide(f1, 10u, tenth, f2);   // digit 2: 0 -> tile 4
     bool in_hi;
     u32 bit3 = fast::spawn_marker(nlo, nhi, tiles_lo, rank, one, in_hi);
-    if (s.ended) bit3 = 0u;
+    if (!run) bit3 = 0u;
     const u32 exp = 2u - fast::nonzero01(tenth);
     const u32 tile = fast::shr<3>(bit3) * exp;
     if (in_hi) { ah += tile; nhi += bit3; } else { al += tile; nlo += bit3; }
@@ -2533,10 +2550,9 @@ __device__ __forceinline__ void roll_step(RollSlot& s, u32 w, const RolloutArgs&
     s.lo = al;
     s.hi = ah;
     s.act = act;
-    if (!s.ended) {
-        s.t += 1u;
-        s.ended = s.t >= 2u && (mask == 0u || s.t - 2u >= a.max_steps);
-    }
+    // branch-free: the board of a reset phase always has a legal move, and t_end >= 2
+    s.t += run ? 1u : 0u;
+    s.ended = s.ended | (mask == 0u) | (s.t >= a.t_end);
 }
 
 // quad boundary: results of a finished game out, next game in
@@ -2714,7 +2730,8 @@ extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint3
         uint8_t* ovf_buf = sz_ovf ? p : nullptr;
         CU(cudaMemsetAsync(next, 0, (size_t)grid * sizeof(unsigned int), st));
         if (ovf_buf) CU(cudaMemsetAsync(ovf_buf, 0, n, st));
-        const RolloutArgs a{seed, env_offset, n, per_queue, max_steps, boards_buf,
+        const RolloutArgs a{seed, env_offset, n, per_queue, max_steps,
+                            max_steps > 0xFFFFFFFDu ? 0xFFFFFFFFu : max_steps + 2u, boards_buf,
                             score_buf, steps_buf, ovf_buf, trace, trace_stride, s->table, s->table_hashed, 1u,
                             philox_key_schedule(seed)};
 #define G2048_LAUNCH_ROLL(SM, FR, TR, TH)                                                                  \
