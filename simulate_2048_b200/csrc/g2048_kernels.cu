@@ -2362,18 +2362,20 @@ constexpr int kRollSlots = 2;
 struct RollSlot {
     u32 lo, hi;     // board
     u32 act;        // action of the next step (already drawn)
-    u32 t;          // 0, 1: reset tiles still to place; t >= 2: playing step t - 2
+    u32 t;          // 0, 1: reset tiles still to place; t >= 2: playing step t - 2.  Bit 31 = the game
+                    // is over (or there is none): the slot is frozen until the next quad boundary —
+                    // in the counter's sign bit `playing` and `running` are one signed compare each
     u32 elo, ehi;   // global env id (Philox counter words 0, 1 of the game stream)
     u32 ovf;
     u32 k;          // position of this game in the CTA's queue (env = queue base + k)
     u32 pre;        // prefetched queue position of the NEXT game (kRollNoId: none)
     u32 score;      // < 2^32: even a game that builds a 65536 tile scores ~1.8 M
+    u32 bigw;       // OR of the game's move scores: >= 16384 iff the board MAY hold a tile >= 16384 (rows
+                    // outside the staged table window) — no smaller move can build such a tile; the
+                    // out-of-line path such a game takes re-evaluates it exactly
     bool alive;     // the slot holds a game whose results have not been written yet
-    bool ended;     // that game is over (or there is none): frozen until the next quad boundary
-    bool big;       // the board MAY hold a tile >= 16384 (rows outside the staged table window): set
-                    // when a move scores >= 16384 — no smaller move can build such a tile — and
-                    // re-evaluated exactly on the out-of-line path the flag sends the next move to
 };
+constexpr u32 kRollEnded = 0x80000000u;
 
 // some tile >= 16384 (nibble >= 14).  Plain C: the lop3 asm of fast::has_big_tile crashes ptxas 12.9
 // (SIGSEGV) once two slots are unrolled in the rollout kernel.
@@ -2381,9 +2383,26 @@ __device__ __forceinline__ bool roll_has_big(u32 lo, u32 hi) {
     return ((((lo << 1) & (lo << 2) & lo) | ((hi << 1) & (hi << 2) & hi)) & 0x88888888u) != 0u;
 }
 
+// The per-action orientation words and the action pick table live in DYNAMIC shared memory behind
+// the row table (or at its start when the table is gathered from L2) and are indexed off the extern
+// symbol: through a generic pointer to a static __shared__ array ptxas rebuilt the shared-window
+// address (S2R SR_CgaCtaId + LEA) in front of every lookup — eight instructions per step.
+template <bool kSmem>
 struct RollShared {
-    const uint4* orient;  // per-action orientation words
-    const uint8_t* pick;  // action pick table
+    static constexpr u32 kOrientByte = ((kSmem ? kSmemRows : 0u) + 16u) * 4u;  // after the mbarrier slot
+    static constexpr u32 kPickByte = kOrientByte + 4u * (u32)sizeof(fast::Orient);
+    static constexpr u32 kBytes = kPickByte + 64u;
+    __device__ __forceinline__ fast::Orient orient(u32 action) const {
+        const unsigned char* op = reinterpret_cast<const unsigned char*>(smem_words) + kOrientByte + 32u * action;
+        const uint4 o0 = *reinterpret_cast<const uint4*>(op);
+        fast::Orient o;
+        o.mask = o0.x; o.mul_hi = o0.y; o.mul_lo = o0.z; o.sel_lo = o0.w;
+        o.sel_hi = *reinterpret_cast<const u32*>(op + 16);
+        return o;
+    }
+    __device__ __forceinline__ u32 pick(u32 i) const {
+        return *(reinterpret_cast<const unsigned char*>(smem_words) + kPickByte + i);
+    }
 };
 
 // per-thread constants of the CTA's queue: its first env (local index), its length, and the output
@@ -2415,7 +2434,7 @@ __device__ __forceinline__ RollQueue roll_queue(const RolloutArgs& a, unsigned i
 // the episode of slot `s` is over: its per-env results (rollout_stats_kernel does the rest)
 template <bool kTrace>
 __device__ __forceinline__ void roll_emit(const RollSlot& s, const RolloutArgs& a, const RollQueue& q) {
-    const u32 step = s.t - 2u;
+    const u32 step = (s.t & ~kRollEnded) - 2u;
     if (kTrace) q.trace[(size_t)s.k * a.trace_stride + min(step, a.trace_stride - 1u)] = 0;
     q.boards[s.k] = ((u64)s.hi << 32) | s.lo;
     q.score[s.k] = (int64_t)s.score;
@@ -2449,8 +2468,8 @@ __device__ __forceinline__ u32 queue_take(unsigned int* counter, u32 lane_zero) 
     return k;
 }
 
-template <bool kFromReset, bool kTrace>
-__device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, const RollShared& sm,
+template <bool kFromReset, bool kTrace, class Sh>
+__device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, const Sh& sm,
                                            const RollQueue& q) {
     for (;;) {
         u32 k = s.pre;  // reserved at the previous game start (or none)
@@ -2459,12 +2478,11 @@ __device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, co
         const bool got = k < q.own;
         s.pre = kRollNoId;
         if (got && k + kRollMargin < q.own) s.pre = queue_take(q.counter, lane_zero);  // not read until the next game end
-        s.lo = s.hi = s.act = s.t = s.ovf = 0u;
+        s.lo = s.hi = s.act = s.ovf = s.bigw = 0u;
+        s.t = got ? 0u : kRollEnded;
         s.score = 0;
         s.k = k;
         s.alive = got;
-        s.ended = !got;
-        s.big = false;
         if (!got) {
             s.elo = s.ehi = 0u;
             return;
@@ -2477,11 +2495,12 @@ __device__ __forceinline__ void roll_fetch(RollSlot& s, const RolloutArgs& a, co
         s.lo = b.lo;
         s.hi = b.hi;
         s.t = 2u;
-        s.big = roll_has_big(b.lo, b.hi);
+        s.bigw = roll_has_big(b.lo, b.hi) ? 16384u : 0u;
         const u32 mask = fast::legal_mask(b.lo, b.hi, fast::nz8(b.lo, a.one), fast::nz8(b.hi, a.one), a.one);
         const u32 w = philox_word(a.keys, env, 0u, G2048_PHILOX_TAG_START);
-        s.act = sm.pick[mask * 4u + __umulhi(w, (u32)__popc(mask))];
+        s.act = sm.pick(mask * 4u + __umulhi(w, (u32)__popc(mask)));
         if (mask != 0u && a.max_steps != 0u) return;
+        s.t |= kRollEnded;
         roll_emit<kTrace>(s, a, q);  // nothing to play
     }
 }
@@ -2494,36 +2513,33 @@ __device__ __forceinline__ Philox4 roll_block(const RollSlot& s, const RolloutAr
 }
 
 // one step (or reset phase) of slot `s` with the stream word `w`
-template <bool kTrace, class Lut>
-__device__ __forceinline__ void roll_step(RollSlot& s, u32 w, const RolloutArgs& a, const RollShared& sm,
+template <bool kTrace, class Sh, class Lut>
+__device__ __forceinline__ void roll_step(RollSlot& s, u32 w, const RolloutArgs& a, const Sh& sm,
                                           const RollQueue& q, const Lut& lut) {
     const u32 one = a.one;
-    const bool run = !s.ended;
-    const bool playing = run & (s.t >= 2u);
+    const bool run = (int)s.t >= 0;      // not frozen
+    const bool playing = (int)s.t >= 2;  // and past the reset phases
+    const bool maybe_big = s.bigw >= 16384u;
     // The fast move runs unconditionally — on the EMPTY board in a reset phase, in a frozen slot and
     // when the board may hold a tile >= 16384 (such a row lies outside the staged table window): the
     // move of the empty board is the empty board with score 0, so OR-ing the withheld board back in
     // restores it (one LOP3 per half, no selects on the results).
-    const bool fast_ok = playing & !s.big;
+    const bool fast_ok = playing & !maybe_big;
     const u32 xl = fast_ok ? s.lo : 0u, xh = fast_ok ? s.hi : 0u;
     u32 al, ah, reward;
     {
-        const uint4 o0 = sm.orient[2u * s.act];
-        fast::Orient o;
-        o.mask = o0.x; o.mul_hi = o0.y; o.mul_lo = o0.z; o.sel_lo = o0.w;
-        o.sel_hi = sm.orient[2u * s.act + 1u].x;
         bool moved;
-        reward = fast::move_fast(xl, xh, o, lut, one, al, ah, moved);
+        reward = fast::move_fast(xl, xh, sm.orient(s.act), lut, one, al, ah, moved);
     }
     al |= s.lo ^ xl;
     ah |= s.hi ^ xh;
-    if (s.big & playing) {  // never in random play: the exact out-of-line move
+    if (maybe_big & playing) {  // never in random play: the exact out-of-line move
         const uint4 r = rollout_move_slow(s.lo, s.hi, s.act);
         al = r.x; ah = r.y; reward = r.z;
         s.ovf |= r.w;
-        s.big = roll_has_big(al, ah);
+        s.bigw = roll_has_big(al, ah) ? 16384u : 0u;
     }
-    s.big |= reward >= 16384u;
+    s.bigw |= reward;
     s.score += reward;
     u32 nlo = fast::nz8(al, one), nhi = fast::nz8(ah, one);
     const u32 tiles_lo = fast::popc(nlo), ne = 16u - (tiles_lo + fast::popc(nhi));
@@ -2546,20 +2562,21 @@ __device__ __forceinline__ void roll_step(RollSlot& s, u32 w, const RolloutArgs&
     }
     const u32 mask = fast::legal_mask(al, ah, nlo, nhi, one);
     // digit 3: the next action, the k-th legal one of the new board
-    const u32 act = sm.pick[mask * 4u + fast::mulhi(f2, fast::popc(mask))];
+    const u32 act = sm.pick(mask * 4u + fast::mulhi(f2, fast::popc(mask)));
     s.lo = al;
     s.hi = ah;
     s.act = act;
-    // branch-free: the board of a reset phase always has a legal move, and t_end >= 2
-    s.t += run ? 1u : 0u;
-    s.ended = s.ended | (mask == 0u) | (s.t >= a.t_end);
+    // branch-free: the board of a reset phase always has a legal move, t_end is in [2, 2^31), and a
+    // frozen counter is negative
+    if (run) s.t += 1u;
+    if ((mask == 0u) | ((int)s.t >= (int)a.t_end)) s.t |= kRollEnded;
 }
 
 // quad boundary: results of a finished game out, next game in
-template <bool kFromReset, bool kTrace>
-__device__ __forceinline__ void roll_finish(RollSlot& s, const RolloutArgs& a, const RollShared& sm,
+template <bool kFromReset, bool kTrace, class Sh>
+__device__ __forceinline__ void roll_finish(RollSlot& s, const RolloutArgs& a, const Sh& sm,
                                             const RollQueue& q) {
-    if (s.alive && s.ended) {
+    if (s.alive && (int)s.t < 0) {
         roll_emit<kTrace>(s, a, q);
         roll_fetch<kFromReset, kTrace>(s, a, sm, q);
     }
@@ -2575,8 +2592,8 @@ __device__ __forceinline__ void roll_finish(RollSlot& s, const RolloutArgs& a, c
 // loop until the warp is done (a lane without games holds frozen slots), so the votes are
 // full-warp.  The two-slot quad keeps both steps of an iteration in one basic block: ptxas
 // interleaves the two dependent chains (ILP 2).
-template <bool kFromReset, bool kTrace, class Lut>
-__device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RollShared& sm, const Lut& lut,
+template <bool kFromReset, bool kTrace, class Sh, class Lut>
+__device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const Sh& sm, const Lut& lut,
                                              unsigned int* next) {
     const u32 FULL = 0xFFFFFFFFu;
     const RollQueue q = roll_queue(a, next);
@@ -2600,7 +2617,7 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RollSha
             if (!slot[0].alive && slot[1].alive) {  // the queue is empty: keep the lane's last game in slot 0
                 slot[0] = slot[1];
                 slot[1].alive = false;
-                slot[1].ended = true;
+                slot[1].t |= kRollEnded;
             }
         } else {
             if (!__any_sync(FULL, slot[0].alive)) break;
@@ -2615,15 +2632,16 @@ __device__ __forceinline__ void rollout_loop(const RolloutArgs& a, const RollSha
 
 template <bool kSmem, bool kFromReset, bool kTrace, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1) rollout_kernel(const RolloutArgs a, unsigned int* next) {
-    __shared__ __align__(16) uint4 sh_orient[8];
-    __shared__ uint8_t sh_pick[64];
+    using Sh = RollShared<kSmem>;
     u64* bar = reinterpret_cast<u64*>(smem_words + kSmemRows);
     if (kSmem) table_stage_begin(smem_words, bar, a.table_hashed);
-    if (threadIdx.x < 32) reinterpret_cast<u32*>(sh_orient)[threadIdx.x] = reinterpret_cast<const u32*>(c_orient)[threadIdx.x];
-    if (threadIdx.x < 64) sh_pick[threadIdx.x] = c_pick[threadIdx.x];
+    unsigned char* sh = reinterpret_cast<unsigned char*>(smem_words);
+    if (threadIdx.x < 32)
+        reinterpret_cast<u32*>(sh + Sh::kOrientByte)[threadIdx.x] = reinterpret_cast<const u32*>(c_orient)[threadIdx.x];
+    if (threadIdx.x < 64) sh[Sh::kPickByte + threadIdx.x] = c_pick[threadIdx.x];
     if (kSmem) table_stage_wait(bar); else __syncthreads();
 
-    const RollShared sm{sh_orient, sh_pick};
+    const Sh sm{};
     if (kSmem) rollout_loop<kFromReset, kTrace>(a, sm, SmemLut{}, next);
     else rollout_loop<kFromReset, kTrace>(a, sm, GlobalLut{a.table_hashed}, next);
 }
@@ -2704,8 +2722,8 @@ extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint3
     int rc = current_state(&s);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool smem = n >= (size_t)s->sms * 512 && s->smem_optin >= kSmemTableBytes + 64;
-    const int bytes = smem ? (int)kSmemTableBytes + 64 : 0;
+    const bool smem = n >= (size_t)s->sms * 512 && s->smem_optin >= RollShared<true>::kBytes;
+    const int bytes = smem ? (int)RollShared<true>::kBytes : (int)RollShared<false>::kBytes;
     const int threads = smem ? g_roll_threads : kRollSmallThreads;
     const int grid = smem ? s->sms : grid_for((n + kRollSlots - 1) / kRollSlots, kRollSmallThreads, s->sms, 8);
     // scratch (stream-ordered): the queue counters, and the per-env result arrays the caller does not
@@ -2731,7 +2749,7 @@ extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint3
         CU(cudaMemsetAsync(next, 0, (size_t)grid * sizeof(unsigned int), st));
         if (ovf_buf) CU(cudaMemsetAsync(ovf_buf, 0, n, st));
         const RolloutArgs a{seed, env_offset, n, per_queue, max_steps,
-                            max_steps > 0xFFFFFFFDu ? 0xFFFFFFFFu : max_steps + 2u, boards_buf,
+                            max_steps > 0x7FFFFFFDu ? 0x7FFFFFFFu : max_steps + 2u, boards_buf,
                             score_buf, steps_buf, ovf_buf, trace, trace_stride, s->table, s->table_hashed, 1u,
                             philox_key_schedule(seed)};
 #define G2048_LAUNCH_ROLL(SM, FR, TR, TH)                                                                  \
