@@ -2706,9 +2706,11 @@ __global__ void __launch_bounds__(256) rollout_stats_kernel(const u64* __restric
     }
 }
 
-// persistent, one CTA per SM, table in shared memory: 768 threads x 2 slots
-// (environment G2048_ROLL_THREADS=512 selects the smaller CTA; a tuning knob for measurements)
-static int g_roll_threads = [] { const char* e = getenv("G2048_ROLL_THREADS"); return (e && atoi(e) == 512) ? 512 : 768; }();
+// persistent, one CTA per SM, table in shared memory: 640 threads x 2 slots at 94 registers (no
+// spills; 768 threads are capped at 80 registers and keep more games in flight at the end: 155.0 /
+// 153.7 / 149.5 G env-steps/s at 640 / 768 / 512 threads on 2^24 envs, 127.5 / 123.6 / 126.8 on 2^20).
+// (environment G2048_ROLL_THREADS = 512 | 640 | 768: a tuning knob for measurements)
+static int g_roll_threads = [] { const char* e = getenv("G2048_ROLL_THREADS"); const int t = e ? atoi(e) : 0; return (t == 512 || t == 640 || t == 768) ? t : 0; }();
 constexpr int kRollSmallThreads = 128;  // small batches: table gathered from L2
 
 extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint32_t max_steps,
@@ -2724,7 +2726,7 @@ extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint3
     cudaStream_t st = (cudaStream_t)stream;
     const bool smem = n >= (size_t)s->sms * 512 && s->smem_optin >= RollShared<true>::kBytes;
     const int bytes = smem ? (int)RollShared<true>::kBytes : (int)RollShared<false>::kBytes;
-    const int threads = smem ? g_roll_threads : kRollSmallThreads;
+    const int threads = smem ? (g_roll_threads ? g_roll_threads : 640) : kRollSmallThreads;
     const int grid = smem ? s->sms : grid_for((n + kRollSlots - 1) / kRollSlots, kRollSmallThreads, s->sms, 8);
     // scratch (stream-ordered): the queue counters, and the per-env result arrays the caller does not
     // ask for (the kernel always writes boards / score / steps; the statistics pass reads them)
@@ -2769,6 +2771,7 @@ extern "C" int g2048_rollout(uint64_t seed, uint64_t env_offset, size_t n, uint3
         }                                                             \
     } while (0)
         if (smem && threads == 768) G2048_LAUNCH_ROLL_T(true, 768);
+        else if (smem && threads == 640) G2048_LAUNCH_ROLL_T(true, 640);
         else if (smem) G2048_LAUNCH_ROLL_T(true, 512);
         else G2048_LAUNCH_ROLL_T(false, kRollSmallThreads);
 #undef G2048_LAUNCH_ROLL_T
