@@ -43,8 +43,8 @@ sys.path.insert(0, ROOT)
 
 BYTES_INJECTED = 23  # read board 8 + action 1 + spawn 1; write board 8 + reward 4 + flags 1
 BYTES_PHILOX = 22
-ROLLOUT_INSTR_PER_STEP = 222.0   # thread instructions per env-step of rollout_kernel (ncu, profiles/r02_rollout_ncu_summary.txt)
-ROLLOUT_SLOTS_PER_STEP = 249.0   # warp issue slots x 32 per env-step (same capture; 28.6 of 32 lanes active)
+ROLLOUT_INSTR_PER_STEP = 163.6   # thread instructions per env-step of rollout_kernel (ncu, profiles/r02_rollout_game_stream_ncu_summary.txt)
+ROLLOUT_SLOTS_PER_STEP = 172.9   # warp issue slots x 32 per env-step (same capture; 30.28 of 32 lanes active)
 METRIC = 'env_steps_per_sec'
 UNIT = 'env-steps/s'
 
@@ -477,15 +477,16 @@ def run_ours(args):
         'stats_equal_oracle': (got_stats == want_stats) if want_stats is not None else None,
         'oracle_vector': 'tests/golden/rollout_stats.json (oracle/g2048_oracle.c orc_rollout_mt)',
         'summary': r_stats.summary(),
-        'kernel': 'rollout_kernel<true, true, false, 768> + rollout_stats_kernel: two games per lane, one queue '
-                  'per CTA, prefetched game ids',
+        'kernel': 'rollout_kernel<true, true, false, 640> + rollout_stats_kernel: two games per lane, one queue '
+                  'per CTA, prefetched game ids, per-env game stream (one Philox4x32-10 block per four steps of a '
+                  'game, include/g2048.h "Game stream")',
         # issue ceiling of one GPU: 148 SMs x 4 schedulers x 1 warp-instruction / clk x 32 lanes / instr per step
         'issue_ceiling_per_gpu': 148 * 4 * 1.965e9 * 32 / ROLLOUT_INSTR_PER_STEP,
         'issue_ceiling_per_gpu_warp_slots': 148 * 4 * 1.965e9 * 32 / ROLLOUT_SLOTS_PER_STEP,
         'instr_per_step': ROLLOUT_INSTR_PER_STEP, 'issue_slots_per_step': ROLLOUT_SLOTS_PER_STEP,
-        'integer_pipe_utilisation': {'alu_pipe_pct': 71.1, 'fmaheavy_pipe_pct': 72.7, 'issue_active_pct': 70.6,
-                                     'lanes_active_of_32': 28.6, 'kernel': 'rollout_kernel<1,1,0,768> on 2^22 envs'},
-        'instr_per_step_source': 'stored: profiles/r02_rollout_ncu_summary.txt (ncu --set full on 2^22 envs), not '
+        'integer_pipe_utilisation': {'alu_pipe_pct': 71.8, 'fmaheavy_pipe_pct': 68.9, 'issue_active_pct': 71.6,
+                                     'lanes_active_of_32': 30.28, 'kernel': 'rollout_kernel<1,1,0,640> on 2^22 envs'},
+        'instr_per_step_source': 'stored: profiles/r02_rollout_game_stream_ncu_summary.txt (ncu --set full on 2^22 envs), not '
                                  'measured in this run',
     }
     rollout['frac_of_issue_ceiling'] = rollout['env_steps_per_sec'] / (world * rollout['issue_ceiling_per_gpu'])
