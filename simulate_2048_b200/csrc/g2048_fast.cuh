@@ -228,7 +228,10 @@ G2048_HD u32 differ8_dirty(u32 a, u32 b, u32 one) {
 // bank of an entry is the low 5 bits of its index; un-hashed that is the column-0 nibble, which
 // is 0 for about half of all cells in real boards, so distinct rows pile up on banks 0 and 16
 // (ncu: 38.8 wavefronts per warp-step instead of ~20).  XOR-ing column 1 in spreads them.
-G2048_HD u32 hash_rows(u32 w) { return lop3<kA ^ (kB & kC)>(w, shr<4>(w), 0x0FFF0FFFu); }
+// kAluShift: the shift as SHF on the ALU pipe instead of IMAD.HI (4 cycles of the FMA-heavy pipe per
+// warp) — for the Philox-mode step kernel, whose FMA-heavy pipe carries the generator's IMAD.WIDEs.
+template <bool kAluShift = false>
+G2048_HD u32 hash_rows(u32 w) { return lop3<kA ^ (kB & kC)>(w, kAluShift ? w >> 4 : shr<4>(w), 0x0FFF0FFFu); }
 G2048_HD u32 hash_row16(u32 row) { return (row ^ ((row >> 4) & 0x0FFFu)) & 0xFFFFu; }
 
 // true when some tile is >= 16384 (nibble >= 14): such boards leave the fast path, which keeps
@@ -284,12 +287,12 @@ struct FastOut {
 
 // Afterstate of (lo,hi) under the action whose orientation words are `o`.  Returns the merge
 // score; `moved` is evaluated in the oriented frame (core.py:258).
-template <class Lut>
+template <bool kAluShift = false, class Lut>
 G2048_HD u32 move_fast(u32 lo, u32 hi, const Orient& o, const Lut& lut, u32 one, u32& al, u32& ah,
                        bool& moved) {
     u32 xl = lo, xh = hi;
     orient_forward(xl, xh, o);
-    const u32 yl = hash_rows(xl), yh = hash_rows(xh);
+    const u32 yl = hash_rows<kAluShift>(xl), yh = hash_rows<kAluShift>(xh);
     // byte offsets: one ALU op per lookup for the extraction, the x4 on the FMA pipe (IMAD.SHL;
     // for the high row a run-time multiplier, or ptxas folds shift + base into an ALU-pipe LEA)
     const u32 four = one << 2;
@@ -376,7 +379,7 @@ G2048_HD FastOut transition_fast(u32 lo, u32 hi, const Orient& o, u32 rank, u32 
                                  const Lut& lut, u32 one) {
     u32 al, ah;
     bool moved;
-    const u32 reward = move_fast(lo, hi, o, lut, one, al, ah, moved);
+    const u32 reward = move_fast<kPhilox>(lo, hi, o, lut, one, al, ah, moved);
 
     // ---- spawn on the rank-th empty cell (row-major) of the afterstate ----
     u32 nlo = nz8(al, one), nhi = nz8(ah, one);
@@ -385,7 +388,9 @@ G2048_HD FastOut transition_fast(u32 lo, u32 hi, const Orient& o, u32 rank, u32 
         // digit 1 (base ne) = spawn rank, digit 2 (base 10) == 0 -> tile 4 (exponent 2)
         u32 f1;
         mul_wide(w0, ne, rank, f1);
-        exp_mul = mad(nonzero01(mulhi(f1, 10u)), 0xE0000000u, 0x40000000u);
+        // hi32(f1 * 10) == 0  <=>  f1 < ceil(2^32 / 10): a compare and a select on the ALU pipe
+        // instead of IMAD.HI + VIMNMX + IMAD (6 cycles of the FMA-heavy pipe, this mode's busiest)
+        exp_mul = f1 < 0x1999999Au ? 0x40000000u : 0x20000000u;
     }
     bool in_hi;
     const u32 g = spawn_prefix(nlo, nhi, tiles_lo, rank, one, in_hi);
