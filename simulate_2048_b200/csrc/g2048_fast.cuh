@@ -181,35 +181,39 @@ struct alignas(32) Orient {
     u32 mul_lo;          // 2^k:      t << k as a product (IMAD)
     u32 sel_lo, sel_hi;  // byte permutation (PRMT selectors); every P_a is an involution, so the
                          // same pair serves forwards and backwards
-    u32 pad0, pad1, pad2;
+    u32 shift;           // k itself, for the variant that shifts on the ALU pipe (SHF)
+    u32 pad1, pad2;
 };
 
 // action 0 left, 1 up, 2 right, 3 down.  Derivation of the selectors: tools/derive_orient.py.
 #define G2048_ORIENT_TABLE                                                             \
     {                                                                                  \
         {0x00000000u, 0x00000000u, 0x00000000u, 0x3210u, 0x7654u, 0u, 0u, 0u},         \
-        {0x0000F0F0u, 0x00100000u, 0x00001000u, 0x6240u, 0x7351u, 0u, 0u, 0u},         \
-        {0x0F0F0F0Fu, 0x10000000u, 0x00000010u, 0x2301u, 0x6745u, 0u, 0u, 0u},         \
-        {0x00000F0Fu, 0x00001000u, 0x00100000u, 0x3715u, 0x2604u, 0u, 0u, 0u},         \
+        {0x0000F0F0u, 0x00100000u, 0x00001000u, 0x6240u, 0x7351u, 12u, 0u, 0u},        \
+        {0x0F0F0F0Fu, 0x10000000u, 0x00000010u, 0x2301u, 0x6745u, 4u, 0u, 0u},         \
+        {0x00000F0Fu, 0x00001000u, 0x00100000u, 0x3715u, 0x2604u, 20u, 0u, 0u},        \
     }
 
 // the one conditional nibble stage: delta swap of the nibble pairs selected by the mask, with the
 // shift distance k (12 / 4 / 20 bits) carried by two per-thread multipliers, so that both shifts
 // run on the FMA pipe and the stage is the same instruction sequence for every action
+template <bool kAluShift = false>
 G2048_HD u32 stage(u32 x, const Orient& o) {
-    const u32 t = lop3<(kA ^ kB) & kC>(x, mulhi(x, o.mul_hi), o.mask);
+    const u32 t = lop3<(kA ^ kB) & kC>(x, kAluShift ? x >> o.shift : mulhi(x, o.mul_hi), o.mask);
     return lop3<kA ^ kB ^ kC>(x, t, t * o.mul_lo);
 }
 
+template <bool kAluShift = false>
 G2048_HD void orient_forward(u32& lo, u32& hi, const Orient& o) {
-    const u32 l = stage(lo, o), h = stage(hi, o);
+    const u32 l = stage<kAluShift>(lo, o), h = stage<kAluShift>(hi, o);
     lo = prmt(l, h, o.sel_lo);
     hi = prmt(l, h, o.sel_hi);
 }
+template <bool kAluShift = false>
 G2048_HD void orient_backward(u32& lo, u32& hi, const Orient& o) {
     const u32 l = prmt(lo, hi, o.sel_lo), h = prmt(lo, hi, o.sel_hi);
-    lo = stage(l, o);
-    hi = stage(h, o);
+    lo = stage<kAluShift>(l, o);
+    hi = stage<kAluShift>(h, o);
 }
 
 // bit 3 of every nibble = (nibble != 0); all other bits 0
@@ -291,7 +295,7 @@ template <bool kAluShift = false, class Lut>
 G2048_HD u32 move_fast(u32 lo, u32 hi, const Orient& o, const Lut& lut, u32 one, u32& al, u32& ah,
                        bool& moved) {
     u32 xl = lo, xh = hi;
-    orient_forward(xl, xh, o);
+    orient_forward<kAluShift>(xl, xh, o);
     const u32 yl = hash_rows<kAluShift>(xl), yh = hash_rows<kAluShift>(xh);
     // byte offsets: one ALU op per lookup for the extraction, the x4 on the FMA pipe (IMAD.SHL;
     // for the high row a run-time multiplier, or ptxas folds shift + base into an ALU-pipe LEA)
@@ -302,7 +306,7 @@ G2048_HD u32 move_fast(u32 lo, u32 hi, const Orient& o, const Lut& lut, u32 one,
     ah = prmt(e2, e3, 0x7632);
     moved = (al != xl) | (ah != xh);
     const u32 reward = shr<14>(add(add(e0, e1, one), add(e2, e3, one), one) << 16);  // (sum & 0xFFFF) * 4
-    orient_backward(al, ah, o);
+    orient_backward<kAluShift>(al, ah, o);
     return reward;
 }
 

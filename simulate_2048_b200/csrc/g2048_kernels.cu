@@ -441,7 +441,12 @@ __device__ __forceinline__ void step_tile4(const Boards4& in, u32 actions, u32 s
         const uint4 o0 = *reinterpret_cast<const uint4*>(op);
         fast::Orient o;
         o.mask = o0.x; o.mul_hi = o0.y; o.mul_lo = o0.z; o.sel_lo = o0.w;
-        o.sel_hi = *reinterpret_cast<const u32*>(op + 16);
+        if (kPhilox) {   // + the shift distance itself: this mode shifts on the ALU pipe
+            const uint2 o1 = *reinterpret_cast<const uint2*>(op + 16);
+            o.sel_hi = o1.x; o.shift = o1.y;
+        } else {
+            o.sel_hi = *reinterpret_cast<const u32*>(op + 16);
+        }
         u32 rank = 0, exp_mul = 0, w0 = 0;  // exp_mul = exponent << 29 (Philox: drawn inside)
         if (kPhilox) {
             w0 = pw[k];
