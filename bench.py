@@ -432,8 +432,8 @@ def run_ours(args):
     achieved = BYTES_INJECTED * B / mean_launch / 1e9
     traffic = args.ncu_traffic
     if traffic is None:
-        try:  # dram bytes per env measured by `ncu --set full` (profiles/r01_traffic.json)
-            with open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')) as f:
+        try:  # dram bytes per env measured by `ncu --set full` (profiles/r02_traffic.json)
+            with open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')) as f:
                 traffic = json.load(f)['dram_bytes_per_env'] * B
         except Exception:
             traffic = None
@@ -512,7 +512,7 @@ def run_ours(args):
                      'mean_launch_ms': mean_launch * 1e3,
                      'best_launch_ms': best_launch * 1e3,
                      'algorithmic_bytes_per_launch': BYTES_INJECTED * B,
-                     'traffic_source': 'stored: ncu --set full DRAM bytes per env (profiles/r01_traffic.json) x envs; '
+                     'traffic_source': 'stored: ncu --set full DRAM bytes per env (profiles/r02_traffic.json) x envs; '
                                        'not measured in this run',
                      'other_kernels': {'philox_step': philox, 'rollout_sharded': rollout}},
         'clocks': clocks.summary(),
