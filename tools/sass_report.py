@@ -11,7 +11,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, 'simulate_2048_b200', 'libg2048.so')
 ALU = {'LOP3', 'SHF', 'PRMT', 'ISETP', 'SEL', 'LEA', 'IADD3', 'VIADD', 'PLOP3', 'VIMNMX', 'MOV', 'CS2R', 'P2R', 'R2P', 'VOTE'}
-WANT = ['step_lut_kernelILb0ELi640ELi1', 'step_lut_kernelILb1ELi512ELi1', 'rollout_kernelILb1ELb1ELb0ELi768',
+WANT = ['step_lut_kernelILb0ELi640ELi1', 'step_lut_kernelILb1ELi640ELi1', 'rollout_kernelILb1ELb1ELb0ELi640',
         'expand_quad_kernelILi2ELb1', 'expand_children_kernelILi2', 'expand_moves_smem_kernel', 'selfplay_step_kernelILb1',
         'env_step_kernelILb1', 'rollout_stats_kernel']
 txt = subprocess.run(['cuobjdump', '-sass', lib], capture_output=True, text=True).stdout
