@@ -2339,7 +2339,7 @@ __device__ __noinline__ uint4 rollout_move_slow(u32 lo, u32 hi, u32 action) {
 }
 
 // Every lane plays kRollSlots games at once, one step of each per loop iteration: the two
-// dependent chains interleave (ILP 2 with 6 warps per scheduler instead of ILP 1 with 8).
+// dependent chains interleave (ILP 2 with 5 warps per scheduler instead of ILP 1 with 8).
 //
 // Random numbers: a game draws from its env's own GAME stream (include/g2048.h "Game stream"):
 // word p of the stream is word p & 3 of block p >> 2, so ONE Philox4x32-10 block feeds four
