@@ -241,7 +241,7 @@ int g2048_expand_children(const uint64_t* after, const uint8_t* child_count,
 /*
  * g2048_expand with the compact children layout as ONE call without a host round trip: the
  * per-board child totals are scanned on the device (n < 2^17: a single kernel launch, tiles
- * chained by ticket + aggregate look-back; larger batches: moves, a three-kernel scan, children).
+ * chained by ticket + aggregate look-back; larger batches: moves with per-group totals, one prefix kernel, children that derive the offsets).
  *   child_offsets[n] is an OUTPUT (exclusive prefix sum of the per-board totals, what a caller of
  *   g2048_expand computes on the host side); children has room for `capacity` boards (> 0): a
  *   board whose children would run past it writes none; total_out[2] (device, optional) receives

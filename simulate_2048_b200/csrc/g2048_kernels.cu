@@ -1368,6 +1368,11 @@ struct ExpandArgs {
     int64_t* offsets_out;  // g2048_expand_compact: the offsets are an OUTPUT (device-side scan)
     size_t capacity;       // children buffer capacity in boards (0 = unlimited): a board whose
                            // children would run past it writes none
+    // large-batch g2048_expand_compact: the moves kernel writes the child total of every group of
+    // 32 boards, scan_top_kernel turns them into the exclusive prefix of every tile of 1024 boards,
+    // and the children kernel derives each board's offset from the two (see scan_top_kernel)
+    u32* group_sums;
+    const unsigned long long* tile_prefix;
 };
 
 __device__ __forceinline__ u32 empty_cells16(Board b) {
@@ -1480,15 +1485,33 @@ __device__ __forceinline__ void expand_moves_board(const ExpandArgs& a, size_t i
     expand_moves_store(a, i, expand_moves_compute(a, a.boards[i], lut));
 }
 
-// persistent, hashed table staged in shared memory
+__device__ __forceinline__ u32 sum_bytes4(u32 x) { return (x * 0x01010101u) >> 24; }  // four counts <= 30
+
+// persistent, hashed table staged in shared memory.  A warp takes 32 consecutive boards per trip;
+// with `group_sums` it also writes their child total (the first level of the device-side scan of
+// g2048_expand_compact: five shuffles here replace a kernel that re-read every child count).
 __global__ void __launch_bounds__(1024, 1) expand_moves_smem_kernel(const ExpandArgs a) {
     u32* smem_tab = smem_words;
     u64* bar = reinterpret_cast<u64*>(smem_words + kSmemRows);
     table_stage_begin(smem_tab, bar, a.table_hashed);
     table_stage_wait(bar);
     const SmemLut lut{};
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < a.n; i += (size_t)gridDim.x * blockDim.x)
-        expand_moves_board(a, i, lut);
+    const u32 lane = threadIdx.x & 31u;
+    for (size_t base = blockIdx.x * (size_t)blockDim.x + threadIdx.x - lane; base < a.n;
+         base += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = base + lane;
+        u32 tot = 0u;
+        if (i < a.n) {
+            const MovesOut r = expand_moves_compute(a, a.boards[i], lut);
+            expand_moves_store(a, i, r);
+            tot = sum_bytes4(r.cc4);
+        }
+        if (a.group_sums) {  // kernel argument: warp-uniform
+#pragma unroll
+            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
+            if (lane == 0u) a.group_sums[base >> 5] = tot;
+        }
+    }
 }
 
 // small batches: the same table gathered from L2
@@ -1598,16 +1621,18 @@ __global__ void __launch_bounds__(kChildWarps * 32) expand_children_kernel(const
     const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const size_t warp = (blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5;
     const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
-    // the records of the NEXT tile are fetched into registers while the current one is expanded
+    // The records of the NEXT tile are loaded into registers while the current one is expanded;
+    // whatever consumes the loaded values (the offset scan, the capacity test) runs one trip later,
+    // when they have arrived.
     struct TileRegs {
         uint4 s01, s23;
-        u32 cc4;
+        u32 cc4, gsum;
         unsigned long long off;
     };
-    auto fetch = [&](size_t tile_base) {
+    auto load = [&](size_t tile_base) {
         TileRegs r;
         r.s01 = r.s23 = make_uint4(0u, 0u, 0u, 0u);
-        r.cc4 = 0u;
+        r.cc4 = r.gsum = 0u;
         r.off = 0ull;
         const size_t mine = tile_base + lane;
         if (mine < a.n) {
@@ -1615,18 +1640,41 @@ __global__ void __launch_bounds__(kChildWarps * 32) expand_children_kernel(const
             const uint4* src = reinterpret_cast<const uint4*>(a.after + mine * 4);
             r.s01 = src[0];
             r.s23 = src[1];
-            r.off = (kLayout == G2048_CHILDREN_COMPACT) ? (unsigned long long)a.child_offsets[mine]
-                                                        : (unsigned long long)mine * 128ull;
-            if (kLayout == G2048_CHILDREN_COMPACT && a.capacity != 0 &&
-                r.off + ((r.cc4 * 0x01010101u) >> 24) > a.capacity)
-                r.cc4 = 0u;  // does not fit: nothing is written for this board
+            if (kLayout != G2048_CHILDREN_COMPACT) r.off = (unsigned long long)mine * 128ull;
+            else if (!a.tile_prefix) r.off = (unsigned long long)a.child_offsets[mine];
+        }
+        if (kLayout == G2048_CHILDREN_COMPACT && a.tile_prefix && tile_base < a.n) {
+            // device-side offsets: prefix of my tile of 1024 boards + the groups of 32 boards in
+            // front of mine inside it (one coalesced load, lane = group) + a scan over my 32 boards
+            const size_t g = tile_base >> 5;
+            r.off = a.tile_prefix[g >> 5];
+            if (lane < (u32)(g & 31u)) r.gsum = a.group_sums[(g & ~(size_t)31) + lane];
         }
         return r;
     };
-    TileRegs cur = fetch(warp * 32);
+    auto finish = [&](TileRegs& r, size_t tile_base) {
+        if (kLayout != G2048_CHILDREN_COMPACT) return;
+        const u32 tot = sum_bytes4(r.cc4);
+        if (a.tile_prefix) {
+            const u32 FULL = 0xFFFFFFFFu;
+            u32 gp = r.gsum, inc = tot;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) gp += __shfl_xor_sync(FULL, gp, o);
+#pragma unroll
+            for (u32 d = 1; d < 32u; d <<= 1) {
+                const u32 v = __shfl_up_sync(FULL, inc, d);
+                if (lane >= d) inc += v;
+            }
+            r.off += (unsigned long long)gp + (inc - tot);
+            if (a.offsets_out && tile_base + lane < a.n) a.offsets_out[tile_base + lane] = (int64_t)r.off;
+        }
+        if (a.capacity != 0 && r.off + tot > a.capacity) r.cc4 = 0u;  // does not fit: nothing is written for this board
+    };
+    TileRegs cur = load(warp * 32);
     for (size_t tile = warp * 32; tile < a.n; tile += n_warps * 32) {
+        finish(cur, tile);
         expand_record(s_tile[w], lane, cur.s01, cur.s23, cur.cc4, cur.off);
-        cur = fetch(tile + n_warps * 32);  // in flight during the expansion below
+        cur = load(tile + n_warps * 32);  // in flight during the expansion below
         __syncwarp();
         expand_children_tile<kLayout>(a, s_tile[w], (u32)min((size_t)32, a.n - tile), lane);
         __syncwarp();
@@ -1659,8 +1707,6 @@ static int launch_expand_children(const ExpandArgs& a, const DeviceState* s, cud
 // ---------------------------------------------------------------------------------------------
 constexpr unsigned long long kAggValid = 1ull << 63;
 constexpr unsigned long long kGroupArrival = 1ull << 48;  // group word: arrivals << 48 | sum of the child totals
-
-__device__ __forceinline__ u32 sum_bytes4(u32 x) { return (x * 0x01010101u) >> 24; }  // four counts <= 30
 
 // The aggregate and its valid bit travel in ONE 64-bit word, so relaxed accesses are enough: a
 // release store would first wait for the CTA's earlier output stores to become visible, and an
@@ -1821,10 +1867,8 @@ __global__ void __launch_bounds__(kQuadWarps * 32) expand_quad_kernel(const Expa
     }
 }
 
-// Large batches: moves kernel (writes child_count), then a three-kernel scan of the per-board
-// totals (tile sums, scan of the tile sums by one CTA, per-tile apply), then the children kernel.
-constexpr int kScanThreads = 256, kScanPerThread = 4, kScanTileBoards = kScanThreads * kScanPerThread;
-
+// Large batches: moves kernel (writes child_count and the child total of every group of 32 boards),
+// scan_top_kernel (prefix of every tile of 1024 boards), children kernel (derives the offsets).
 // exclusive scan of one value per thread over the CTA; returns the CTA total through `total`
 template <int kThreads>
 __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long long v, unsigned long long* s_warp,
@@ -1848,63 +1892,41 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
     return warp_off + inc - v;
 }
 
-__device__ __forceinline__ uint4 load_counts4(const uint8_t* child_count, size_t board, size_t n) {
-    // child counts of boards board .. board + 3 (4 bytes each), zero past the end
-    if (board + 4 <= n) return *reinterpret_cast<const uint4*>(child_count + board * 4);
-    uint4 r = make_uint4(0u, 0u, 0u, 0u);
-    const u32* c = reinterpret_cast<const u32*>(child_count);
-    if (board < n) r.x = c[board];
-    if (board + 1 < n) r.y = c[board + 1];
-    if (board + 2 < n) r.z = c[board + 2];
-    return r;
-}
-
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(const uint8_t* __restrict__ child_count,
-                                                                      unsigned long long* __restrict__ tile_sums,
-                                                                      size_t n, size_t tiles) {
-    __shared__ unsigned long long s_warp[kScanThreads / 32];
-    for (size_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const uint4 c = load_counts4(child_count, t * kScanTileBoards + threadIdx.x * kScanPerThread, n);
-        unsigned long long total;
-        block_exclusive_scan<kScanThreads>(sum_bytes4(c.x) + sum_bytes4(c.y) + sum_bytes4(c.z) + sum_bytes4(c.w),
-                                           s_warp, total);
-        if (threadIdx.x == 0) tile_sums[t] = total;
-    }
-}
-
-// one CTA: exclusive scan of the tile sums in place, chunk by chunk with a running carry
-__global__ void __launch_bounds__(1024) scan_top_kernel(unsigned long long* __restrict__ tile_sums, size_t tiles,
+// One CTA: the exclusive prefix of every tile of 1024 boards from the group sums the moves kernel
+// wrote (32 groups of 32 boards per tile, 128 bytes per thread), chunk by chunk with a running
+// carry — 128 KiB of input per million boards.  The children kernel adds the groups in front of a
+// warp's own group and a warp scan over its 32 boards, so no per-board pass is left between the
+// moves and the children (round 2 started with three scan kernels — tile sums, top, apply —
+// and a second and third read of the child counts: 40 -> 32 us at 2^17 boards, 150 -> 145 us at 2^20).
+__global__ void __launch_bounds__(1024) scan_top_kernel(const u32* __restrict__ group_sums, size_t groups,
+                                                        unsigned long long* __restrict__ tile_prefix, size_t tiles,
                                                         size_t capacity, unsigned long long* __restrict__ total_out) {
     __shared__ unsigned long long s_warp[32];
     unsigned long long carry = 0ull;
     for (size_t base = 0; base < tiles; base += 1024) {
         const size_t j = base + threadIdx.x;
-        const unsigned long long v = j < tiles ? tile_sums[j] : 0ull;
+        unsigned long long v = 0ull;
+        if (j < tiles) {
+            const size_t g0 = j * 32;
+            if (g0 + 32 <= groups) {
+                const uint4* p = reinterpret_cast<const uint4*>(group_sums + g0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint4 q = p[k];
+                    v += (unsigned long long)q.x + q.y + q.z + q.w;
+                }
+            } else {
+                for (size_t g = g0; g < groups; ++g) v += group_sums[g];
+            }
+        }
         unsigned long long total;
         const unsigned long long ex = block_exclusive_scan<1024>(v, s_warp, total);
-        if (j < tiles) tile_sums[j] = carry + ex;
+        if (j < tiles) tile_prefix[j] = carry + ex;
         carry += total;
     }
     if (threadIdx.x == 0 && total_out) {
         total_out[0] = carry;
         total_out[1] = (capacity != 0 && carry > capacity) ? 1ull : 0ull;
-    }
-}
-
-__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint8_t* __restrict__ child_count,
-                                                                  const unsigned long long* __restrict__ tile_prefix,
-                                                                  int64_t* __restrict__ offsets, size_t n, size_t tiles) {
-    __shared__ unsigned long long s_warp[kScanThreads / 32];
-    for (size_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-        const size_t board = t * kScanTileBoards + threadIdx.x * kScanPerThread;
-        const uint4 c = load_counts4(child_count, board, n);
-        const u32 t0 = sum_bytes4(c.x), t1 = sum_bytes4(c.y), t2 = sum_bytes4(c.z), t3 = sum_bytes4(c.w);
-        unsigned long long total;
-        const unsigned long long ex = tile_prefix[t] + block_exclusive_scan<kScanThreads>(t0 + t1 + t2 + t3, s_warp, total);
-        if (board < n) offsets[board] = (int64_t)ex;
-        if (board + 1 < n) offsets[board + 1] = (int64_t)(ex + t0);
-        if (board + 2 < n) offsets[board + 2] = (int64_t)(ex + t0 + t1);
-        if (board + 3 < n) offsets[board + 3] = (int64_t)(ex + t0 + t1 + t2);
     }
 }
 
@@ -2026,27 +2048,26 @@ extern "C" int g2048_expand_compact(const uint64_t* boards, uint64_t* after, int
         if (rc == G2048_OK && fe != cudaSuccess) return cuda_fail(fe, "cudaFreeAsync(scratch)");
         return rc;
     }
-    // large batch: moves -> scan of the child totals -> children
-    const size_t tiles = (n + kScanTileBoards - 1) / kScanTileBoards;
-    unsigned char* scratch = nullptr;  // [tile sums | afterstates | child counts] as needed
-    const size_t sums_bytes = (tiles * 8 + 15) / 16 * 16;
-    const size_t need = sums_bytes + (after ? 0 : n * 32) + (child_count ? 0 : n * 4);
+    // large batch: moves (+ group sums) -> prefix of the tiles -> children (+ offsets)
+    const size_t groups = (n + 31) / 32, tiles = (groups + 31) / 32;
+    unsigned char* scratch = nullptr;  // [tile prefix | group sums | afterstates | child counts] as needed
+    const size_t prefix_bytes = (tiles * 8 + 15) / 16 * 16, sums_bytes = (groups * 4 + 15) / 16 * 16;
+    const size_t need = prefix_bytes + sums_bytes + (after ? 0 : n * 32) + (child_count ? 0 : n * 4);
     CU(cudaMallocFromPoolAsync(&scratch, need, s->pool, st));
     auto launch = [&]() -> int {
-        unsigned long long* sums = reinterpret_cast<unsigned long long*>(scratch);
-        u64* after_buf = after ? reinterpret_cast<u64*>(after) : reinterpret_cast<u64*>(scratch + sums_bytes);
-        uint8_t* count_buf = child_count ? child_count : scratch + sums_bytes + (after ? 0 : n * 32);
+        unsigned long long* prefix = reinterpret_cast<unsigned long long*>(scratch);
+        u32* sums = reinterpret_cast<u32*>(scratch + prefix_bytes);
+        unsigned char* p = scratch + prefix_bytes + sums_bytes;
+        u64* after_buf = after ? reinterpret_cast<u64*>(after) : reinterpret_cast<u64*>(p);
+        uint8_t* count_buf = child_count ? child_count : p + (after ? 0 : n * 32);
         ExpandArgs a{reinterpret_cast<const u64*>(boards), after_buf, rewards, mask, num_empty, count_buf,
-                     reinterpret_cast<u64*>(children), child_offsets, G2048_CHILDREN_COMPACT, n, s->table,
-                     s->table_hashed, 1u, child_offsets, capacity};
+                     reinterpret_cast<u64*>(children), nullptr, G2048_CHILDREN_COMPACT, n, s->table,
+                     s->table_hashed, 1u, child_offsets, capacity, sums, prefix};
         CU(cudaFuncSetAttribute(expand_moves_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(kSmemTableBytes + 64u)));
         expand_moves_smem_kernel<<<s->sms, 1024, kSmemTableBytes + 64u, st>>>(a);
         CU(cudaGetLastError());
-        const int sgrid = (int)(tiles < (size_t)s->sms * 8 ? tiles : (size_t)s->sms * 8);
-        scan_tile_sums_kernel<<<sgrid, kScanThreads, 0, st>>>(count_buf, sums, n, tiles);
-        scan_top_kernel<<<1, 1024, 0, st>>>(sums, tiles, capacity, tot);
-        scan_apply_kernel<<<sgrid, kScanThreads, 0, st>>>(count_buf, sums, child_offsets, n, tiles);
+        scan_top_kernel<<<1, 1024, 0, st>>>(sums, groups, prefix, tiles, capacity, tot);
         CU(cudaGetLastError());
         return launch_expand_children(a, s, st);
     };

@@ -119,10 +119,10 @@ def test_expand_odd_child_offsets(T, ops):
     np.testing.assert_array_equal(host(shifted.children[1:]), host(ex.children))
 
 
-@pytest.mark.parametrize('n', [1, 127, 129, 40000, (1 << 17) + 1025])
+@pytest.mark.parametrize('n', [1, 127, 129, 40000, (1 << 17) + 1025, (1 << 19) + 33 * 1024 + 7])
 def test_expand_compact_device_scan(T, ops, oracle, n):
     """g2048_expand_compact: offsets scanned on the device (single-launch look-back below 2^17
-    boards, three-kernel scan above), no host round trip; buffers of an earlier call are reused
+    boards; group sums from the moves kernel + tile prefixes above), no host round trip; buffers of an earlier call are reused
     with DIFFERENT boards (the offsets are recomputed, never stale); a capacity that is too small
     raises the overflow flag and never writes past the buffer."""
     b1 = synthetic_packed(n, seed=3 * n + 1)
