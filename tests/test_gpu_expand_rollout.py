@@ -334,3 +334,30 @@ def test_rollout_persistent_kernel_variants(T, ops, oracle):
     np.testing.assert_array_equal(tr.trace.cpu().numpy(), wt['trace'])
     np.testing.assert_array_equal(tr.steps.cpu().numpy(), wt['steps'])
     np.testing.assert_array_equal(tr.stats.cpu().numpy().view(np.uint64), wt['stats'])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('threads', [512, 768])
+def test_rollout_other_cta_sizes(threads):
+    """The 512- and 768-thread instantiations of the persistent rollout kernel (the library picks
+    640; G2048_ROLL_THREADS selects the others for measurements) give the oracle's episodes too.
+    The knob is read when the library loads, so the check runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        'import sys; sys.path.insert(0, ".")\n'
+        'import numpy as np, torch\n'
+        'from oracle import c_oracle\n'
+        'from simulate_2048_b200 import ops\n'
+        'n = 148 * 768 + 13\n'
+        'out = ops.rollout(n, seed=77, env_offset=3)\n'
+        'want = c_oracle.rollout(n, seed=77, env_offset=3)\n'
+        'assert (out.boards.cpu().numpy().view(np.uint64) == want["boards"]).all()\n'
+        'assert (out.score.cpu().numpy() == want["score"]).all() and (out.steps.cpu().numpy() == want["steps"]).all()\n'
+        'assert (out.stats.cpu().numpy().view(np.uint64) == want["stats"]).all()\n'
+        'print("ok")\n')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, G2048_ROLL_THREADS=str(threads))
+    r = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith('ok'), r.stderr[-2000:]
