@@ -361,3 +361,33 @@ def test_rollout_other_cta_sizes(threads):
     env = dict(os.environ, G2048_ROLL_THREADS=str(threads))
     r = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and r.stdout.strip().endswith('ok'), r.stderr[-2000:]
+
+
+@pytest.mark.parametrize('n', [3000, 148 * 640 + 41])
+def test_rollout_big_tiles_leave_and_rejoin_the_fast_path(T, ops, oracle, n):
+    """Rollouts from boards that hold, or are about to build, tiles >= 16384: such a board's rows lie
+    outside the staged table window, so its moves take the exact out-of-line path.  The kernel does
+    not test the board every step: a game carries the OR of its move scores (>= 16384 iff a tile
+    >= 16384 may have been built) and the out-of-line path re-evaluates the board exactly.  Covered:
+    boards that start with 16384 / 32768 tiles (incl. 32768 pairs that overflow), boards of 4096 /
+    8192 tiles that cross the threshold mid-game, both kernel variants (table gathered from L2 /
+    staged in shared memory)."""
+    rng = np.random.default_rng(n)
+    start = synthetic_packed(n, seed=n, max_exp=15)                       # anything up to 32768
+    dense = rng.integers(12, 14, (n // 3, 16)).astype(np.uint64)          # full boards of 4096 / 8192: merge chains
+    dense[rng.random(dense.shape) < 0.15] = 0
+    start[: n // 3] = np.bitwise_or.reduce(dense << (4 * np.arange(16, dtype=np.uint64))[None, :], axis=1)
+    pairs = rng.integers(14, 16, (n // 8, 16)).astype(np.uint64)          # 16384 / 32768 everywhere: overflows
+    start[n // 3: n // 3 + n // 8] = np.bitwise_or.reduce(pairs << (4 * np.arange(16, dtype=np.uint64))[None, :], axis=1)
+    got = ops.rollout(n, seed=31, env_offset=9, boards=dev(T, start), max_steps=500)
+    want = oracle.rollout(n, seed=31, env_offset=9, from_reset=False, boards=start, max_steps=500)
+    np.testing.assert_array_equal(host(got.boards), want['boards'])
+    np.testing.assert_array_equal(got.score.cpu().numpy(), want['score'])
+    np.testing.assert_array_equal(got.steps.cpu().numpy(), want['steps'])
+    np.testing.assert_array_equal(got.maxexp.cpu().numpy(), want['maxexp'])
+    np.testing.assert_array_equal(got.stats.cpu().numpy().view(np.uint64), want['stats'])
+    st = want['stats']
+    assert st[6] > 0 and st[8 + 15] > 0          # some games overflowed, some ended holding a 32768
+    # the threshold is crossed mid-game: games that started below 16384 and ended with one
+    began_small = oracle.unpack(start).reshape(n, -1).max(axis=1) < 16384
+    assert (began_small & (want['maxexp'] >= 14)).sum() > 0
