@@ -134,6 +134,60 @@ def test_game_stream_layout_v3(oracle):
         assert empties[rank] == (byte >> 2) & 0xF and bool(four) == bool(byte & 0x40)
 
 
+def test_rollout_oracle_against_an_independent_replay(oracle):
+    """orc_rollout (the C oracle the GPU rollouts are compared with) replayed WITHOUT any C code: the
+    NumPy restatement of the reference engine for the transitions, the big-int Philox above for the
+    game stream, the mixed-radix digits and the k-th-legal-action policy in plain Python — whole
+    games from reset (words 0, 1 = reset tiles, word step + 2 per step) and from given boards (first
+    action from the quad-layout word of tag 3, word step per step, a step cap)."""
+    from oracle import np_engine as ne
+
+    def word(key, env, p):
+        return _philox_py([env & 0xFFFFFFFF, env >> 32, p >> 2, 6], [key & 0xFFFFFFFF, key >> 32])[p & 3]
+
+    def spawn(board, w):
+        free = np.flatnonzero(board.reshape(-1) == 0)
+        p1 = w * len(free)
+        p2 = (p1 & 0xFFFFFFFF) * 10
+        out = board.reshape(-1).copy()
+        out[free[p1 >> 32]] = 4 if (p2 >> 32) == 0 else 2
+        return out.reshape(4, 4), p2 & 0xFFFFFFFF
+
+    def play(board, rem, key, env, first_word, cap):
+        score = steps = 0
+        while steps < cap:
+            legal = ne.legal_actions(board)
+            if not legal:
+                break
+            action = legal[(rem * len(legal)) >> 32]
+            after, reward = ne.latent_state(board, action)
+            board, rem = spawn(np.asarray(after), word(key, env, first_word + steps))
+            score += int(reward)
+            steps += 1
+        return board, score, steps
+
+    key, off = 0x1234567890ABCDEF, 10**12 + 5
+    want = oracle.rollout(6, seed=key, env_offset=off)
+    for i in range(6):
+        env = off + i
+        b = np.zeros((4, 4), dtype=np.int64)
+        b, _ = spawn(b, word(key, env, 0))
+        b, rem = spawn(b, word(key, env, 1))
+        b, score, steps = play(b, rem, key, env, 2, 1 << 20)
+        assert steps == want['steps'][i] and score == want['score'][i]
+        assert int(oracle.pack(b.reshape(1, 16).astype(np.int32))[0][0]) == int(want['boards'][i])
+    start = oracle.reset(6, seed=3)
+    want = oracle.rollout(6, seed=key, env_offset=off, from_reset=False, boards=start, max_steps=40)
+    for i in range(6):
+        env = off + i
+        q = env >> 2
+        rem = _philox_py([q & 0xFFFFFFFF, q >> 32, 0, 3], [key & 0xFFFFFFFF, key >> 32])[env & 3]
+        b = oracle.unpack(start[i:i + 1]).reshape(4, 4).astype(np.int64)
+        b, score, steps = play(b, rem, key, env, 0, 40)
+        assert steps == want['steps'][i] and score == want['score'][i]
+        assert int(oracle.pack(b.reshape(1, 16).astype(np.int32))[0][0]) == int(want['boards'][i])
+
+
 def test_philox_digits_are_uniform(oracle):
     """Digit 2 (p = 0.1) and digit 3 are independent of digit 1: chi-square-free sanity bounds."""
     n = 200_000
