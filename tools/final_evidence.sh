@@ -1,3 +1,6 @@
+#!/bin/bash
+# tools/final_evidence.sh — the one-GPU evidence run of a round (under gpurun): GPU tests, smoke, both bench
+# arms, the ncu launch list and one full capture of the step kernel, both soak scripts.  Outputs in gpurun_out/r3_*.
 set -u
 O=gpurun_out
 python -m pytest tests -x -q -m gpu > $O/r3_tF.log 2>&1; echo "pytest rc=$?" >> $O/r3_tF.log; tail -3 $O/r3_tF.log

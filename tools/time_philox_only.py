@@ -1,3 +1,4 @@
+"""Philox-mode g2048_step on 2^26 boards at 512 / 640 / 768 threads per CTA (CUDA events, 20 launches)."""
 import sys
 import numpy as np
 import torch
